@@ -1,0 +1,135 @@
+"""oracle/oraclelib.py -- TEST INFRASTRUCTURE: ctypes binding of oracle/libpm_oracle.so (the CPU restatement).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpm_oracle.so")
+
+RECORD_DTYPE = np.dtype([("type", "<i4"), ("id", "<i4"), ("index", "<i4"), ("kind", "<i4"),
+                         ("loc", "<f4", 3), ("dir", "<f4", 3), ("energy", "<f4", 3)])
+
+
+class Scene(C.Structure):
+    """Mirror of pm_scene (include/pmb200_types.h)."""
+    _fields_ = [("n_spheres", C.c_int32), ("n_planes", C.c_int32),
+                ("spheres", (C.c_float * 4) * 3), ("planes", (C.c_float * 2) * 5),
+                ("light", C.c_float * 3), ("sz_img", C.c_int32),
+                ("cam_ox", C.c_float), ("cam_oy", C.c_float), ("animate", C.c_int32)]
+
+    def copy(self):
+        s = Scene()
+        C.memmove(C.byref(s), C.byref(self), C.sizeof(Scene))
+        return s
+
+    def spheres_np(self):
+        return np.array([[self.spheres[i][j] for j in range(4)] for i in range(3)], np.float32)
+
+    def planes_np(self):
+        return np.array([[self.planes[i][j] for j in range(2)] for i in range(5)], np.float32)
+
+
+def available():
+    return os.path.exists(LIB_PATH)
+
+
+def _p(a, t=C.c_void_p):
+    return a.ctypes.data_as(t) if a is not None else None
+
+
+class Oracle:
+    def __init__(self):
+        self.lib = L = C.CDLL(LIB_PATH)
+        L.pmo_mwc_next.restype = C.c_uint32
+        L.pmo_rand_float.restype = C.c_float
+        L.pmo_rand_float.argtypes = [C.c_void_p, C.c_void_p, C.c_float]
+        L.pmo_mwc_table.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.pmo_position_objects.argtypes = [C.POINTER(Scene), C.c_float]
+        L.pmo_emit.restype = C.c_long
+        L.pmo_emit.argtypes = [C.POINTER(Scene), C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long]
+        L.pmo_render.argtypes = [C.POINTER(Scene), C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                 C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.pmo_raytrace.restype = C.c_int
+
+    # -- scene -----------------------------------------------------------------------------------
+    def default_scene(self, sz_img=512, animate=1):
+        s = Scene()
+        self.lib.pmo_scene_default(C.byref(s))
+        s.sz_img = sz_img
+        s.animate = animate
+        return s
+
+    def position_objects(self, scene, t):
+        s = scene.copy()
+        self.lib.pmo_position_objects(C.byref(s), C.c_float(t))
+        return s
+
+    # -- RNG --------------------------------------------------------------------------------------
+    def mwc_table(self, n, w=6548, z=316):
+        """Returns (table[n,3], (w,z) state after the 3n draws)."""
+        st = np.array([w, z], np.uint32)
+        tab = np.zeros((n, 3), np.float32)
+        self.lib.pmo_mwc_table(C.c_void_p(st.ctypes.data), C.c_void_p(st.ctypes.data + 4), _p(tab), n)
+        return tab, (int(st[0]), int(st[1]))
+
+    def mwc_draws(self, n, w=6548, z=316):
+        st = np.array([w, z], np.uint32)
+        out = np.zeros(n, np.uint32)
+        for i in range(n):
+            out[i] = self.lib.pmo_mwc_next(C.c_void_p(st.ctypes.data), C.c_void_p(st.ctypes.data + 4))
+        return out, (int(st[0]), int(st[1]))
+
+    # -- stage 1 -----------------------------------------------------------------------------------
+    def emit(self, scene, table, n0, n1, t=0.0, media=False, rng=(6548, 316), grid=None, max_records=0,
+             want_grid=True):
+        """Returns (grid, records, rng_state_after).  grid is accumulated into (not cleared) if given."""
+        table = np.ascontiguousarray(table, np.float32)
+        st = np.array(rng, np.uint32)
+        if grid is None and want_grid:
+            grid = np.zeros((32, 32, 32, 3), np.float32)
+        rec = np.zeros(max_records, RECORD_DTYPE) if max_records else None
+        cnt = self.lib.pmo_emit(C.byref(scene), t, _p(table), n0, n1, int(media),
+                                C.c_void_p(st.ctypes.data), C.c_void_p(st.ctypes.data + 4),
+                                _p(grid) if want_grid else None, _p(rec), max_records)
+        if rec is not None:
+            assert cnt <= max_records, (cnt, max_records)
+            rec = rec[:cnt]
+        return grid, rec, (int(st[0]), int(st[1]))
+
+    # -- stages 3-5 --------------------------------------------------------------------------------
+    def render(self, scene, grid, w, h, t=0.0, interp=False, media=False, y0=0, y1=None, want_u8=True):
+        grid = np.ascontiguousarray(grid, np.float32)
+        y1 = h if y1 is None else y1
+        rgb = np.zeros((h, w, 3), np.float32)
+        u8 = np.zeros((h, w, 4), np.uint8) if want_u8 else None
+        self.lib.pmo_render(C.byref(scene), t, _p(grid), w, h, y0, y1, int(interp), int(media), _p(rgb), _p(u8))
+        return rgb, u8
+
+    # -- probes --------------------------------------------------------------------------------------
+    def voxel(self, p):
+        p = np.asarray(p, np.float32); v = np.zeros(3, np.int32)
+        self.lib.pmo_voxel(_p(p), _p(v))
+        return v
+
+    def raytrace(self, scene, ray, org):
+        ray = np.asarray(ray, np.float32); org = np.asarray(org, np.float32)
+        d = C.c_float(0); ty = C.c_int(0); ix = C.c_int(0)
+        hit = self.lib.pmo_raytrace(C.byref(scene), _p(ray), _p(org), C.byref(d), C.byref(ty), C.byref(ix))
+        return bool(hit), d.value, ty.value, ix.value
+
+    def integrate_volume(self, grid, p):
+        grid = np.ascontiguousarray(grid, np.float32)
+        p = np.asarray(p, np.float32); c = np.zeros(3, np.float32)
+        self.lib.pmo_integrate_volume(_p(grid), _p(p), _p(c))
+        return c
+
+    def gather(self, grid, p, type_, id_, interp=False):
+        grid = np.ascontiguousarray(grid, np.float32)
+        p = np.asarray(p, np.float32); c = np.zeros(3, np.float32)
+        self.lib.pmo_gather(_p(grid), _p(p), C.c_int(type_), C.c_int(id_), C.c_int(int(interp)), _p(c))
+        return c
