@@ -1,0 +1,280 @@
+"""pmb200 -- host-side Python mirror of the C-ABI in include/pmb200.h (ctypes; no compute happens here).
+
+The product is libpmb200.so (hand-written sm_100a CUDA behind a C ABI).  This module only loads it and
+marshals pointers: numpy / torch buffers in, status codes out.  It fails loudly if the library is missing
+or no CUDA device is present -- there is no CPU fallback and the oracle under oracle/ is never imported here.
+
+Reference call surface mirrored (simplePBO.cpp:125-182, callbacksPBO.cpp:47-101):
+    initRandomNumbers()            -> PhotonMapper.init_random_numbers() / launch_init_random_numbers_kernel()
+    simpleRunCuda(interp, media)   -> PhotonMapper.emit(t, media)        / launch_emit_photons_kernel(...)
+    photonMappingCuda(interp, media)-> PhotonMapper.render(...)           / launch_photon_mapping_kernel(...)
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpmb200.so")
+
+PM_TRACE_MEDIA, PM_TRACE_RECORDS, PM_TRACE_NO_MAP = 1, 2, 4
+GRID_N = 32
+ACC_HIT_ENTRIES = 5 * 32 * 32 * 3
+ACC_ENTRIES = ACC_HIT_ENTRIES + 32 * 32 * 32 * 3
+
+RECORD_DTYPE = np.dtype([("type", "<i4"), ("id", "<i4"), ("index", "<i4"), ("kind", "<i4"),
+                         ("loc", "<f4", 3), ("dir", "<f4", 3), ("energy", "<f4", 3)])
+
+
+class Scene(C.Structure):
+    """pm_scene (include/pmb200_types.h)."""
+    _fields_ = [("n_spheres", C.c_int32), ("n_planes", C.c_int32),
+                ("spheres", (C.c_float * 4) * 3), ("planes", (C.c_float * 2) * 5),
+                ("light", C.c_float * 3), ("sz_img", C.c_int32),
+                ("cam_ox", C.c_float), ("cam_oy", C.c_float), ("animate", C.c_int32)]
+
+
+class PmError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load libpmb200.so (once).  Raises if it has not been built: the product never falls back to CPU code."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PmError(f"{LIB_PATH} is missing: build it with `make -C {_HERE}` (or __graft_entry__.build())")
+        L = C.CDLL(LIB_PATH)
+        vp, i32, i64, f32, u32, b = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint32, C.c_bool
+        sig = {
+            "pm_create": (i32, [C.POINTER(vp), i32]), "pm_destroy": (i32, [vp]),
+            "pm_last_error": (C.c_char_p, [vp]), "pm_version": (C.c_char_p, []),
+            "pm_default_context": (vp, []), "pm_set_stream": (i32, [vp, vp]), "pm_sync": (i32, [vp]),
+            "pm_scene_default": (None, [C.POINTER(Scene)]), "pm_set_scene": (i32, [vp, C.POINTER(Scene)]),
+            "pm_get_scene": (i32, [vp, C.POINTER(Scene)]),
+            "pm_position_objects": (i32, [C.POINTER(Scene), f32, C.POINTER(Scene)]),
+            "pm_set_photon_count": (i32, [vp, i64]), "pm_set_photon_range": (i32, [vp, i64, i64]),
+            "pm_set_energy_scale": (i32, [vp, f32]),
+            "pm_init_random_table": (i32, [vp]), "pm_set_random_table_host": (i32, [vp, vp, i64]),
+            "pm_get_random_table_host": (i32, [vp, vp, i64]),
+            "pm_set_mwc_state": (i32, [vp, u32, u32]), "pm_get_mwc_state": (i32, [vp, C.POINTER(u32), C.POINTER(u32)]),
+            "pm_clear_map": (i32, [vp]), "pm_trace": (i32, [vp, f32, C.c_uint]),
+            "pm_accumulators": (i32, [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]),
+            "pm_get_accumulators_host": (i32, [vp, vp]),
+            "pm_build_map": (i32, [vp]), "pm_get_map_host": (i32, [vp, vp]), "pm_set_map_host": (i32, [vp, vp]),
+            "pm_map_device": (i32, [vp, C.POINTER(vp)]),
+            "pm_set_record_capacity": (i32, [vp, i64]), "pm_record_count": (i32, [vp, C.POINTER(i64)]),
+            "pm_get_records_host": (i32, [vp, vp, i64]),
+            "pm_record_buffers": (i32, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
+            "pm_render": (i32, [vp, f32, b, b, i32, i32, i32, i32, vp, vp]),
+            "pm_render_host": (i32, [vp, f32, b, b, i32, i32, vp, vp]),
+            "pm_frame_host": (i32, [vp, f32, b, b, b, i32, i32, vp, vp]),
+            "pm_launch_count": (i64, [vp]),
+            "launch_init_random_numbers_kernel": (None, []),
+            "launch_emit_photons_kernel": (None, [vp, C.c_uint, C.c_uint, f32, b, b]),
+            "launch_photon_mapping_kernel": (None, [vp, C.c_uint, C.c_uint, f32, b, b]),
+        }
+        for name, (res, args) in sig.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def default_scene(sz_img=512, animate=1):
+    s = Scene()
+    lib().pm_scene_default(C.byref(s))
+    s.sz_img = sz_img
+    s.animate = animate
+    return s
+
+
+def _ptr(a):
+    """Device or host pointer of a numpy array, a torch tensor, an int address, or None."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    if isinstance(a, np.ndarray):
+        return C.c_void_p(a.ctypes.data)
+    if hasattr(a, "data_ptr"):
+        return C.c_void_p(a.data_ptr())
+    raise TypeError(type(a))
+
+
+class PhotonMapper:
+    """One pm_context: a photon mapper bound to one GPU and one stream."""
+
+    def __init__(self, device=-1, n_photons=10000, scene=None):
+        self.L = lib()
+        h = C.c_void_p()
+        rc = self.L.pm_create(C.byref(h), device)
+        if rc != 0:
+            raise PmError({-4: "no CUDA device: pmb200 has no CPU fallback"}.get(rc, f"pm_create failed ({rc})"))
+        self.h = h
+        self.n_photons = 0
+        self.set_photon_count(n_photons)
+        if scene is not None:
+            self.set_scene(scene)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.pm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise PmError(f"pmb200 error {rc}: {self.L.pm_last_error(self.h).decode()}")
+
+    # -- configuration -----------------------------------------------------------------------------
+    def set_stream(self, cuda_stream):
+        self._ck(self.L.pm_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def sync(self):
+        self._ck(self.L.pm_sync(self.h))
+
+    def set_scene(self, scene):
+        self._ck(self.L.pm_set_scene(self.h, C.byref(scene)))
+
+    def get_scene(self):
+        s = Scene()
+        self._ck(self.L.pm_get_scene(self.h, C.byref(s)))
+        return s
+
+    def set_photon_count(self, n):
+        self._ck(self.L.pm_set_photon_count(self.h, n))
+        self.n_photons = n
+
+    def set_photon_range(self, first, last):
+        self._ck(self.L.pm_set_photon_range(self.h, first, last))
+
+    def set_energy_scale(self, s):
+        self._ck(self.L.pm_set_energy_scale(self.h, s))
+
+    # -- random table ------------------------------------------------------------------------------
+    def init_random_numbers(self):
+        """initRandomNumbers() (simplePBO.cpp:125) == launch_init_random_numbers_kernel on this context."""
+        self._ck(self.L.pm_init_random_table(self.h))
+
+    def set_random_table(self, xyz):
+        xyz = np.ascontiguousarray(xyz, np.float32)
+        self._ck(self.L.pm_set_random_table_host(self.h, _ptr(xyz), xyz.shape[0]))
+
+    def get_random_table(self, n=None):
+        n = self.n_photons if n is None else n
+        out = np.empty((n, 3), np.float32)
+        self._ck(self.L.pm_get_random_table_host(self.h, _ptr(out), n))
+        return out
+
+    def set_mwc_state(self, w, z):
+        self._ck(self.L.pm_set_mwc_state(self.h, w, z))
+
+    def get_mwc_state(self):
+        w, z = C.c_uint32(), C.c_uint32()
+        self._ck(self.L.pm_get_mwc_state(self.h, C.byref(w), C.byref(z)))
+        return w.value, z.value
+
+    # -- stage 1 -------------------------------------------------------------------------------------
+    def clear_map(self):
+        self._ck(self.L.pm_clear_map(self.h))
+
+    def trace(self, t=0.0, media=False, records=False, no_map=False):
+        flags = (PM_TRACE_MEDIA if media else 0) | (PM_TRACE_RECORDS if records else 0) | (PM_TRACE_NO_MAP if no_map else 0)
+        self._ck(self.L.pm_trace(self.h, t, flags))
+
+    def accumulators(self):
+        """(device pointer, number of int64 entries) of the exact accumulators."""
+        p, n = C.c_void_p(), C.c_size_t()
+        self._ck(self.L.pm_accumulators(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def get_accumulators(self):
+        out = np.empty(ACC_ENTRIES, np.int64)
+        self._ck(self.L.pm_get_accumulators_host(self.h, _ptr(out)))
+        return out
+
+    def build_map(self):
+        self._ck(self.L.pm_build_map(self.h))
+
+    def emit(self, t=0.0, media=False):
+        """simpleRunCuda() (simplePBO.cpp:166): clear the map, trace every photon, finalise the map."""
+        self.clear_map()
+        self.trace(t, media)
+        self.build_map()
+
+    def get_map(self):
+        g = np.empty((32, 32, 32, 3), np.float32)
+        self._ck(self.L.pm_get_map_host(self.h, _ptr(g)))
+        return g
+
+    def set_map(self, grid):
+        grid = np.ascontiguousarray(grid, np.float32)
+        assert grid.size == 32 * 32 * 32 * 3
+        self._ck(self.L.pm_set_map_host(self.h, _ptr(grid)))
+
+    def map_device_ptr(self):
+        p = C.c_void_p()
+        self._ck(self.L.pm_map_device(self.h, C.byref(p)))
+        return p.value
+
+    # -- records -------------------------------------------------------------------------------------
+    def set_record_capacity(self, n):
+        self._ck(self.L.pm_set_record_capacity(self.h, n))
+
+    def record_count(self):
+        n = C.c_int64()
+        self._ck(self.L.pm_record_count(self.h, C.byref(n)))
+        return n.value
+
+    def get_records(self):
+        n = self.record_count()
+        out = np.zeros(n, RECORD_DTYPE)
+        self._ck(self.L.pm_get_records_host(self.h, _ptr(out), n))
+        return out
+
+    def record_buffers(self):
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._ck(self.L.pm_record_buffers(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    # -- stages 3-5 -------------------------------------------------------------------------------------
+    def render_device(self, w, h, t=0.0, interp=False, media=False, rgba=None, rgbf=None, y0=0, y1=None):
+        """photonMappingCuda() (simplePBO.cpp:130) into caller-owned DEVICE buffers (torch tensors or addresses)."""
+        y1 = h if y1 is None else y1
+        self._ck(self.L.pm_render(self.h, t, interp, media, w, h, y0, y1, _ptr(rgba), _ptr(rgbf)))
+
+    def render(self, w, h, t=0.0, interp=False, media=False, want_u8=True, want_f32=True, out_u8=None, out_f32=None):
+        """Render through HOST buffers; returns (rgba uint8 [h,w,4], rgbf float32 [h,w,4])."""
+        u8 = out_u8 if out_u8 is not None else (np.empty((h, w, 4), np.uint8) if want_u8 else None)
+        f32 = out_f32 if out_f32 is not None else (np.empty((h, w, 4), np.float32) if want_f32 else None)
+        self._ck(self.L.pm_render_host(self.h, t, interp, media, w, h, _ptr(u8), _ptr(f32)))
+        return u8, f32
+
+    def frame(self, w, h, t=0.0, emit=True, interp=False, media=False, out_u8=None, out_f32=None):
+        """One display() frame (callbacksPBO.cpp:47-101) through host buffers."""
+        self._ck(self.L.pm_frame_host(self.h, t, emit, interp, media, w, h, _ptr(out_u8), _ptr(out_f32)))
+
+    def launch_count(self):
+        return self.L.pm_launch_count(self.h)
+
+
+# -- the reference's three launchers, verbatim names (process-global default context) --------------------
+def launch_init_random_numbers_kernel():
+    lib().launch_init_random_numbers_kernel()
+
+
+def launch_emit_photons_kernel(pos, image_width, image_height, animTime, interpolateFlag, participatingMediaFlag):
+    lib().launch_emit_photons_kernel(_ptr(pos), image_width, image_height, animTime, interpolateFlag, participatingMediaFlag)
+
+
+def launch_photon_mapping_kernel(pos, image_width, image_height, animTime, interpolateFlag, participatingMediaFlag):
+    lib().launch_photon_mapping_kernel(_ptr(pos), image_width, image_height, animTime, interpolateFlag, participatingMediaFlag)

@@ -1,0 +1,532 @@
+// pm_api.cu -- host side of libpmb200.so: the context behind the C-ABI of include/pmb200.h.
+//
+// Mirrors the reference's host launch surface: the three extern "C" launchers of photonMappingKernel.cu
+// (PMK:1523-1582) over a process-global default context, plus the handle-based extended API.  Host code is
+// C++ calling the CUDA kernels of pm_trace.cu / pm_map.cu / pm_render.cu; no CPU compute path exists here.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "pm_kernels.cuh"
+
+using namespace pm;
+
+struct pm_context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+
+  pm_scene scene;
+  DeviceScene dsc;                 // as of the last launch (after positionObjects)
+  int64_t n_photons = 0;           // nrPhotons == table length
+  int64_t first = 0, last = 0;     // photon range traced by this context
+  float energy_scale = 1.0f;
+
+  float *d_table = nullptr;
+  int64_t table_cap = 0;
+  uint32_t mwc_w = PM_MWC_SEED_W, mwc_z = PM_MWC_SEED_Z;
+  MwcJump *d_jump = nullptr;
+
+  long long *d_acc = nullptr;      // kAccEntries int64
+  float *d_grid = nullptr;         // PM_GRID_FLOATS
+  float4 *d_vol = nullptr, *d_surf = nullptr;
+  bool tables_valid = false;
+
+  float4 *d_rec_pos = nullptr, *d_rec_pow = nullptr, *d_rec_dir = nullptr;
+  unsigned long long *d_rec_count = nullptr;
+  int64_t rec_cap = 0;
+
+  uchar4 *d_fb_u8 = nullptr;
+  float4 *d_fb_f32 = nullptr;
+  int64_t fb_pixels = 0;
+
+  int64_t launches = 0;
+};
+
+#define CK(ctx, call)                                                                          \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess) {                                                                  \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                        \
+      return PM_ERR_CUDA;                                                                      \
+    }                                                                                          \
+  } while (0)
+#define ARG(ctx, cond, msg)                                                                    \
+  do {                                                                                         \
+    if (!(cond)) { if (ctx) (ctx)->err = (msg); return PM_ERR_ARG; }                          \
+  } while (0)
+
+// ---- host-side MWC arithmetic (see pm_math.cuh MwcJump) ------------------------------------------------
+static uint32_t h_mulmod(uint32_t a, uint32_t b, uint32_t m) { return (uint32_t)(((unsigned long long)a * b) % m); }
+static uint32_t h_powmod(uint32_t a, unsigned long long e, uint32_t m) {
+  uint32_t r = 1;
+  while (e) { if (e & 1) r = h_mulmod(r, a, m); a = h_mulmod(a, a, m); e >>= 1; }
+  return r;
+}
+// one MWC lane is x -> x * a mod (a*2^16 - 1): (2^16)^-1 == a because a*2^16 == 1 mod m
+static uint32_t h_lane_mult(int lane) { return lane == 0 ? 36969u : 18000u; }
+static uint32_t h_mwc_advance(int lane, uint32_t x, unsigned long long steps) {
+  uint32_t m = mwc_modulus(lane);
+  return h_mulmod(x, h_powmod(h_lane_mult(lane), steps, m), m);
+}
+static bool mwc_state_ok(uint32_t w, uint32_t z) { return w != 0 && z != 0 && w < mwc_modulus(1) && z < mwc_modulus(0); }
+
+static void fill_jump_tables(MwcJump *J) {
+  for (int lane = 0; lane < 2; lane++) {
+    uint32_t m = mwc_modulus(lane);
+    uint32_t base = h_lane_mult(lane);
+    for (int level = 0; level < 3; level++) {
+      uint32_t cur = 1;
+      for (int k = 0; k < 1024; k++) { J->pw[lane][level][k] = cur; cur = h_mulmod(cur, base, m); }
+      base = cur;   // base^(1024)
+    }
+  }
+}
+
+// positionObjects, PMK:1380-1404, evaluated once on the host: cos(float)/sin(float) resolve to the float
+// overloads, the other two arguments are double expressions.
+static void position_objects(pm_scene *sc, float t) {
+  if (!sc->animate) return;
+  sc->spheres[0][0] = (float)(1.0 * (double)cosf(t));
+  sc->spheres[0][1] = (float)(0.5 * sin(2.0 * (double)t));
+  sc->spheres[0][2] = (float)((double)sinf(t) + 3.5);
+  sc->spheres[1][0] = 0.0f;
+  sc->spheres[1][1] = (float)(sin(0.5 * (double)t + 5.0) - 0.25);
+  sc->spheres[1][2] = 3.5f;
+}
+
+static DeviceScene make_device_scene(const pm_scene &in, float t) {
+  pm_scene s = in;
+  position_objects(&s, t);
+  DeviceScene d;
+  memset(&d, 0, sizeof(d));
+  d.n_spheres = std::min(std::max(s.n_spheres, 0), PM_MAX_SPHERES);
+  d.n_planes = std::min(std::max(s.n_planes, 0), PM_MAX_PLANES);
+  for (int i = 0; i < PM_MAX_SPHERES; i++) {
+    for (int j = 0; j < 4; j++) d.sph[i][j] = s.spheres[i][j];
+    d.sph_r2[i] = s.spheres[i][3] * s.spheres[i][3];   // pow(radius, 2.0f), PMK:120
+  }
+  for (int i = 0; i < PM_MAX_PLANES; i++) { d.pl_axis[i] = (int)s.planes[i][0]; d.pl_off[i] = s.planes[i][1]; }
+  for (int j = 0; j < 3; j++) d.light[j] = s.light[j];
+  d.sz_img = (float)s.sz_img;
+  d.cam_ox = s.cam_ox; d.cam_oy = s.cam_oy;
+  return d;
+}
+
+extern "C" {
+
+const char *pm_version(void) { return "pmb200 0.1 (sm_100a)"; }
+
+void pm_scene_default(pm_scene *sc) {
+  static const float sp[3][4] = {{1.0f, -1.0f, 1.0f, 0.4f}, {-0.6f, -1.0f, 4.5f, 0.4f}, {0.0f, 0.0f, 1.5f, 1.0f}};
+  static const float pl[5][2] = {{0, 1.5f}, {1, -1.5f}, {0, -1.5f}, {1, 1.5f}, {2, 6.0f}};
+  memset(sc, 0, sizeof(*sc));
+  sc->n_spheres = 2; sc->n_planes = 5;
+  memcpy(sc->spheres, sp, sizeof(sp)); memcpy(sc->planes, pl, sizeof(pl));
+  sc->light[0] = 0.0f; sc->light[1] = 1.4f; sc->light[2] = 3.5f;
+  sc->sz_img = 512; sc->cam_ox = 0.0f; sc->cam_oy = 0.0f; sc->animate = 1;
+}
+
+int pm_position_objects(const pm_scene *in, float t, pm_scene *out) {
+  if (!in || !out) return PM_ERR_ARG;
+  *out = *in;
+  position_objects(out, t);
+  return PM_OK;
+}
+
+int pm_create(pm_context **out, int device) {
+  if (!out) return PM_ERR_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return PM_ERR_NO_DEVICE;
+  }
+  pm_context *c = new pm_context();
+  if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+  c->device = device;
+  pm_scene_default(&c->scene);
+  c->dsc = make_device_scene(c->scene, 0.0f);
+  auto fail = [&](cudaError_t e) { fprintf(stderr, "pmb200: pm_create: %s\n", cudaGetErrorString(e)); delete c; return PM_ERR_CUDA; };
+  cudaError_t e;
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&c->d_acc, sizeof(long long) * kAccEntries)) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&c->d_grid, sizeof(float) * PM_GRID_FLOATS)) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&c->d_vol, sizeof(float4) * kVolTableEntries)) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&c->d_surf, sizeof(float4) * kSurfTableEntries)) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&c->d_jump, sizeof(MwcJump))) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&c->d_rec_count, sizeof(unsigned long long))) != cudaSuccess) return fail(e);
+  if ((e = cudaMemset(c->d_acc, 0, sizeof(long long) * kAccEntries)) != cudaSuccess) return fail(e);
+  if ((e = cudaMemset(c->d_grid, 0, sizeof(float) * PM_GRID_FLOATS)) != cudaSuccess) return fail(e);
+  if ((e = cudaMemset(c->d_rec_count, 0, sizeof(unsigned long long))) != cudaSuccess) return fail(e);
+  {
+    std::vector<MwcJump> J(1);
+    fill_jump_tables(J.data());
+    if ((e = cudaMemcpy(c->d_jump, J.data(), sizeof(MwcJump), cudaMemcpyHostToDevice)) != cudaSuccess) return fail(e);
+  }
+  *out = c;
+  int rc = pm_set_photon_count(c, 10000);   // nrPhotons, PMK:29
+  if (rc != PM_OK) { pm_destroy(c); *out = nullptr; return rc; }
+  return PM_OK;
+}
+
+int pm_destroy(pm_context *c) {
+  if (!c) return PM_ERR_ARG;
+  cudaSetDevice(c->device);
+  cudaFree(c->d_table); cudaFree(c->d_acc); cudaFree(c->d_grid); cudaFree(c->d_vol); cudaFree(c->d_surf);
+  cudaFree(c->d_jump); cudaFree(c->d_rec_pos); cudaFree(c->d_rec_pow); cudaFree(c->d_rec_dir); cudaFree(c->d_rec_count);
+  cudaFree(c->d_fb_u8); cudaFree(c->d_fb_f32);
+  delete c;
+  return PM_OK;
+}
+
+const char *pm_last_error(const pm_context *c) { return c ? c->err.c_str() : "null context"; }
+int64_t pm_launch_count(const pm_context *c) { return c ? c->launches : 0; }
+
+int pm_set_stream(pm_context *c, void *stream) {
+  if (!c) return PM_ERR_ARG;
+  c->stream = (cudaStream_t)stream;
+  return PM_OK;
+}
+int pm_sync(pm_context *c) {
+  if (!c) return PM_ERR_ARG;
+  CK(c, cudaStreamSynchronize(c->stream));
+  return PM_OK;
+}
+
+int pm_set_scene(pm_context *c, const pm_scene *s) {
+  ARG(c, c && s, "null argument");
+  ARG(c, s->n_spheres >= 0 && s->n_spheres <= PM_MAX_SPHERES && s->n_planes >= 0 && s->n_planes <= PM_MAX_PLANES, "object counts out of range");
+  ARG(c, s->sz_img > 0, "sz_img must be positive");
+  c->scene = *s;
+  return PM_OK;
+}
+int pm_get_scene(const pm_context *c, pm_scene *s) {
+  if (!c || !s) return PM_ERR_ARG;
+  *s = c->scene;
+  return PM_OK;
+}
+int pm_set_energy_scale(pm_context *c, float scale) {
+  if (!c) return PM_ERR_ARG;
+  c->energy_scale = scale;
+  return PM_OK;
+}
+
+int pm_set_photon_count(pm_context *c, int64_t n) {
+  ARG(c, c != nullptr, "null context");
+  ARG(c, n >= 3 && n <= (int64_t)100000000, "photon count must be in [3, 1e8]");   // 9*n medium draws must stay < 2^30
+  CK(c, cudaSetDevice(c->device));
+  if (n > c->table_cap) {
+    CK(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_table); c->d_table = nullptr; c->table_cap = 0;
+    CK(c, cudaMalloc(&c->d_table, sizeof(float) * 3 * (size_t)n));
+    c->table_cap = n;
+  }
+  // the reference's table is zero-initialised device memory until launch_init_random_numbers_kernel runs
+  CK(c, cudaMemsetAsync(c->d_table, 0, sizeof(float) * 3 * (size_t)n, c->stream));
+  c->n_photons = n; c->first = 0; c->last = n;
+  return PM_OK;
+}
+int pm_set_photon_range(pm_context *c, int64_t first, int64_t last) {
+  ARG(c, c != nullptr, "null context");
+  ARG(c, first >= 0 && first <= last && last <= c->n_photons, "photon range outside [0, photon count]");
+  c->first = first; c->last = last;
+  return PM_OK;
+}
+
+int pm_set_mwc_state(pm_context *c, uint32_t w, uint32_t z) {
+  ARG(c, c != nullptr, "null context");
+  ARG(c, mwc_state_ok(w, z), "MWC state must be non-zero and below a*65536-1");
+  c->mwc_w = w; c->mwc_z = z;
+  return PM_OK;
+}
+int pm_get_mwc_state(const pm_context *c, uint32_t *w, uint32_t *z) {
+  if (!c || !w || !z) return PM_ERR_ARG;
+  *w = c->mwc_w; *z = c->mwc_z;
+  return PM_OK;
+}
+
+int pm_init_random_table(pm_context *c) {
+  ARG(c, c != nullptr, "null context");
+  CK(c, cudaSetDevice(c->device));
+  CK(c, launch_mwc_table(c->d_table, c->n_photons, c->mwc_w, c->mwc_z, c->d_jump, c->stream));
+  c->launches++;
+  unsigned long long draws = 3ull * (unsigned long long)c->n_photons;
+  c->mwc_z = h_mwc_advance(0, c->mwc_z, draws);
+  c->mwc_w = h_mwc_advance(1, c->mwc_w, draws);
+  return PM_OK;
+}
+int pm_set_random_table_host(pm_context *c, const float *xyz, int64_t n) {
+  ARG(c, c && xyz, "null argument");
+  ARG(c, n == c->n_photons, "table length must equal the photon count");
+  CK(c, cudaSetDevice(c->device));
+  CK(c, cudaMemcpyAsync(c->d_table, xyz, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  return PM_OK;
+}
+int pm_get_random_table_host(pm_context *c, float *xyz, int64_t n) {
+  ARG(c, c && xyz, "null argument");
+  ARG(c, n >= 0 && n <= c->n_photons, "table length exceeds the photon count");
+  CK(c, cudaSetDevice(c->device));
+  CK(c, cudaMemcpyAsync(xyz, c->d_table, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  return PM_OK;
+}
+
+int pm_clear_map(pm_context *c) {
+  ARG(c, c != nullptr, "null context");
+  CK(c, cudaSetDevice(c->device));
+  CK(c, cudaMemsetAsync(c->d_acc, 0, sizeof(long long) * kAccEntries, c->stream));
+  if (c->d_rec_count) CK(c, cudaMemsetAsync(c->d_rec_count, 0, sizeof(unsigned long long), c->stream));
+  c->tables_valid = false;
+  return PM_OK;
+}
+
+int pm_set_record_capacity(pm_context *c, int64_t cap) {
+  ARG(c, c != nullptr && cap >= 0, "bad capacity");
+  CK(c, cudaSetDevice(c->device));
+  CK(c, cudaStreamSynchronize(c->stream));
+  cudaFree(c->d_rec_pos); cudaFree(c->d_rec_pow); cudaFree(c->d_rec_dir);
+  c->d_rec_pos = c->d_rec_pow = c->d_rec_dir = nullptr; c->rec_cap = 0;
+  if (cap > 0) {
+    CK(c, cudaMalloc(&c->d_rec_pos, sizeof(float4) * (size_t)cap));
+    CK(c, cudaMalloc(&c->d_rec_pow, sizeof(float4) * (size_t)cap));
+    CK(c, cudaMalloc(&c->d_rec_dir, sizeof(float4) * (size_t)cap));
+    c->rec_cap = cap;
+  }
+  CK(c, cudaMemsetAsync(c->d_rec_count, 0, sizeof(unsigned long long), c->stream));
+  return PM_OK;
+}
+
+int pm_trace(pm_context *c, float t, unsigned flags) {
+  ARG(c, c != nullptr, "null context");
+  if ((flags & PM_TRACE_RECORDS) && c->rec_cap == 0) { c->err = "PM_TRACE_RECORDS needs pm_set_record_capacity first"; return PM_ERR_STATE; }
+  CK(c, cudaSetDevice(c->device));
+  c->dsc = make_device_scene(c->scene, t);
+  CK(c, launch_trace(c->dsc, c->d_table, c->first, c->last, flags, c->mwc_w, c->mwc_z, c->d_jump,
+                     (unsigned long long *)c->d_acc, c->d_rec_pos, c->d_rec_pow, c->d_rec_dir, c->d_rec_count, c->rec_cap, c->stream));
+  if (c->last > c->first) c->launches++;
+  if (flags & PM_TRACE_MEDIA) {   // the medium scattering consumed 9 draws per photon of the WHOLE job
+    unsigned long long draws = 9ull * (unsigned long long)c->n_photons;
+    c->mwc_z = h_mwc_advance(0, c->mwc_z, draws);
+    c->mwc_w = h_mwc_advance(1, c->mwc_w, draws);
+  }
+  c->tables_valid = false;
+  return PM_OK;
+}
+
+int pm_accumulators(pm_context *c, void **dev_ptr, size_t *n) {
+  if (!c || !dev_ptr || !n) return PM_ERR_ARG;
+  *dev_ptr = c->d_acc; *n = kAccEntries;
+  return PM_OK;
+}
+
+int pm_get_accumulators_host(pm_context *c, int64_t *out) {
+  ARG(c, c && out, "null argument");
+  CK(c, cudaSetDevice(c->device));
+  CK(c, cudaMemcpyAsync(out, c->d_acc, sizeof(long long) * kAccEntries, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  return PM_OK;
+}
+
+int pm_build_map(pm_context *c) {
+  ARG(c, c != nullptr, "null context");
+  CK(c, cudaSetDevice(c->device));
+  CK(c, launch_build_map(c->d_acc, c->energy_scale, c->d_grid, c->stream));
+  CK(c, launch_build_tables(c->d_grid, c->d_vol, c->d_surf, c->stream));
+  c->launches += 2;
+  c->tables_valid = true;
+  return PM_OK;
+}
+int pm_get_map_host(pm_context *c, float *grid) {
+  ARG(c, c && grid, "null argument");
+  CK(c, cudaSetDevice(c->device));
+  CK(c, cudaMemcpyAsync(grid, c->d_grid, sizeof(float) * PM_GRID_FLOATS, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  return PM_OK;
+}
+int pm_set_map_host(pm_context *c, const float *grid) {
+  ARG(c, c && grid, "null argument");
+  CK(c, cudaSetDevice(c->device));
+  CK(c, cudaMemcpyAsync(c->d_grid, grid, sizeof(float) * PM_GRID_FLOATS, cudaMemcpyHostToDevice, c->stream));
+  CK(c, launch_build_tables(c->d_grid, c->d_vol, c->d_surf, c->stream));
+  c->launches++;
+  CK(c, cudaStreamSynchronize(c->stream));
+  c->tables_valid = true;
+  return PM_OK;
+}
+int pm_map_device(pm_context *c, float **dev_grid) {
+  if (!c || !dev_grid) return PM_ERR_ARG;
+  *dev_grid = c->d_grid;
+  return PM_OK;
+}
+
+int pm_record_count(pm_context *c, int64_t *n) {
+  ARG(c, c && n, "null argument");
+  CK(c, cudaSetDevice(c->device));
+  unsigned long long cnt = 0;
+  CK(c, cudaMemcpyAsync(&cnt, c->d_rec_count, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  *n = (int64_t)cnt;
+  return PM_OK;
+}
+int pm_record_buffers(pm_context *c, float **pos, float **pow, float **dir) {
+  if (!c) return PM_ERR_ARG;
+  if (pos) *pos = (float *)c->d_rec_pos;
+  if (pow) *pow = (float *)c->d_rec_pow;
+  if (dir) *dir = (float *)c->d_rec_dir;
+  return PM_OK;
+}
+int pm_get_records_host(pm_context *c, pm_record *out, int64_t max_records) {
+  ARG(c, c && out, "null argument");
+  int64_t n = 0;
+  int rc = pm_record_count(c, &n);
+  if (rc != PM_OK) return rc;
+  if (n > c->rec_cap) { c->err = "record buffers overflowed (raise pm_set_record_capacity)"; return PM_ERR_STATE; }
+  ARG(c, n <= max_records, "host buffer too small");
+  std::vector<float4> pos((size_t)n), pw((size_t)n), dir((size_t)n);
+  CK(c, cudaMemcpy(pos.data(), c->d_rec_pos, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost));
+  CK(c, cudaMemcpy(pw.data(), c->d_rec_pow, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost));
+  CK(c, cudaMemcpy(dir.data(), c->d_rec_dir, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost));
+  std::vector<unsigned long long> key((size_t)n);   // (photon index, call ordinal, slot)
+  std::vector<int64_t> order((size_t)n);
+  for (int64_t i = 0; i < n; i++) {
+    uint32_t meta, idx;
+    memcpy(&meta, &pos[i].w, 4); memcpy(&idx, &pw[i].w, 4);
+    key[i] = ((unsigned long long)idx << 4) | (meta & 15u);
+    order[i] = i;
+  }
+  std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return key[a] < key[b]; });
+  for (int64_t j = 0; j < n; j++) {
+    int64_t i = order[j];
+    uint32_t meta; int32_t idx;
+    memcpy(&meta, &pos[i].w, 4); memcpy(&idx, &pw[i].w, 4);
+    int seq, kind, type, id;
+    unpack_meta(meta, seq, kind, type, id);
+    pm_record &r = out[j];
+    r.type = type; r.id = id; r.index = idx; r.kind = kind;
+    r.loc[0] = pos[i].x; r.loc[1] = pos[i].y; r.loc[2] = pos[i].z;
+    r.dir[0] = dir[i].x; r.dir[1] = dir[i].y; r.dir[2] = dir[i].z;
+    r.energy[0] = pw[i].x; r.energy[1] = pw[i].y; r.energy[2] = pw[i].z;
+  }
+  return PM_OK;
+}
+
+int pm_render(pm_context *c, float t, bool interp, bool media, int width, int height, int y0, int y1,
+              pm_uchar4 *dev_rgba, float *dev_rgbf) {
+  ARG(c, c != nullptr, "null context");
+  ARG(c, width > 0 && height > 0 && y0 >= 0 && y0 <= y1 && y1 <= height, "bad frame geometry");
+  if (!c->tables_valid) { c->err = "pm_render before pm_build_map / pm_set_map_host"; return PM_ERR_STATE; }
+  CK(c, cudaSetDevice(c->device));
+  c->dsc = make_device_scene(c->scene, t);
+  CK(c, launch_render(c->dsc, c->d_vol, c->d_surf, width, height, y0, y1, interp, media, (uchar4 *)dev_rgba, (float4 *)dev_rgbf, c->stream));
+  if (y1 > y0) c->launches++;
+  return PM_OK;
+}
+
+static int ensure_framebuffers(pm_context *c, int64_t pixels) {
+  if (pixels <= c->fb_pixels) return PM_OK;
+  CK(c, cudaStreamSynchronize(c->stream));
+  cudaFree(c->d_fb_u8); cudaFree(c->d_fb_f32);
+  c->d_fb_u8 = nullptr; c->d_fb_f32 = nullptr; c->fb_pixels = 0;
+  CK(c, cudaMalloc(&c->d_fb_u8, sizeof(uchar4) * (size_t)pixels));
+  CK(c, cudaMalloc(&c->d_fb_f32, sizeof(float4) * (size_t)pixels));
+  c->fb_pixels = pixels;
+  return PM_OK;
+}
+
+int pm_render_host(pm_context *c, float t, bool interp, bool media, int width, int height, pm_uchar4 *host_rgba, float *host_rgbf) {
+  ARG(c, c != nullptr, "null context");
+  ARG(c, width > 0 && height > 0, "bad frame geometry");
+  CK(c, cudaSetDevice(c->device));
+  int64_t pixels = (int64_t)width * height;
+  int rc = ensure_framebuffers(c, pixels);
+  if (rc != PM_OK) return rc;
+  rc = pm_render(c, t, interp, media, width, height, 0, height, host_rgba ? (pm_uchar4 *)c->d_fb_u8 : nullptr, host_rgbf ? (float *)c->d_fb_f32 : nullptr);
+  if (rc != PM_OK) return rc;
+  if (host_rgba) CK(c, cudaMemcpyAsync(host_rgba, c->d_fb_u8, sizeof(uchar4) * (size_t)pixels, cudaMemcpyDeviceToHost, c->stream));
+  if (host_rgbf) CK(c, cudaMemcpyAsync(host_rgbf, c->d_fb_f32, sizeof(float4) * (size_t)pixels, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  return PM_OK;
+}
+
+int pm_frame_host(pm_context *c, float t, bool emit, bool interp, bool media, int width, int height, pm_uchar4 *host_rgba, float *host_rgbf) {
+  ARG(c, c != nullptr, "null context");
+  int rc;
+  if (emit) {
+    if ((rc = pm_clear_map(c)) != PM_OK) return rc;
+    if ((rc = pm_trace(c, t, media ? PM_TRACE_MEDIA : 0u)) != PM_OK) return rc;
+    if ((rc = pm_build_map(c)) != PM_OK) return rc;
+  }
+  return pm_render_host(c, t, interp, media, width, height, host_rgba, host_rgbf);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// legacy drop-in symbols (PMK:1523-1582): default context, synchronous, abort on error like checkCUDAError
+// ---------------------------------------------------------------------------------------------------
+static pm_context *g_default = nullptr;
+static std::once_flag g_default_once;
+
+pm_context *pm_default_context(void) {
+  std::call_once(g_default_once, [] {
+    pm_context *c = nullptr;
+    int rc = pm_create(&c, -1);
+    if (rc != PM_OK) {
+      fprintf(stderr, "Cuda error: %s: %s.\n", "pmb200 default context", rc == PM_ERR_NO_DEVICE ? "no CUDA device (there is no CPU fallback)" : "initialisation failed");
+      exit(EXIT_FAILURE);
+    }
+    const char *env = getenv("PMB200_NR_PHOTONS");
+    if (env && *env) {
+      long long n = atoll(env);
+      if (pm_set_photon_count(c, n) != PM_OK) {
+        fprintf(stderr, "Cuda error: %s: %s.\n", "PMB200_NR_PHOTONS", pm_last_error(c));
+        exit(EXIT_FAILURE);
+      }
+    }
+    g_default = c;
+  });
+  return g_default;
+}
+
+static void legacy_check(pm_context *c, int rc, const char *msg) {   // checkCUDAError, PMK:49-55
+  if (rc == PM_OK) {
+    cudaError_t e = cudaStreamSynchronize(c->stream);   // cudaThreadSynchronize() after every launch
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess) return;
+    c->err = cudaGetErrorString(e);
+  }
+  fprintf(stderr, "Cuda error: %s: %s.\n", msg, c->err.c_str());
+  exit(EXIT_FAILURE);
+}
+
+void launch_init_random_numbers_kernel(void) {
+  pm_context *c = pm_default_context();
+  legacy_check(c, pm_init_random_table(c), "init_random_numbers_kernel failed!");
+}
+
+void launch_emit_photons_kernel(pm_uchar4 *pos, unsigned int image_width, unsigned int image_height, float animTime,
+                                bool interpolateFlag, bool participatingMediaFlag) {
+  (void)pos; (void)image_width; (void)image_height; (void)interpolateFlag;   // unused by the reference too
+  pm_context *c = pm_default_context();
+  legacy_check(c, pm_clear_map(c), "init_photons_kernel failed!");
+  int rc = pm_trace(c, animTime, participatingMediaFlag ? PM_TRACE_MEDIA : 0u);
+  if (rc == PM_OK) rc = pm_build_map(c);
+  legacy_check(c, rc, "emit_photons_kernel failed!");
+}
+
+void launch_photon_mapping_kernel(pm_uchar4 *pos, unsigned int image_width, unsigned int image_height, float animTime,
+                                  bool interpolateFlag, bool participatingMediaFlag) {
+  pm_context *c = pm_default_context();
+  if (!c->tables_valid) {   // the reference renders whatever the (zeroed) grid holds
+    legacy_check(c, pm_build_map(c), "photon_mapping_kernel failed!");
+  }
+  legacy_check(c, pm_render(c, animTime, interpolateFlag, participatingMediaFlag, (int)image_width, (int)image_height, 0,
+                            (int)image_height, pos, nullptr), "photon_mapping_kernel failed!");
+}
+
+}  // extern "C"

@@ -1,0 +1,43 @@
+// pm_layout.h -- HBM layout of the photon map and its derived tables (host + device).
+#pragma once
+
+#include <stdint.h>
+#include "../../include/pmb200_types.h"
+
+namespace pm {
+
+// ---- exact accumulators (int64 fixed point; order-independent, so bit-reproducible for any GPU count) -----
+// acc_hit[plane id 0..4][a][b][rgb]  : energy of wall hits whose clamped voxel lies on that wall's slab,
+//                                      keyed by the two in-plane voxel coordinates (scale 2^24: every energy
+//                                      the reference produces -- 10, 5/sqrt(b), -0.25 -- is exact)
+// acc_vox[x][y][z][rgb]              : everything that is deposited straight into a voxel: volume photons
+//                                      (5e-5*rgb) and the fully expanded splat of the rare off-slab hit
+//                                      (scale 2^36)
+constexpr int    kAccHitEntries = PM_MAX_PLANES * PM_GRID_N * PM_GRID_N * 3;   // 15 360
+constexpr int    kAccVoxEntries = PM_GRID_VOXELS * 3;                          // 98 304
+constexpr int    kAccEntries    = kAccHitEntries + kAccVoxEntries;             // 113 664 int64 = 909 312 B
+constexpr double kHitScale      = 16777216.0;          // 2^24
+constexpr double kVoxScale      = 68719476736.0;       // 2^36
+
+// ---- gather tables, rebuilt from the float photon map whenever it changes -------------------------------
+// The reference's gathers depend only on the integer voxel of the query point, so their sums are tabulated
+// once per map, in the reference's own summation order (=> bit-identical to summing per pixel):
+//   vol_table [35][35][35] float4 : integrateVolumePhotons (PMK:831-870) for voxel coords -1..33 per axis
+//   surf_table[5][37][37]  float4 : integrate (PMK:314-389) per wall id, in-plane voxel coords -2..34
+constexpr int kVolLo = -1, kVolN = 35;
+constexpr int kSurfLo = -2, kSurfN = 37;
+constexpr int kVolTableEntries  = kVolN * kVolN * kVolN;                // 42 875
+constexpr int kSurfTableEntries = PM_MAX_PLANES * kSurfN * kSurfN;      //  6 845
+
+// ---- photon records (Mode B input): SoA float4 buffers -----------------------------------------------
+// pos_meta[i]    = (x, y, z, bits(meta))     meta: seq[0:4) | kind[4] | (type+1)[5:7) | (id+1)[7:11)
+// power_index[i] = (r, g, b, bits(photon index))
+// dir[i]         = (dx, dy, dz, 0)
+__host__ __device__ inline uint32_t pack_meta(int seq, int kind, int type, int id) {
+  return (uint32_t)(seq & 15) | ((uint32_t)(kind & 1) << 4) | ((uint32_t)((type + 1) & 3) << 5) | ((uint32_t)((id + 1) & 15) << 7);
+}
+__host__ __device__ inline void unpack_meta(uint32_t m, int &seq, int &kind, int &type, int &id) {
+  seq = (int)(m & 15u); kind = (int)((m >> 4) & 1u); type = (int)((m >> 5) & 3u) - 1; id = (int)((m >> 7) & 15u) - 1;
+}
+
+}  // namespace pm

@@ -1,0 +1,131 @@
+/* include/pmb200.h -- the C-ABI of libpmb200.so, the B200-native drop-in for the CUDA hot path of
+ * gamalik/cuda-photon-mapper (PMK = /root/reference/photonMappingKernel.cu).
+ *
+ * Two layers:
+ *   (1) the reference's three extern "C" launchers, same names, argument meaning and error behaviour
+ *       (PMK:1523, :1549, :1569; declared by their caller at simplePBO.cpp:27-29).  A host program that
+ *       links photonMappingKernel.cu can link libpmb200.so instead.
+ *   (2) an extended, handle-based API (pm_*) that exposes what the reference hides in __device__ globals
+ *       and #defines (scene, photon count, RNG table, photon map), adds a headless float framebuffer,
+ *       photon-range / row-band sharding for multi-GPU, and the k-NN photon-map pipeline (Mode B).
+ *
+ * Plain pointers and sizes only; no CUDA or torch types in any signature.  Pointers named dev_* are device
+ * pointers owned by the caller; host_* are host pointers.  All pm_* calls return 0 on success or a negative
+ * pm_status; pm_last_error() gives the text.  pm_* launches are asynchronous on the context's stream unless
+ * the name ends in _host or says otherwise.  There is no CPU fallback: without a CUDA device pm_create fails.
+ */
+#ifndef PMB200_H
+#define PMB200_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+#include "pmb200_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* layout-compatible with CUDA's uchar4 (the mapped GL pixel-buffer object of simplePBO.cpp:137) */
+typedef struct pm_uchar4 { unsigned char x, y, z, w; } pm_uchar4;
+
+/* ------------------------------------------------------------------------------------------------
+ * (1) Legacy drop-in symbols.  Process-global default context, default stream, fully synchronous; on a
+ * CUDA error they print "Cuda error: <msg>: <str>." to stderr and exit(EXIT_FAILURE), as checkCUDAError
+ * does (PMK:49-55).  Photon count = 10 000 (PMK:29) unless the environment variable PMB200_NR_PHOTONS is set.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* replaces PMK:1569 launch_init_random_numbers_kernel: fills the random-direction table from the MWC
+ * generator (seeds 6548/316), bit-identical to the reference's serial <<<1,1>>> loop, but in parallel. */
+void launch_init_random_numbers_kernel(void);
+
+/* replaces PMK:1523 launch_emit_photons_kernel: clear the photon map, trace all photons at animTime.
+ * pos / image_width / image_height are ignored, as in the reference. */
+void launch_emit_photons_kernel(pm_uchar4 *pos, unsigned int image_width, unsigned int image_height,
+                                float animTime, bool interpolateFlag, bool participatingMediaFlag);
+
+/* replaces PMK:1549 launch_photon_mapping_kernel: render image_width x image_height pixels into the DEVICE
+ * buffer pos ({r,g,b,0}, row 0 = top). */
+void launch_photon_mapping_kernel(pm_uchar4 *pos, unsigned int image_width, unsigned int image_height,
+                                  float animTime, bool interpolateFlag, bool participatingMediaFlag);
+
+/* ------------------------------------------------------------------------------------------------
+ * (2) Extended API
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pm_context pm_context;
+
+typedef enum pm_status {
+  PM_OK = 0,
+  PM_ERR_CUDA = -1,        /* a CUDA runtime call failed (text in pm_last_error) */
+  PM_ERR_ARG = -2,         /* invalid argument */
+  PM_ERR_STATE = -3,       /* call order violated (e.g. trace before a table exists) */
+  PM_ERR_NO_DEVICE = -4    /* no CUDA device: there is no CPU fallback */
+} pm_status;
+
+int         pm_create(pm_context **out, int device /* -1: current device */);
+int         pm_destroy(pm_context *ctx);
+const char *pm_last_error(const pm_context *ctx);
+const char *pm_version(void);
+pm_context *pm_default_context(void);                 /* the context behind the legacy symbols */
+int         pm_set_stream(pm_context *ctx, void *cuda_stream /* cudaStream_t; NULL = default stream */);
+int         pm_sync(pm_context *ctx);
+
+/* scene / parameters (reference: __device__ globals PMK:59-73, #define nrPhotons PMK:29) */
+void pm_scene_default(pm_scene *scene);
+int  pm_set_scene(pm_context *ctx, const pm_scene *scene);
+int  pm_get_scene(const pm_context *ctx, pm_scene *scene);
+int  pm_position_objects(const pm_scene *in, float animTime, pm_scene *out);   /* PMK:1380-1404, host side */
+int  pm_set_photon_count(pm_context *ctx, int64_t n_photons);                  /* table size, nrPhotons */
+int  pm_set_photon_range(pm_context *ctx, int64_t first, int64_t last);        /* this GPU traces [first,last) */
+int  pm_set_energy_scale(pm_context *ctx, float scale);   /* photon map is multiplied by this when built (1 = reference) */
+
+/* random-direction table T2 (PMK:80) */
+int pm_init_random_table(pm_context *ctx);       /* MWC stream, == launch_init_random_numbers_kernel */
+int pm_set_random_table_host(pm_context *ctx, const float *host_xyz, int64_t n);
+int pm_get_random_table_host(pm_context *ctx, float *host_xyz, int64_t n);
+int pm_set_mwc_state(pm_context *ctx, uint32_t w, uint32_t z);   /* where the medium-scatter draws continue from */
+int pm_get_mwc_state(const pm_context *ctx, uint32_t *w, uint32_t *z);
+
+/* stage 1: photon emission + tracing (PMK:1215-1375 emitPhotons; F9-F17 of SURVEY.md 8(a)) */
+#define PM_TRACE_MEDIA    1u   /* participatingMediaFlag */
+#define PM_TRACE_RECORDS  2u   /* also append photon records to the SoA buffers (Mode B input) */
+#define PM_TRACE_NO_MAP   4u   /* skip the voxel-map accumulation (records only) */
+int pm_clear_map(pm_context *ctx);                                 /* init_photons_kernel, PMK:1503-1521 */
+int pm_trace(pm_context *ctx, float animTime, unsigned flags);
+/* the exact (int64 fixed-point) accumulators the trace adds into; sum them across GPUs (e.g. NCCL
+ * all-reduce, ncclInt64/ncclSum) between pm_trace and pm_build_map for multi-GPU runs */
+int pm_accumulators(pm_context *ctx, void **dev_ptr, size_t *n_int64);
+int pm_get_accumulators_host(pm_context *ctx, int64_t *host_out /* n_int64 entries */);
+int pm_build_map(pm_context *ctx);                                 /* accumulators -> float photon map + gather tables */
+int pm_get_map_host(pm_context *ctx, float *host_grid /* 32*32*32*3 */);
+int pm_set_map_host(pm_context *ctx, const float *host_grid);      /* inject a photon map (parity tests) */
+int pm_map_device(pm_context *ctx, float **dev_grid);
+
+/* photon records (valid after pm_trace with PM_TRACE_RECORDS) */
+int pm_set_record_capacity(pm_context *ctx, int64_t max_records);
+int pm_record_count(pm_context *ctx, int64_t *n);                  /* synchronises */
+int pm_get_records_host(pm_context *ctx, pm_record *host_out, int64_t max_records);   /* canonical (index, call) order */
+int pm_record_buffers(pm_context *ctx, float **dev_pos_meta /* float4[] */, float **dev_power_index /* float4[] */,
+                      float **dev_dir /* float4[] */);
+
+/* stages 3-5: eye rays, photon-map gather, volumetric ray-march (PMK:926-1017, :1409-1462).
+ * Renders rows [y0,y1) of a width x height frame.  dev_rgba (uchar4, may be NULL) and dev_rgbf (float4 =
+ * pre-quantisation rgb + 1, may be NULL) are whole-frame DEVICE buffers. */
+int pm_render(pm_context *ctx, float animTime, bool interpolateFlag, bool participatingMediaFlag,
+              int width, int height, int y0, int y1, pm_uchar4 *dev_rgba, float *dev_rgbf);
+/* the same through HOST buffers: device frame buffers are owned by the context, results are copied back
+ * (synchronous). */
+int pm_render_host(pm_context *ctx, float animTime, bool interpolateFlag, bool participatingMediaFlag,
+                   int width, int height, pm_uchar4 *host_rgba, float *host_rgbf);
+/* one whole reference frame through host buffers: (optional emit) + render + copy-back; what display() does
+ * (callbacksPBO.cpp:47-101) minus OpenGL */
+int pm_frame_host(pm_context *ctx, float animTime, bool emitFlag, bool interpolateFlag, bool participatingMediaFlag,
+                  int width, int height, pm_uchar4 *host_rgba, float *host_rgbf);
+
+/* instrumentation: number of kernels this context has launched so far */
+int64_t pm_launch_count(const pm_context *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

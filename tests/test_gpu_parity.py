@@ -1,0 +1,197 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every test drives libpmb200.so through its C-ABI
+(pmb200 = ctypes over include/pmb200.h) and checks it against the CPU oracle (oracle/pm_oracle.c) on the same
+seeded inputs.  Bars (BASELINE.json north_star):
+  * integer / byte / index work (MWC stream, photon records' ids, uchar4 frame): bit-exact;
+  * photon positions / power: north_star allows 1e-5 relative; we assert BIT-exact (same FP32 operation order);
+  * float framebuffer for an identical photon map: bit-exact;
+  * photon map (float sums over thousands of deposits, summed in a different order than the sequential
+    reference): |diff| <= 2e-5 * max|map| -- the tolerance is the FP32 rounding of the REFERENCE's sequential
+    sums, the product's sums are exact int64 fixed point;
+  * rendered frame from the product's own map vs the oracle's: relative L1 <= 1e-4, PSNR >= 60 dB.
+"""
+import numpy as np
+import pytest
+
+from tests.util import bits_equal, cfg1_scene, copy_scene, grid_from_records
+
+pytestmark = pytest.mark.gpu
+
+MAP_TOL = 2e-5
+
+
+def _mapper(pm, n, scene=None):
+    m = pm.PhotonMapper(n_photons=n)
+    if scene is not None:
+        m.set_scene(scene)
+    return m
+
+
+def test_mwc_table_bit_exact(pm, oracle):
+    """launch_init_random_numbers_kernel replacement: parallel jump-ahead == the serial MWC loop (PMK:1483-1498)."""
+    for n in (3, 1000, 10000, 300001):
+        m = _mapper(pm, n)
+        m.init_random_numbers()
+        tab = m.get_random_table()
+        ref, st = oracle.mwc_table(n)
+        assert bits_equal(tab, ref), n
+        assert m.get_mwc_state() == st
+        # a second call continues the stream, as the reference's global m_w/m_z would
+        m.init_random_numbers()
+        ref2, st2 = oracle.mwc_table(n, *st)
+        assert bits_equal(m.get_random_table(), ref2)
+        assert m.get_mwc_state() == st2
+        m.close()
+
+
+@pytest.mark.parametrize("media", [False, True])
+@pytest.mark.parametrize("t", [0.0, 0.7])
+@pytest.mark.parametrize("scene_name", ["default", "cfg1"])
+def test_trace_records_and_map(pm, oracle, media, t, scene_name):
+    """Stage 1: photon records bit-exact (position, direction, power, object ids, order), photon map within MAP_TOL."""
+    n = 20000
+    osc = oracle.default_scene()
+    if scene_name == "cfg1":
+        cfg1_scene(osc)
+    m = _mapper(pm, n, copy_scene(pm.Scene, osc))
+    m.init_random_numbers()
+    table, st = oracle.mwc_table(n)
+    m.set_record_capacity(16 * n)
+    m.clear_map()
+    m.trace(t, media=media, records=True)
+    m.build_map()
+    rec = m.get_records()
+    grid = m.get_map()
+    ogrid, orec, ost = oracle.emit(osc, table, 0, n, t, media, rng=st, max_records=16 * n)
+    assert len(rec) == len(orec)
+    assert rec.tobytes() == orec.tobytes()
+    assert m.get_mwc_state() == ost
+    scale = np.abs(ogrid).max()
+    assert np.abs(grid - ogrid).max() <= MAP_TOL * scale
+    m.close()
+
+
+def test_map_matches_exact_sum_of_records(pm, oracle):
+    """The product's map is the correctly rounded exact sum of the deposits (int64 fixed point), so it must agree
+    with a float64 accumulation of the oracle's records to ~1 ulp -- much tighter than against the reference's
+    own sequential FP32 sums."""
+    n = 3000
+    osc = oracle.default_scene()
+    m = _mapper(pm, n, copy_scene(pm.Scene, osc))
+    m.init_random_numbers()
+    table, st = oracle.mwc_table(n)
+    m.emit(0.0, media=True)
+    grid = m.get_map()
+    _, orec, _ = oracle.emit(osc, table, 0, n, 0.0, True, rng=st, max_records=16 * n)
+    exact = grid_from_records(orec)
+    scale = np.abs(exact).max()
+    assert np.abs(grid - exact).max() <= 3e-7 * scale
+    m.close()
+
+
+@pytest.mark.parametrize("interp", [False, True])
+@pytest.mark.parametrize("media", [False, True])
+@pytest.mark.parametrize("t", [0.0, 1.3])
+def test_render_bit_exact_on_injected_map(pm, oracle, interp, media, t):
+    """Stages 3-5 on the oracle's photon map: float framebuffer and uchar4 frame bit-exact (all four flag
+    combinations of the legacy ABI, static and animated scene)."""
+    n, w, h = 20000, 256, 256
+    osc = oracle.default_scene(sz_img=256)
+    table, st = oracle.mwc_table(n)
+    ogrid, _, _ = oracle.emit(osc, table, 0, n, t, media, rng=st)
+    oimg, ou8 = oracle.render(osc, ogrid, w, h, t, interp, media)
+    m = _mapper(pm, n, copy_scene(pm.Scene, osc))
+    m.set_map(ogrid)
+    u8, f32 = m.render(w, h, t, interp, media)
+    assert bits_equal(f32[..., :3], oimg)
+    assert np.all(f32[..., 3] == 1.0)
+    assert np.array_equal(u8, ou8)
+    m.close()
+
+
+def test_render_rect_frame_and_row_bands(pm, oracle):
+    """Non-square frame with a camera offset, rendered in two row bands (the multi-GPU screen split)."""
+    import torch
+    n, w, h = 5000, 320, 180
+    osc = oracle.default_scene(sz_img=180)
+    osc.cam_ox = -70.0
+    table, st = oracle.mwc_table(n)
+    ogrid, _, _ = oracle.emit(osc, table, 0, n, 0.0, True, rng=st)
+    oimg, ou8 = oracle.render(osc, ogrid, w, h, 0.0, False, True)
+    m = _mapper(pm, n, copy_scene(pm.Scene, osc))
+    m.set_map(ogrid)
+    rgba = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+    rgbf = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
+    m.render_device(w, h, 0.0, False, True, rgba=rgba, rgbf=rgbf, y0=0, y1=77)
+    m.render_device(w, h, 0.0, False, True, rgba=rgba, rgbf=rgbf, y0=77, y1=h)
+    m.sync()
+    assert bits_equal(rgbf.cpu().numpy()[..., :3], oimg)
+    assert np.array_equal(rgba.cpu().numpy(), ou8)
+    m.close()
+
+
+def test_full_frame_vs_oracle(pm, oracle):
+    """Whole path (trace -> map -> render) against the whole oracle path: image tolerance from north_star
+    (relative L1 <= 1e-4, PSNR >= 60 dB on the float frame; uchar4 frame differs in <= 0.1% of channel values, by 1)."""
+    n, w, h = 50000, 256, 256
+    osc = oracle.default_scene(sz_img=256)
+    table, st = oracle.mwc_table(n)
+    ogrid, _, _ = oracle.emit(osc, table, 0, n, 0.0, True, rng=st)
+    oimg, ou8 = oracle.render(osc, ogrid, w, h, 0.0, False, True)
+    m = _mapper(pm, n, copy_scene(pm.Scene, osc))
+    m.init_random_numbers()
+    u8 = np.empty((h, w, 4), np.uint8); f32 = np.empty((h, w, 4), np.float32)
+    m.frame(w, h, 0.0, emit=True, interp=False, media=True, out_u8=u8, out_f32=f32)
+    img = f32[..., :3]
+    rel_l1 = np.abs(img - oimg).sum() / np.abs(oimg).sum()
+    mse = np.mean((img.astype(np.float64) - oimg) ** 2)
+    psnr = 10 * np.log10(float(oimg.max()) ** 2 / mse) if mse > 0 else np.inf
+    assert rel_l1 <= 1e-4, rel_l1
+    assert psnr >= 60.0, psnr
+    d = np.abs(u8.astype(np.int32) - ou8.astype(np.int32))
+    assert d.max() <= 1 and (d > 0).mean() <= 1e-3
+    m.close()
+
+
+def test_photon_range_sharding_is_exact(pm, oracle):
+    """Tracing [0,n) in one go and in three shards gives bit-identical accumulators (int64, order independent)
+    and therefore a bit-identical map: the multi-GPU invariance the design relies on."""
+    n = 30000
+    m = _mapper(pm, n)
+    m.init_random_numbers()
+    st = m.get_mwc_state()
+    m.clear_map(); m.trace(0.0, media=True); m.build_map()
+    whole = m.get_accumulators()
+    g_whole = m.get_map()
+    m.set_mwc_state(*st)
+    m.clear_map()
+    for a, b in ((0, 7000), (7000, 7001), (7001, n)):
+        m.set_mwc_state(*st)
+        m.set_photon_range(a, b)
+        m.trace(0.0, media=True)
+    m.build_map()
+    parts = m.get_accumulators()
+    assert np.array_equal(whole, parts)
+    assert bits_equal(g_whole, m.get_map())
+    m.close()
+
+
+def test_legacy_abi_frame(pm, oracle):
+    """The three reference launchers in display() order (callbacksPBO.cpp:55-63): initRandomNumbers once, emit, render
+    into a device uchar4 buffer.  Default context: 10 000 photons, 512x512, szImg 512."""
+    import torch
+    w = h = 512
+    n = 10000
+    osc = oracle.default_scene()
+    table, st = oracle.mwc_table(n)
+    pos = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+    pm.launch_init_random_numbers_kernel()
+    for t, interp, media in ((0.0, False, False), (0.25, True, True)):
+        pm.launch_emit_photons_kernel(pos, w, h, t, interp, media)
+        pm.launch_photon_mapping_kernel(pos, w, h, t, interp, media)
+        ogrid, _, st2 = oracle.emit(osc, table, 0, n, t, media, rng=st)
+        st = st2
+        _, ou8 = oracle.render(osc, ogrid, w, h, t, interp, media)
+        got = pos.cpu().numpy()
+        d = np.abs(got.astype(np.int32) - ou8.astype(np.int32))
+        assert d.max() <= 1 and (d > 0).mean() <= 2e-3, (t, d.max(), (d > 0).mean())
+        assert np.all(got[..., 3] == 0)
