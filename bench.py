@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of pmb200 (the B200-native photon-mapping hot path).
+
+Metric (BASELINE.json): ms/frame at 1920x1080 with a 16M-photon volumetric (participating-media) photon map
+-- config 4, the configuration the north-star target is quoted on.  One "step" = one frame of the hot path:
+clear map -> trace all photons (medium scattering on) -> [all-reduce of the exact accumulators when N > 1]
+-> build map + gather tables -> eye rays + ray-march gather -> uchar4 frame + float4 framebuffer on rank 0.
+The random-direction table is initialised once before the timed region, as the reference does (display():
+callbacksPBO.cpp:55-58).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--photons P] [--width W --height H]
+
+N > 1 is launched by torchrun, one rank per GPU (strong scaling: the photons and the screen rows are split).
+--impl reference times the reference's own CPU implementation of the path (oracle/_ref, all host threads) on
+a bounded sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ms/frame 1080p, 16M-photon volumetric map (trace + map build + ray-march render)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--photons", type=int, default=16777216)
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--no-ref-cuda", action="store_true", help="skip timing the reference CUDA kernels")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(a, extra=None):
+    cfg = {"workload": "BASELINE config 4: default participating-media scene, %d photons, %dx%d, Mode A "
+                       "(reference voxel-map estimator), media on, interpolate off" % (a.photons, a.width, a.height),
+           "photons": a.photons, "width": a.width, "height": a.height, "media": True, "interpolate": False,
+           "rng": "MWC table (reference stream, jump-ahead)", "energy_scale": 10000.0 / a.photons,
+           "cache": "inputs larger than L2: the 12 B/photon direction table (%.0f MB) is streamed every frame"
+                    % (a.photons * 12 / 1e6)}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks: NVML sampled on a thread while the GPU is under load
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.samples, self.reasons, self.stop_flag, self.thread, self.max_mhz = [], set(), False, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def start(self):
+        if self.nv:
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join()
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the reference's own routines on the host cores (oracle/_ref), bounded sample
+# ------------------------------------------------------------------------------------------------------
+def cpu_reference_frame_ms(a, photon_div=16, row_div=8):
+    """Returns (estimated ms/frame, descriptor dict).  Sample: photons/photon_div traced + height/row_div rows
+    rendered, each scaled back to the whole frame."""
+    from oracle import oraclelib, refhost
+    if not oraclelib.available():
+        import subprocess
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "libpm_oracle.so"])
+    orc = oraclelib.Oracle()
+    n_s = max(a.photons // photon_div, 1000)
+    rows = max(a.height // row_div, 1)
+    table, st = orc.mwc_table(n_s)
+    if refhost.available():
+        r = refhost.RefHost()
+        cores = r.omp_threads()
+        r.set_scene(sz_img=a.height)
+        r.set_table(table); r.set_rng(*st); r.clear_grid()
+        t0 = time.perf_counter()
+        r.emit_omp(0, n_s, 0.0, False, True)
+        t1 = time.perf_counter()
+        # rows [0, rows) of the frame; the camera offset is applied like the product's cam_ox
+        r.render_f32(a.width, rows, 0.0, False, True, ox=-(a.width - a.height) / 2.0, oy=(a.height - rows) / 2.0, omp=True)
+        t2 = time.perf_counter()
+        kind = "reference"
+    else:
+        sc = orc.default_scene(sz_img=a.height)
+        sc.cam_ox = -(a.width - a.height) / 2.0
+        cores = 1
+        t0 = time.perf_counter()
+        grid, _, _ = orc.emit(sc, table, 0, n_s, 0.0, True, rng=st)
+        t1 = time.perf_counter()
+        y0 = (a.height - rows) // 2
+        orc.render(sc, grid, a.width, a.height, 0.0, False, True, y0=y0, y1=y0 + rows, want_u8=False)
+        t2 = time.perf_counter()
+        kind = "port"
+    emit_ms = (t1 - t0) * 1e3 * (a.photons / n_s)
+    render_ms = (t2 - t1) * 1e3 * (a.height / rows)
+    return emit_ms + render_ms, {
+        "kind": kind, "cores": cores,
+        "sample": "%d of %d photons traced (x%.0f) + %d of %d rows rendered (x%.0f), media on; %s" % (
+            n_s, a.photons, a.photons / n_s, rows, a.height, a.height / rows,
+            "reference routines (photonMappingKernel.cu:1-1521) as host C++ with OpenMP" if kind == "reference"
+            else "sequential oracle port (oracle/_ref absent)"),
+        "emit_ms_scaled": emit_ms, "render_ms_scaled": render_ms}
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    desc = None
+    for i in range(a.warmup + a.steps):
+        v, desc = cpu_reference_frame_ms(a, photon_div=64, row_div=16)
+        if i >= a.warmup:
+            vals.append(v)
+    v = float(np.mean(vals))
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "ms", "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": v, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(a),
+            "cpu_baseline": {"value": v, "unit": "ms", "cores": desc["cores"], "kind": desc["kind"], "sample": desc["sample"]},
+            "e2e": {"value": v, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------
+# the reference CUDA kernels on this GPU (B-CUDA): reported beside our number, not a target
+# ------------------------------------------------------------------------------------------------------
+def time_reference_cuda(a, table_host, dev_rgba):
+    path = os.path.join(ROOT, "oracle", "_ref", "libpmref_cuda_%d.so" % a.photons)
+    if not os.path.exists(path):
+        return {"unavailable": "oracle/_ref/libpmref_cuda_%d.so not built" % a.photons}
+    L = C.CDLL(path)
+    L.refcu_time_frames.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    assert L.refcu_capacity() == a.photons
+    assert L.refcu_set_table(table_host.ctypes.data_as(C.c_void_p), a.photons) == 0
+    assert L.refcu_set_szimg(a.height) == 0
+    e, r = C.c_float(), C.c_float()
+    rc = L.refcu_time_frames(C.c_void_p(dev_rgba.data_ptr()), a.width, a.height, 0.0, 0, 1, 1, 3, C.byref(e), C.byref(r))
+    if rc != 0:
+        return {"unavailable": "refcu_time_frames failed"}
+    return {"ms_per_frame": e.value + r.value, "emit_ms": e.value, "render_ms": r.value, "steps": 3, "warmup": 1,
+            "what": "photonMappingKernel.cu recompiled for sm_100a (nrPhotons=%d, szImg=%d), its own launchers, CUDA events"
+                    % (a.photons, a.height)}
+
+
+class _CudaArray:
+    """Wrap a raw device pointer for torch.as_tensor (zero copy) via __cuda_array_interface__."""
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference_arm(a)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import pmb200
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: pmb200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    W, H, NP = a.width, a.height, a.photons
+    assert H % world == 0, "rows must split evenly across ranks"
+
+    m = pmb200.PhotonMapper(device=local, n_photons=NP)
+    stream = torch.cuda.current_stream()
+    m.set_stream(stream.cuda_stream)
+    scene = pmb200.default_scene(sz_img=H)
+    scene.cam_ox = -(W - H) / 2.0
+    m.set_scene(scene)
+    m.set_energy_scale(10000.0 / NP)
+    m.init_random_numbers()                       # once, outside the timed region (callbacksPBO.cpp:55-58)
+    first, last = NP * rank // world, NP * (rank + 1) // world
+    m.set_photon_range(first, last)
+    rows = H // world
+    y0, y1 = rank * rows, (rank + 1) * rows
+
+    rgba = torch.zeros((H, W, 4), dtype=torch.uint8, device="cuda")
+    rgbf = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
+    acc_ptr, acc_n = m.accumulators()
+    acc = torch.as_tensor(_CudaArray(acc_ptr, acc_n, "<i8"), device="cuda")
+
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(a.steps)]
+
+    def step(e=None):
+        if e: e[0].record()
+        m.clear_map()
+        m.trace(0.0, media=True)
+        if e: e[1].record()
+        if world > 1:
+            dist.all_reduce(acc)                  # exact: int64 sum
+        if e: e[2].record()
+        m.build_map()
+        if e: e[3].record()
+        m.render_device(W, H, 0.0, False, True, rgba=rgba, rgbf=rgbf, y0=y0, y1=y1)
+        if world > 1:
+            dist.all_gather_into_tensor(rgba.view(-1), rgba[y0:y1].reshape(-1))
+            dist.all_gather_into_tensor(rgbf.view(-1), rgbf[y0:y1].reshape(-1))
+        if e: e[4].record()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler: sampler.start()
+    for _ in range(max(a.warmup, 3)):
+        step()
+    barrier()
+    launches0 = m.launch_count()
+    t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_beg.record()
+    for i in range(a.steps):
+        step(ev[i])
+    t_end.record()
+    barrier()
+    launches = m.launch_count() - launches0
+    total_ms = t_beg.elapsed_time(t_end)
+    if world > 1:
+        tt = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms = float(tt.item())
+    ms_per_step = total_ms / a.steps
+    stages = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(4)] for e in ev]).mean(0)
+
+    # ---- end to end through the C-ABI with HOST buffers (pinned): frame call + D2H of both framebuffers ----
+    h_rgba = torch.empty((H, W, 4), dtype=torch.uint8).pin_memory()
+    h_rgbf = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
+    e2e_steps = max(3, min(a.steps, 30))
+
+    def e2e_step():
+        m.set_scene(scene)                        # the frame's only host input: the scene / parameter block
+        if world == 1:
+            m.frame(W, H, 0.0, emit=True, interp=False, media=True, out_u8=h_rgba, out_f32=h_rgbf)
+        else:
+            step()
+            if rank == 0:
+                h_rgba.copy_(rgba, non_blocking=True); h_rgbf.copy_(rgbf, non_blocking=True)
+            torch.cuda.synchronize()
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    if world > 1:
+        tt = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tt.item())
+    clocks = sampler.stop() if sampler else None
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md 6.65 TB/s)"
+        trace_ms = float(stages[0])
+        n_local = last - first
+        trace_bytes = 12.0 * n_local              # algorithmic: one float3 direction per photon
+        achieved = trace_bytes / (trace_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": ms_per_step, "unit": "ms", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": workload_config(a, {"parallelism": "photon-range x%d + row-band x%d" % (world, world)}),
+            "photons_per_s": NP / (ms_per_step * 1e-3), "pixels_per_s": W * H / (ms_per_step * 1e-3),
+            "stages_ms": {"clear+trace": float(stages[0]), "allreduce": float(stages[1]), "build_map+tables": float(stages[2]),
+                          "render(+gather)": float(stages[3])},
+            "gpu_launches": int(launches),
+            "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": C.sizeof(pmb200.Scene),
+                    "d2h_bytes_per_step": W * H * 4 + W * H * 16, "steps": e2e_steps,
+                    "what": "pm_frame_host: scene struct in, emit+render, uchar4 + float4 frames copied to pinned host memory"},
+            "roofline": {"kernel": "trace_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": trace_bytes, "avg_launch_ms": trace_ms,
+                         "note": "Mode A trace keeps no photon records: 12 B/photon of compulsory HBM traffic; the kernel is "
+                                 "FP32/FP64-issue bound (see DESIGN.md, profiles/)"},
+            "clocks": clocks,
+        }
+        if not a.no_cpu_baseline and world == 1:
+            try:
+                v, d = cpu_reference_frame_ms(a)
+                line["cpu_baseline"] = {"value": v, "unit": "ms", "cores": d["cores"], "kind": d["kind"], "sample": d["sample"],
+                                        "emit_ms_scaled": d["emit_ms_scaled"], "render_ms_scaled": d["render_ms_scaled"]}
+            except Exception as ex:   # the baseline is reported, never required for the measurement itself
+                line["cpu_baseline"] = {"value": None, "unit": "ms", "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
+        if not a.no_ref_cuda and world == 1:
+            try:
+                line["reference_cuda_kernel"] = time_reference_cuda(a, m.get_random_table(), rgba)
+            except Exception as ex:
+                line["reference_cuda_kernel"] = {"unavailable": repr(ex)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

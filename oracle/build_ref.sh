@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # oracle/build_ref.sh -- TEST INFRASTRUCTURE.  Builds the reference's OWN hot file into oracle/_ref/:
 #   oracle/_ref/libpmref_host.so   photonMappingKernel.cu:1-1521 as host C++ (sequential oracle + OpenMP CPU baseline)
-#   oracle/_ref/libpmref_cuda.so   the whole photonMappingKernel.cu for sm_100a (reference CUDA kernel speed baseline)
+#   oracle/_ref/libpmref_cuda_<N>.so  the whole photonMappingKernel.cu for sm_100a with nrPhotons = N (reference CUDA kernel speed baseline)
 #
 # The reference source is compiled from where it lies (/root/reference, read-only).  It is streamed
 # through sed into a mktemp staging directory OUTSIDE the repository, compiled, and the staging
@@ -19,7 +19,6 @@ REF="${PM_REFERENCE_DIR:-/root/reference}"
 SRC="$REF/photonMappingKernel.cu"
 OUT="$HERE/_ref"
 CAP_HOST="${PM_REF_CAPACITY_HOST:-16777216}"
-CAP_CUDA="${PM_REF_CAPACITY_CUDA:-16777216}"
 if [ ! -f "$SRC" ]; then
   echo "build_ref.sh: $SRC not present (GPU box?) -- keeping prebuilt oracle/_ref/" >&2
   exit 0
@@ -45,12 +44,15 @@ g++ -O2 -fopenmp -ffp-contract=off -fPIC -shared -std=c++17 -w \
     "$HERE/ref_host_harness.cpp" -o "$OUT/libpmref_host.so"
 echo "built $OUT/libpmref_host.so"
 
-# ---- CUDA build (sm_100a) ------------------------------------------------------------------------
+# ---- CUDA builds (sm_100a): one library per photon count, because nrPhotons is compile-time in the reference ----
 if [ -f "$HERE/ref_cuda_harness.cu" ] && command -v nvcc >/dev/null 2>&1; then
   sed -e 's/^#define nrPhotons 10000/#define nrPhotons PM_REF_CAPACITY/' "$SRC" > "$TMP/pmk_cuda.inc"
   grep -q 'PM_REF_CAPACITY' "$TMP/pmk_cuda.inc"
-  nvcc -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -shared -w \
-       -I"$HERE" -I"$HERE/shim" -DPM_REF_CAPACITY="$CAP_CUDA" -DPM_REF_STAGED="\"$TMP/pmk_cuda.inc\"" \
-       "$HERE/ref_cuda_harness.cu" -o "$OUT/libpmref_cuda.so"
-  echo "built $OUT/libpmref_cuda.so"
+  for CAP in ${PM_REF_CAPACITIES_CUDA:-10000 1048576 16777216}; do
+    nvcc -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -shared -w -Xlinker -Bsymbolic \
+         -I"$HERE" -I"$HERE/shim" -DPM_REF_CAPACITY="$CAP" -DPM_REF_STAGED="\"$TMP/pmk_cuda.inc\"" \
+         "$HERE/ref_cuda_harness.cu" -o "$OUT/libpmref_cuda_$CAP.so" &
+  done
+  wait
+  ls "$OUT"/libpmref_cuda_*.so
 fi
