@@ -18,6 +18,7 @@ using namespace pm;
 
 struct pm_context {
   int device = 0;
+  int num_sms = 148;
   cudaStream_t stream = nullptr;
   std::string err;
 
@@ -27,7 +28,7 @@ struct pm_context {
   int64_t first = 0, last = 0;     // photon range traced by this context
   float energy_scale = 1.0f;
 
-  float *d_table = nullptr;
+  float4 *d_table = nullptr;       // one row per photon: (x, y, z, 0)
   int64_t table_cap = 0;
   uint32_t mwc_w = PM_MWC_SEED_W, mwc_z = PM_MWC_SEED_Z;
   MwcJump *d_jump = nullptr;
@@ -62,12 +63,8 @@ struct pm_context {
   } while (0)
 
 // ---- host-side MWC arithmetic (see pm_math.cuh MwcJump) ------------------------------------------------
-static uint32_t h_mulmod(uint32_t a, uint32_t b, uint32_t m) { return (uint32_t)(((unsigned long long)a * b) % m); }
-static uint32_t h_powmod(uint32_t a, unsigned long long e, uint32_t m) {
-  uint32_t r = 1;
-  while (e) { if (e & 1) r = h_mulmod(r, a, m); a = h_mulmod(a, a, m); e >>= 1; }
-  return r;
-}
+static uint32_t h_mulmod(uint32_t a, uint32_t b, uint32_t m) { return host_mulmod(a, b, m); }
+static uint32_t h_powmod(uint32_t a, unsigned long long e, uint32_t m) { return host_powmod(a, e, m); }
 // one MWC lane is x -> x * a mod (a*2^16 - 1): (2^16)^-1 == a because a*2^16 == 1 mod m
 static uint32_t h_lane_mult(int lane) { return lane == 0 ? 36969u : 18000u; }
 static uint32_t h_mwc_advance(int lane, uint32_t x, unsigned long long steps) {
@@ -155,6 +152,7 @@ int pm_create(pm_context **out, int device) {
   auto fail = [&](cudaError_t e) { fprintf(stderr, "pmb200: pm_create: %s\n", cudaGetErrorString(e)); delete c; return PM_ERR_CUDA; };
   cudaError_t e;
   if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(e);
+  if ((e = cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&c->d_acc, sizeof(long long) * kAccEntries)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&c->d_grid, sizeof(float) * PM_GRID_FLOATS)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&c->d_vol, sizeof(float4) * kVolTableEntries)) != cudaSuccess) return fail(e);
@@ -224,11 +222,11 @@ int pm_set_photon_count(pm_context *c, int64_t n) {
   if (n > c->table_cap) {
     CK(c, cudaStreamSynchronize(c->stream));
     cudaFree(c->d_table); c->d_table = nullptr; c->table_cap = 0;
-    CK(c, cudaMalloc(&c->d_table, sizeof(float) * 3 * (size_t)n));
+    CK(c, cudaMalloc(&c->d_table, sizeof(float4) * (size_t)n));
     c->table_cap = n;
   }
   // the reference's table is zero-initialised device memory until launch_init_random_numbers_kernel runs
-  CK(c, cudaMemsetAsync(c->d_table, 0, sizeof(float) * 3 * (size_t)n, c->stream));
+  CK(c, cudaMemsetAsync(c->d_table, 0, sizeof(float4) * (size_t)n, c->stream));
   c->n_photons = n; c->first = 0; c->last = n;
   return PM_OK;
 }
@@ -265,7 +263,9 @@ int pm_set_random_table_host(pm_context *c, const float *xyz, int64_t n) {
   ARG(c, c && xyz, "null argument");
   ARG(c, n == c->n_photons, "table length must equal the photon count");
   CK(c, cudaSetDevice(c->device));
-  CK(c, cudaMemcpyAsync(c->d_table, xyz, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  std::vector<float4> rows((size_t)n);
+  for (int64_t i = 0; i < n; i++) rows[i] = make_float4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], 0.0f);
+  CK(c, cudaMemcpyAsync(c->d_table, rows.data(), sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));
   return PM_OK;
 }
@@ -273,8 +273,10 @@ int pm_get_random_table_host(pm_context *c, float *xyz, int64_t n) {
   ARG(c, c && xyz, "null argument");
   ARG(c, n >= 0 && n <= c->n_photons, "table length exceeds the photon count");
   CK(c, cudaSetDevice(c->device));
-  CK(c, cudaMemcpyAsync(xyz, c->d_table, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  std::vector<float4> rows((size_t)n);
+  CK(c, cudaMemcpyAsync(rows.data(), c->d_table, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));
+  for (int64_t i = 0; i < n; i++) { xyz[3 * i] = rows[i].x; xyz[3 * i + 1] = rows[i].y; xyz[3 * i + 2] = rows[i].z; }
   return PM_OK;
 }
 
@@ -308,9 +310,11 @@ int pm_trace(pm_context *c, float t, unsigned flags) {
   if ((flags & PM_TRACE_RECORDS) && c->rec_cap == 0) { c->err = "PM_TRACE_RECORDS needs pm_set_record_capacity first"; return PM_ERR_STATE; }
   CK(c, cudaSetDevice(c->device));
   c->dsc = make_device_scene(c->scene, t);
-  CK(c, launch_trace(c->dsc, c->d_table, c->first, c->last, flags, c->mwc_w, c->mwc_z, c->d_jump,
-                     (unsigned long long *)c->d_acc, c->d_rec_pos, c->d_rec_pow, c->d_rec_dir, c->d_rec_count, c->rec_cap, c->stream));
-  if (c->last > c->first) c->launches++;
+  cudaError_t terr = cudaSuccess;
+  c->launches += launch_trace(c->dsc, c->d_table, c->first, c->last, flags, c->mwc_w, c->mwc_z, c->d_jump,
+                              (unsigned long long *)c->d_acc, c->d_rec_pos, c->d_rec_pow, c->d_rec_dir, c->d_rec_count,
+                              c->rec_cap, c->num_sms, c->stream, &terr);
+  CK(c, terr);
   if (flags & PM_TRACE_MEDIA) {   // the medium scattering consumed 9 draws per photon of the WHOLE job
     unsigned long long draws = 9ull * (unsigned long long)c->n_photons;
     c->mwc_z = h_mwc_advance(0, c->mwc_z, draws);

@@ -8,12 +8,20 @@
 
 namespace pm {
 
+// host-side MWC arithmetic: one MWC lane is x -> x * a mod (a*2^16 - 1)  (see pm_math.cuh MwcJump)
+inline uint32_t host_mulmod(uint32_t a, uint32_t b, uint32_t m) { return (uint32_t)(((unsigned long long)a * b) % m); }
+inline uint32_t host_powmod(uint32_t a, unsigned long long e, uint32_t m) {
+  uint32_t r = 1;
+  while (e) { if (e & 1) r = host_mulmod(r, a, m); a = host_mulmod(a, a, m); e >>= 1; }
+  return r;
+}
+
 // pm_trace.cu
-cudaError_t launch_mwc_table(float *table, long long n, uint32_t w0, uint32_t z0, const MwcJump *J, cudaStream_t st);
-cudaError_t launch_trace(const DeviceScene &sc, const float *table, long long first, long long last, unsigned flags,
-                         uint32_t w0, uint32_t z0, const MwcJump *J, unsigned long long *acc, float4 *rec_pos,
-                         float4 *rec_pow, float4 *rec_dir, unsigned long long *rec_count, long long rec_cap,
-                         cudaStream_t st);
+cudaError_t launch_mwc_table(float4 *table, long long n, uint32_t w0, uint32_t z0, const MwcJump *J, cudaStream_t st);
+// returns the number of kernels launched; *err receives the CUDA status
+int launch_trace(const DeviceScene &sc, const float4 *table, long long first, long long last, unsigned flags, uint32_t w0,
+                 uint32_t z0, const MwcJump *J, unsigned long long *acc, float4 *rec_pos, float4 *rec_pow, float4 *rec_dir,
+                 unsigned long long *rec_count, long long rec_cap, int num_sms, cudaStream_t st, cudaError_t *err);
 
 // pm_map.cu
 cudaError_t launch_build_map(const long long *acc, float energy_scale, float *grid, cudaStream_t st);

@@ -13,9 +13,12 @@ namespace pm {
 // acc_vox[x][y][z][rgb]              : everything that is deposited straight into a voxel: volume photons
 //                                      (5e-5*rgb) and the fully expanded splat of the rare off-slab hit
 //                                      (scale 2^36)
+// acc_grey[x][y][z]                  : deposits with r == g == b (every volume photon of the reference's medium
+//                                      walk): one atomic instead of three; added to all three channels (scale 2^36)
 constexpr int    kAccHitEntries = PM_MAX_PLANES * PM_GRID_N * PM_GRID_N * 3;   // 15 360
 constexpr int    kAccVoxEntries = PM_GRID_VOXELS * 3;                          // 98 304
-constexpr int    kAccEntries    = kAccHitEntries + kAccVoxEntries;             // 113 664 int64 = 909 312 B
+constexpr int    kAccGreyEntries = PM_GRID_VOXELS;                             // 32 768
+constexpr int    kAccEntries    = kAccHitEntries + kAccVoxEntries + kAccGreyEntries;   // 146 432 int64 = 1 171 456 B
 constexpr double kHitScale      = 16777216.0;          // 2^24
 constexpr double kVoxScale      = 68719476736.0;       // 2^36
 

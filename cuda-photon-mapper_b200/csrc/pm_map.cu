@@ -30,7 +30,8 @@ __global__ void __launch_bounds__(128) build_map_kernel(const long long *__restr
   if (v >= PM_GRID_VOXELS) return;
   int z = v % PM_GRID_N, y = (v / PM_GRID_N) % PM_GRID_N, x = v / (PM_GRID_N * PM_GRID_N);
   const long long *vox = acc + kAccHitEntries + 3 * v;
-  double s0 = (double)vox[0] / kVoxScale, s1 = (double)vox[1] / kVoxScale, s2 = (double)vox[2] / kVoxScale;
+  const long long grey = acc[kAccHitEntries + kAccVoxEntries + v];
+  double s0 = (double)(vox[0] + grey) / kVoxScale, s1 = (double)(vox[1] + grey) / kVoxScale, s2 = (double)(vox[2] + grey) / kVoxScale;
   const double w05 = (double)0.05f / kHitScale;
   for (int id = 0; id < PM_MAX_PLANES; id++) {
     int on, a, b;

@@ -1,13 +1,20 @@
 // pm_trace.cu -- stage 1: random-direction table + photon emission/tracing (sm_100a).
 //
 // Replaces init_random_numbers_kernel (PMK:1483-1498), init_photons_kernel (PMK:1503-1521) and
-// emit_photons_kernel/emitPhotons (PMK:1464-1480, :1215-1375).  One thread per photon, identical FP32
-// operation order to the sequential oracle (pm_math.cuh), but:
+// emit_photons_kernel/emitPhotons (PMK:1464-1480, :1215-1375).  Per photon the FP32 operation order is
+// identical to the sequential oracle (pm_math.cuh), but the work is organised for the hardware:
 //   * the MWC generator is index-addressed (jump-ahead), so the table fill and the medium-scatter draws are
 //     fully parallel yet bit-identical to the reference's serial stream;
+//   * the medium walk (3 fixed steps, PMK:1239-1272) does not influence the surface walk, so it runs as its
+//     own fully convergent kernel (volume_kernel);
+//   * the surface walk (surface_kernel) is a persistent kernel, one CTA per SM: every lane runs a small state
+//     machine with ONE ray-scene intersection site per iteration, and a lane that finishes its photon is
+//     refilled from its warp's contiguous photon range.  Primary rays, shadow rays, wall bounces and the
+//     mirror/glass chain therefore share the same instructions instead of diverging (the first version of
+//     this kernel ran 17 of 32 lanes on average and stalled on instruction fetch);
 //   * deposits go into exact int64 fixed-point accumulators keyed by wall voxel (pm_layout.h) instead of
-//     ~65 racy float RMWs per photon: the 6x6 splat stencil is linear, so it is applied once per voxel in
-//     pm_map.cu rather than once per photon;
+//     ~65 racy float RMWs per photon; the accumulators are privatised per CTA in shared memory (123 KB, split
+//     into 32-bit halves because shared memory has no native 64-bit add) and flushed once per CTA;
 //   * photon records (Mode B) are appended to SoA float4 buffers with warp-aggregated atomics.
 #include "pm_kernels.cuh"
 
@@ -16,7 +23,7 @@ namespace pm {
 // ------------------------------------------------------------------------------------------------------
 // random table: thread i owns draws 3i..3i+2 of the stream that starts at (w0,z0); rand3 order x,y,z
 // ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) mwc_table_kernel(float *__restrict__ table, long long n, uint32_t w0, uint32_t z0,
+__global__ void __launch_bounds__(256) mwc_table_kernel(float4 *__restrict__ table, long long n, uint32_t w0, uint32_t z0,
                                                         const MwcJump *__restrict__ J) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -25,11 +32,11 @@ __global__ void __launch_bounds__(256) mwc_table_kernel(float *__restrict__ tabl
   s.z = mwc_jump(J, 0, z0, steps);
   s.w = mwc_jump(J, 1, w0, steps);
   float x = rand_float(s, 1.0f), y = rand_float(s, 1.0f), z = rand_float(s, 1.0f);
-  table[3 * i + 0] = x; table[3 * i + 1] = y; table[3 * i + 2] = z;
+  table[i] = make_float4(x, y, z, 0.0f);
 }
 
 // ------------------------------------------------------------------------------------------------------
-// deposits
+// record sink
 // ------------------------------------------------------------------------------------------------------
 struct Sink {
   unsigned long long *acc;       // kAccEntries, or nullptr (PM_TRACE_NO_MAP)
@@ -58,8 +65,80 @@ __device__ __forceinline__ void append_record(const Sink &sk, int seq, int kind,
   }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// medium walk: PMK:1239-1272 + storeVolumePhoton PMK:1147-1161.  Grid-stride, no divergence, coalesced float4
+// table rows.  Photon `index` owns draws [9*index, 9*index+9) of the MWC stream that starts at (w0,z0): a thread
+// jumps to its first photon once (table look-ups) and then advances by the grid stride with one modular
+// multiplication per lane (cz, cw = a^(9*stride) mod m, computed by the launcher).
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) volume_kernel(const __grid_constant__ DeviceScene sc, const float4 *__restrict__ table,
+                                                     long long first, long long last, unsigned flags, uint32_t w0, uint32_t z0,
+                                                     const MwcJump *__restrict__ J, uint32_t cw, uint32_t cz, Sink sk) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long gi = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= last) return;
+  const bool rec = (flags & PM_TRACE_RECORDS) != 0;
+  const v3 light = V(sc.light[0], sc.light[1], sc.light[2]);
+  Mwc base;
+  base.z = mwc_jump(J, 0, z0, 9u * (uint32_t)gi);
+  base.w = mwc_jump(J, 1, w0, 9u * (uint32_t)gi);
+  // randomNumbers[i], i = 0..2 (sic, PMK:1258): the same three table rows scale every photon's draws
+  const float4 t0 = __ldg(table + 0), t1 = __ldg(table + 1), t2 = __ldg(table + 2);
+  for (; gi < last; gi += stride) {
+    const int index = (int)gi;
+    const float4 td = __ldg(table + gi);
+    v3 rgb = V(10.0f, 10.0f, 10.0f);
+    v3 ray = normalize(V(td.x, td.y, td.z));
+    v3 prev = light;
+    Mwc s = base;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      rgb = subs(rgb, 1.0f);
+      v3 P = add(mul(ray, 1.0f), prev);
+      v3 e = mul(rgb, 0.00005f);
+      if (sk.acc) {
+        int vx = clampi(voxel_x(P.x)), vy = clampi(voxel_x(P.y)), vz = clampi(voxel_z(P.z));
+        int v = (vx * PM_GRID_N + vy) * PM_GRID_N + vz;
+        if (e.x == e.y && e.y == e.z) {   // always true on this path: one atomic instead of three
+          acc_add(sk.acc + kAccHitEntries + kAccVoxEntries + v, __double2ll_rn((double)e.x * kVoxScale));
+        } else {
+          unsigned long long *p = sk.acc + kAccHitEntries + 3 * v;
+          acc_add(p + 0, __double2ll_rn((double)e.x * kVoxScale));
+          acc_add(p + 1, __double2ll_rn((double)e.y * kVoxScale));
+          acc_add(p + 2, __double2ll_rn((double)e.z * kVoxScale));
+        }
+      }
+      if (rec) append_record(sk, i, 1, -1, -1, index, P, V(0.0f, 0.0f, 0.0f), e);
+      const float4 tr = i == 0 ? t0 : (i == 1 ? t1 : t2);
+      v3 r;
+      r.x = rand_float(s, tr.x);
+      r.y = rand_float(s, tr.y);
+      r.z = rand_float(s, tr.z);
+      ray = normalize(r);
+      prev = P;
+    }
+    base.z = mulmod(base.z, cz, mwc_modulus(0));
+    base.w = mulmod(base.w, cw, mwc_modulus(1));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// surface walk
+// ------------------------------------------------------------------------------------------------------
+// CTA-private accumulator for on-slab wall hits: kAccHitEntries x (lo, hi) 32-bit halves in shared memory.
+struct SmemAcc {
+  uint32_t *lo, *hi;
+  __device__ __forceinline__ void add(int e, long long v) {
+    if (v == 0) return;
+    uint32_t vlo = (uint32_t)v, vhi = (uint32_t)((unsigned long long)v >> 32);
+    uint32_t old = atomicAdd(lo + e, vlo);
+    uint32_t h = vhi + ((uint32_t)(old + vlo) < old ? 1u : 0u);   // carry out of the low half, counted exactly once
+    if (h) atomicAdd(hi + e, h);
+  }
+};
+
 // storePhoton + splatEnergy + storeNeighborPhoton, PMK:1059-1144, :1164-1183 (type 0 = sphere: nothing is stored)
-__device__ __forceinline__ void store_photon(const Sink &sk, int type, int id, v3 loc, v3 e) {
+__device__ __forceinline__ void store_photon(const Sink &sk, SmemAcc &sa, int type, int id, v3 loc, v3 e) {
   if (!sk.acc || type == 0) return;
   int vx = clampi(voxel_x(loc.x)), vy = clampi(voxel_x(loc.y)), vz = clampi(voxel_z(loc.z));
   int a, b, on_slab;
@@ -71,11 +150,11 @@ __device__ __forceinline__ void store_photon(const Sink &sk, int type, int id, v
     case 4: on_slab = vz == PM_GRID_N - 1; a = vx; b = vy; break;
     default: on_slab = -1; a = b = 0; break;
   }
-  if (on_slab == 1) {   // the common case: keyed energy sum, stencil applied later
-    unsigned long long *p = sk.acc + ((id * PM_GRID_N + a) * PM_GRID_N + b) * 3;
-    acc_add(p + 0, __float2ll_rn(e.x * (float)kHitScale));
-    acc_add(p + 1, __float2ll_rn(e.y * (float)kHitScale));
-    acc_add(p + 2, __float2ll_rn(e.z * (float)kHitScale));
+  if (on_slab == 1) {   // the common case: keyed energy sum, the 6x6 stencil is applied once per voxel in pm_map.cu
+    int en = ((id * PM_GRID_N + a) * PM_GRID_N + b) * 3;
+    sa.add(en + 0, __float2ll_rn(e.x * (float)kHitScale));
+    sa.add(en + 1, __float2ll_rn(e.y * (float)kHitScale));
+    sa.add(en + 2, __float2ll_rn(e.z * (float)kHitScale));
     return;
   }
   // rare: the clamped voxel is off the wall's slab (a wall that is not on the map boundary): expand per photon
@@ -109,16 +188,6 @@ __device__ __forceinline__ void store_photon(const Sink &sk, int type, int id, v
       }
 }
 
-// storeVolumePhoton, PMK:1147-1161
-__device__ __forceinline__ void store_volume(const Sink &sk, v3 loc, v3 e) {
-  if (!sk.acc) return;
-  int vx = clampi(voxel_x(loc.x)), vy = clampi(voxel_x(loc.y)), vz = clampi(voxel_z(loc.z));
-  unsigned long long *p = sk.acc + kAccHitEntries + ((vx * PM_GRID_N + vy) * PM_GRID_N + vz) * 3;
-  acc_add(p + 0, __double2ll_rn((double)e.x * kVoxScale));
-  acc_add(p + 1, __double2ll_rn((double)e.y * kVoxScale));
-  acc_add(p + 2, __double2ll_rn((double)e.z * kVoxScale));
-}
-
 // getColor / filterColor, PMK:605-617
 __device__ __forceinline__ v3 get_color(v3 in, int type, int idx) {
   v3 m = V(1.0f, 1.0f, 1.0f);
@@ -127,119 +196,200 @@ __device__ __forceinline__ v3 get_color(v3 in, int type, int idx) {
   return V(fminf(m.x, in.x), fminf(m.y, in.y), fminf(m.z, in.z));
 }
 
-// ------------------------------------------------------------------------------------------------------
-// emitPhotons, PMK:1215-1375 -- one thread per photon index in [first, last)
-// ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ DeviceScene sc, const float *__restrict__ table,
-                                                    long long first, long long last, unsigned flags,
-                                                    uint32_t w0, uint32_t z0, const MwcJump *__restrict__ J, Sink sk) {
-  long long gi = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gi >= last) return;
-  const int index = (int)gi;
+// lane states: what the NEXT intersection result means for this lane
+enum : int { ST_IDLE = 0, ST_PRIMARY, ST_SHADOW, ST_CHAIN_R, ST_CHAIN_F1, ST_CHAIN_F2 };
+
+constexpr int kSurfaceThreads = 1024;
+constexpr int kRefillLanes = 8;
+constexpr size_t kSurfaceSmem = sizeof(uint32_t) * 2 * kAccHitEntries;   // 122 880 B
+
+__global__ void __launch_bounds__(kSurfaceThreads, 1) surface_kernel(const __grid_constant__ DeviceScene sc,
+                                                                     const float4 *__restrict__ table, long long first, long long last,
+                                                                     unsigned flags, Sink sk) {
+  extern __shared__ uint32_t smem_u32[];
+  SmemAcc sa;
+  sa.lo = smem_u32; sa.hi = smem_u32 + kAccHitEntries;
+  for (int i = threadIdx.x; i < 2 * kAccHitEntries; i += blockDim.x) smem_u32[i] = 0u;
+  __syncthreads();
+
   const bool media = flags & PM_TRACE_MEDIA;
   const bool rec = (flags & PM_TRACE_RECORDS) != 0;
-  int seq = 0;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  // each warp owns a contiguous slice of the photon range; lanes are refilled from it
+  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+  const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long per = (last - first + warps - 1) / warps;
+  long long cur = first + gw * per;
+  long long end = cur + per < last ? cur + per : last;
+  if (cur > end) cur = end;
 
-  int bounces = 1;
-  v3 rgb = V(10.0f, 10.0f, 10.0f);
   const v3 light = V(sc.light[0], sc.light[1], sc.light[2]);
-  const v3 tdir = V(table[3 * gi], table[3 * gi + 1], table[3 * gi + 2]);
-  v3 ray = normalize(tdir);
-  const v3 original = ray;
-  v3 prev = light, P = V(0.0f, 0.0f, 0.0f);
+  int state = ST_IDLE, index = 0, seq = 0, bounces = 1, level = 1, t_type = 0, t_idx = 0;
+  bool caustics = false, new_point = true, chain_glass = false;
+  v3 rgb = V(0.0f, 0.0f, 0.0f), ray = rgb, prev = rgb, P = rgb, org = rgb;
   Hit h; h.hit = 0; h.type = 0; h.idx = 0; h.dist = -1.0f;
 
-  if (media) {   // PMK:1239-1272: 3 unit steps, deposit 5e-5*rgb, re-direct with 9 MWC draws (stream position 9*index)
-    Mwc s;
-    s.z = mwc_jump(J, 0, z0, 9u * (uint32_t)index);
-    s.w = mwc_jump(J, 1, w0, 9u * (uint32_t)index);
-#pragma unroll 1
-    for (int i = 0; i < 3; i++) {
-      rgb = subs(rgb, 1.0f);
-      P = add(mul(ray, 1.0f), prev);
-      v3 e = mul(rgb, 0.00005f);
-      store_volume(sk, P, e);
-      if (rec) append_record(sk, seq, 1, -1, -1, index, P, V(0.0f, 0.0f, 0.0f), e);
-      seq++;
-      v3 r;   // randomize(randomNumbers[i]), i = 0..2 (sic), PMK:1258
-      r.x = rand_float(s, table[3 * i + 0]);
-      r.y = rand_float(s, table[3 * i + 1]);
-      r.z = rand_float(s, table[3 * i + 2]);
-      ray = normalize(r);
-      prev = P;
+  for (;;) {
+    // ---- refill idle lanes from the warp's slice (emitPhotons prologue, PMK:1229-1237, :1274-1280).  The prologue
+    //      runs with only the idle lanes active, so it is deferred until a quarter of the warp is idle ----
+    unsigned idle = __ballot_sync(0xffffffffu, state == ST_IDLE);
+    if (cur < end && (__popc(idle) >= kRefillLanes || idle == 0xffffffffu)) {
+      long long cand = cur + __popc(idle & lt_mask);
+      if (state == ST_IDLE && cand < end) {
+        index = (int)cand;
+        const float4 td = __ldg(table + cand);
+        ray = normalize(V(td.x, td.y, td.z));
+        rgb = media ? V(7.0f, 7.0f, 7.0f) : V(10.0f, 10.0f, 10.0f);   // the medium walk leaves rgb = 10-1-1-1
+        if (index < 100) {   // CAUSTICS_PHOTONS: aimed at the glass sphere, jittered, not re-normalised
+          v3 aim = normalize(sub(V(sc.sph[0][0], sc.sph[0][1], sc.sph[0][2]), light));
+          ray = add(aim, mul(ray, 0.01f));
+        }
+        prev = light; org = light;
+        bounces = 1; seq = media ? 3 : 0;
+        caustics = false; new_point = true;
+        h.type = 0; h.idx = 0;
+        state = ST_PRIMARY;
+      }
+      cur += __popc(idle);
+      if (cur > end) cur = end;
     }
-    ray = original; prev = light;
-  }
-  if (index < 100) {   // CAUSTICS_PHOTONS, PMK:1274-1278: aimed at the glass sphere, jittered, not re-normalised
-    ray = normalize(sub(V(sc.sph[0][0], sc.sph[0][1], sc.sph[0][2]), light));
-    ray = add(ray, mul(normalize(tdir), 0.01f));
-  }
-  raytrace(sc, ray, prev, h);
+    if (__ballot_sync(0xffffffffu, state != ST_IDLE) == 0u) {
+      if (cur >= end) break;
+      continue;
+    }
+    if (state == ST_IDLE) continue;
 
-  bool caustics = false, new_point = true;
-#pragma unroll 1
-  while (h.hit && bounces <= 5) {
-    if (new_point) P = add(mul(ray, h.dist), prev);
-    if (caustics) {
-      rgb = mul(V(1.0f, 1.0f, 1.0f), 10.0f);
-      store_photon(sk, h.type, h.idx, P, rgb);
-      if (rec) append_record(sk, seq, 0, h.type, h.idx, index, P, ray, rgb);
-      seq++;
-    } else {
-      rgb = mul(divs(mul(get_color(rgb, h.type, h.idx), 1.0f), __fsqrt_rn((float)bounces)), 5.0f);
-      store_photon(sk, h.type, h.idx, P, rgb);
-      if (rec) append_record(sk, seq, 0, h.type, h.idx, index, P, ray, rgb);
-      seq++;
-      {   // shadowPhoton, PMK:1185-1196: continue the same ray, deposit -0.25 at the next hit; dist/hit are not restored
-        int t_type = h.type, t_idx = h.idx;
-        v3 bumped = add(P, mul(ray, 0.00001f));
-        raytrace(sc, ray, bumped, h);
-        v3 sp = add(mul(ray, h.dist), bumped);
-        v3 se = V(-0.25f, -0.25f, -0.25f);
-        store_photon(sk, h.type, h.idx, sp, se);
-        if (rec) append_record(sk, seq, 0, h.type, h.idx, index, sp, ray, se);
-        seq++;
-        h.type = t_type; h.idx = t_idx;
+    // ---- the single intersection site ----
+    raytrace(sc, ray, org, h);
+
+    // ---- mirror / glass chain: handleReflection/handleRefraction{,2,3,4}, PMK:673-827 ----
+    if (state >= ST_CHAIN_R) {
+      bool chain_done = false;
+      if (state == ST_CHAIN_R) {
+        if (!h.hit) chain_done = true;
+        else {
+          P = add(mul(ray, h.dist), P);
+          if (!(h.type == 0 && h.idx == 0)) chain_done = true;
+          else {
+            ray = refract3(sc, ray, P, h.type, h.idx, P, 1.0f);
+            P = add(mul(ray, 0.00001f), P);
+            org = P; state = ST_CHAIN_F1;
+          }
+        }
+      } else if (state == ST_CHAIN_F1) {
+        P = add(mul(ray, h.dist), P);   // executed even on a miss
+        if (!(h.hit && h.type == 0 && h.idx == 0)) chain_done = true;
+        else {
+          ray = refract3(sc, ray, P, h.type, h.idx, P, -1.0f);
+          P = add(mul(ray, 0.00001f), P);
+          org = P; state = ST_CHAIN_F2;
+        }
+      } else {   // ST_CHAIN_F2
+        P = add(mul(ray, h.dist), P);
+        if (level == 4 || !(h.type == 0 && h.idx == 1)) chain_done = true;   // not gated on h.hit: stale ids, as PMK:807
+        else {
+          level++;
+          ray = reflect3(sc, ray, prev, h.type, h.idx, P);
+          org = P; state = ST_CHAIN_R;
+        }
+      }
+      if (!chain_done) continue;
+      caustics = chain_glass; new_point = false; bounces++;
+      state = ST_PRIMARY;   // falls through: the while-condition is evaluated on the chain's last intersection
+    }
+
+    // ---- both remaining states deposit one photon at the intersection just found (single store site) ----
+    v3 loc, e;
+    if (state == ST_PRIMARY) {   // top of the bounce loop, PMK:1289-1301
+      if (!(h.hit && bounces <= 5)) { state = ST_IDLE; continue; }
+      if (new_point) P = add(mul(ray, h.dist), prev);
+      if (caustics) rgb = mul(V(1.0f, 1.0f, 1.0f), 10.0f);
+      else rgb = mul(divs(mul(get_color(rgb, h.type, h.idx), 1.0f), __fsqrt_rn((float)bounces)), 5.0f);
+      loc = P; e = rgb;
+    } else {                     // shadowPhoton, PMK:1185-1196: -0.25 at the next hit along the same ray
+      loc = add(mul(ray, h.dist), org);
+      e = V(-0.25f, -0.25f, -0.25f);
+    }
+    store_photon(sk, sa, h.type, h.idx, loc, e);
+    if (rec) append_record(sk, seq, 0, h.type, h.idx, index, loc, ray, e);
+    seq++;
+    if (state == ST_PRIMARY && !caustics) {
+      t_type = h.type; t_idx = h.idx;
+      org = add(P, mul(ray, 0.00001f));   // the shadow ray starts just beyond the hit
+      state = ST_SHADOW;
+      continue;
+    }
+    if (state == ST_SHADOW) { h.type = t_type; h.idx = t_idx; }   // dist/hit stay clobbered, as in the reference
+    const bool post = true;
+    if (post) {   // PMK:1305-1370: where does the photon go next
+      prev = P;
+      if (h.type == 0 && h.idx == 1) {          // mirror sphere
+        chain_glass = false; level = 1;
+        ray = reflect3(sc, ray, prev, h.type, h.idx, P);
+        org = P; state = ST_CHAIN_R;
+      } else if (h.type == 0 && h.idx == 0) {   // glass sphere
+        chain_glass = true; level = 1;
+        ray = refract3(sc, ray, P, h.type, h.idx, P, 1.0f);
+        P = add(mul(ray, 0.00001f), P);
+        org = P; state = ST_CHAIN_F1;
+      } else {                                   // diffuse wall (prev == hit point: hazard H1)
+        ray = reflect3(sc, ray, prev, h.type, h.idx, P);
+        org = P;
+        caustics = false; new_point = true; bounces++;
+        state = ST_PRIMARY;
       }
     }
-    prev = P;
-    if (h.type == 0 && h.idx == 1) {          // mirror sphere
-      follow_specular(sc, ray, prev, h, P, 1);
-      caustics = false; new_point = false;
-    } else if (h.type == 0 && h.idx == 0) {   // glass sphere
-      follow_specular(sc, ray, prev, h, P, 0);
-      caustics = true; new_point = false;
-    } else {                                   // diffuse wall (prev == hit point: hazard H1)
-      ray = reflect3(sc, ray, prev, h.type, h.idx, P);
-      raytrace(sc, ray, P, h);
-      caustics = false; new_point = true;
+  }
+
+  // ---- flush the CTA-private accumulators ----
+  __syncthreads();
+  if (sk.acc) {
+    for (int e = threadIdx.x; e < kAccHitEntries; e += blockDim.x) {
+      unsigned long long v = (unsigned long long)sa.lo[e] | ((unsigned long long)sa.hi[e] << 32);
+      if (v) atomicAdd(sk.acc + e, v);
     }
-    bounces++;
   }
 }
 
 // ------------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------------
-cudaError_t launch_mwc_table(float *table, long long n, uint32_t w0, uint32_t z0, const MwcJump *J, cudaStream_t st) {
+cudaError_t launch_mwc_table(float4 *table, long long n, uint32_t w0, uint32_t z0, const MwcJump *J, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   unsigned blocks = (unsigned)((n + 255) / 256);
   mwc_table_kernel<<<blocks, 256, 0, st>>>(table, n, w0, z0, J);
   return cudaGetLastError();
 }
 
-cudaError_t launch_trace(const DeviceScene &sc, const float *table, long long first, long long last, unsigned flags,
-                         uint32_t w0, uint32_t z0, const MwcJump *J, unsigned long long *acc, float4 *rec_pos,
-                         float4 *rec_pow, float4 *rec_dir, unsigned long long *rec_count, long long rec_cap,
-                         cudaStream_t st) {
+int launch_trace(const DeviceScene &sc, const float4 *table, long long first, long long last, unsigned flags, uint32_t w0,
+                 uint32_t z0, const MwcJump *J, unsigned long long *acc, float4 *rec_pos, float4 *rec_pow, float4 *rec_dir,
+                 unsigned long long *rec_count, long long rec_cap, int num_sms, cudaStream_t st, cudaError_t *err) {
+  *err = cudaSuccess;
   long long n = last - first;
-  if (n <= 0) return cudaSuccess;
+  if (n <= 0) return 0;
   Sink sk;
   sk.acc = (flags & PM_TRACE_NO_MAP) ? nullptr : acc;
   sk.rec_pos = rec_pos; sk.rec_pow = rec_pow; sk.rec_dir = rec_dir; sk.rec_count = rec_count; sk.rec_cap = rec_cap;
-  unsigned blocks = (unsigned)((n + 255) / 256);
-  trace_kernel<<<blocks, 256, 0, st>>>(sc, table, first, last, flags, w0, z0, J, sk);
-  return cudaGetLastError();
+  int launches = 0;
+  if (flags & PM_TRACE_MEDIA) {
+    long long want = (n + 255) / 256, cap = (long long)num_sms * 8;
+    unsigned blocks = (unsigned)(want < cap ? want : cap);
+    unsigned long long steps = 9ull * blocks * 256ull;
+    volume_kernel<<<blocks, 256, 0, st>>>(sc, table, first, last, flags, w0, z0, J, host_powmod(18000u, steps, mwc_modulus(1)),
+                                          host_powmod(36969u, steps, mwc_modulus(0)), sk);
+    launches++;
+    if ((*err = cudaGetLastError()) != cudaSuccess) return launches;
+  }
+  *err = cudaFuncSetAttribute(surface_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSurfaceSmem);
+  if (*err != cudaSuccess) return launches;
+  long long warps_needed = (n + 31) / 32;
+  long long ctas = (warps_needed + (kSurfaceThreads / 32) - 1) / (kSurfaceThreads / 32);
+  unsigned grid = (unsigned)(ctas < num_sms ? ctas : num_sms);
+  surface_kernel<<<grid, kSurfaceThreads, kSurfaceSmem, st>>>(sc, table, first, last, flags, sk);
+  launches++;
+  *err = cudaGetLastError();
+  return launches;
 }
 
 }  // namespace pm
