@@ -7,18 +7,20 @@
 namespace pm {
 
 // ---- exact accumulators (int64 fixed point; order-independent, so bit-reproducible for any GPU count) -----
-// acc_hit[plane id 0..4][a][b][rgb]  : energy of wall hits whose clamped voxel lies on that wall's slab,
+// acc_hit[plane id 0..4][a][b][r,g,b,grey] : energy of wall hits whose clamped voxel lies on that wall's slab,
 //                                      keyed by the two in-plane voxel coordinates (scale 2^24: every energy
-//                                      the reference produces -- 10, 5/sqrt(b), -0.25 -- is exact)
-// acc_vox[x][y][z][rgb]              : everything that is deposited straight into a voxel: volume photons
-//                                      (5e-5*rgb) and the fully expanded splat of the rare off-slab hit
-//                                      (scale 2^36)
-// acc_grey[x][y][z]                  : deposits with r == g == b (every volume photon of the reference's medium
-//                                      walk): one atomic instead of three; added to all three channels (scale 2^36)
-constexpr int    kAccHitEntries = PM_MAX_PLANES * PM_GRID_N * PM_GRID_N * 3;   // 15 360
+//                                      the reference produces -- 10, 5/sqrt(b), -0.25 -- is exact).  A deposit with
+//                                      r == g == b goes to the grey slot (one atomic instead of three)
+// acc_vox[x][y][z][rgb]              : everything that is deposited straight into a voxel with unequal channels,
+//                                      and the fully expanded splat of the rare off-slab hit (scale 2^36)
+// acc_grey[replica][x][y][z]         : straight deposits with r == g == b -- every volume photon of the reference's
+//                                      medium walk (scale 2^36).  Replicated kGreyReplicas times (a CTA picks a replica
+//                                      by its index) because 50M L2 atomics onto a few thousand hot lines serialise.
+constexpr int    kAccHitEntries = PM_MAX_PLANES * PM_GRID_N * PM_GRID_N * 4;   // 20 480
 constexpr int    kAccVoxEntries = PM_GRID_VOXELS * 3;                          // 98 304
-constexpr int    kAccGreyEntries = PM_GRID_VOXELS;                             // 32 768
-constexpr int    kAccEntries    = kAccHitEntries + kAccVoxEntries + kAccGreyEntries;   // 146 432 int64 = 1 171 456 B
+constexpr int    kGreyReplicas  = 8;
+constexpr int    kAccGreyEntries = kGreyReplicas * PM_GRID_VOXELS;             // 262 144
+constexpr int    kAccEntries    = kAccHitEntries + kAccVoxEntries + kAccGreyEntries;   // 380 928 int64 = 3 047 424 B
 constexpr double kHitScale      = 16777216.0;          // 2^24
 constexpr double kVoxScale      = 68719476736.0;       // 2^36
 

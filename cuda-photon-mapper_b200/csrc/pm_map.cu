@@ -30,21 +30,23 @@ __global__ void __launch_bounds__(128) build_map_kernel(const long long *__restr
   if (v >= PM_GRID_VOXELS) return;
   int z = v % PM_GRID_N, y = (v / PM_GRID_N) % PM_GRID_N, x = v / (PM_GRID_N * PM_GRID_N);
   const long long *vox = acc + kAccHitEntries + 3 * v;
-  const long long grey = acc[kAccHitEntries + kAccVoxEntries + v];
+  long long grey = 0;
+#pragma unroll
+  for (int r = 0; r < kGreyReplicas; r++) grey += acc[kAccHitEntries + kAccVoxEntries + r * PM_GRID_VOXELS + v];
   double s0 = (double)(vox[0] + grey) / kVoxScale, s1 = (double)(vox[1] + grey) / kVoxScale, s2 = (double)(vox[2] + grey) / kVoxScale;
   const double w05 = (double)0.05f / kHitScale;
   for (int id = 0; id < PM_MAX_PLANES; id++) {
     int on, a, b;
     slab_of(id, x, y, z, on, a, b);
     if (!on) continue;
-    const long long *hit = acc + id * PM_GRID_N * PM_GRID_N * 3;
+    const long long *hit = acc + id * PM_GRID_N * PM_GRID_N * 4;
     // sources (a',b') whose window [a'-3, a'+3) x [b'-3, b'+3) contains (a,b): a' in [a-2, a+3]
     int a_lo = max(a - 2, 0), a_hi = min(a + 3, PM_GRID_N - 1);
     int b_lo = max(b - 2, 0), b_hi = min(b + 3, PM_GRID_N - 1);
     for (int ap = a_lo; ap <= a_hi; ap++)
       for (int bp = b_lo; bp <= b_hi; bp++) {
-        const long long *h = hit + (ap * PM_GRID_N + bp) * 3;
-        long long h0 = h[0], h1 = h[1], h2 = h[2];
+        const long long *h = hit + (ap * PM_GRID_N + bp) * 4;
+        long long h0 = h[0] + h[3], h1 = h[1] + h[3], h2 = h[2] + h[3];
         if ((h0 | h1 | h2) == 0) continue;
         double wgt;
         if (ap == a && bp == b) wgt = 1.0 / kHitScale;   // the direct deposit

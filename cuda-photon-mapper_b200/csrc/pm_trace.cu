@@ -100,7 +100,8 @@ __global__ void __launch_bounds__(256) volume_kernel(const __grid_constant__ Dev
         int vx = clampi(voxel_x(P.x)), vy = clampi(voxel_x(P.y)), vz = clampi(voxel_z(P.z));
         int v = (vx * PM_GRID_N + vy) * PM_GRID_N + vz;
         if (e.x == e.y && e.y == e.z) {   // always true on this path: one atomic instead of three
-          acc_add(sk.acc + kAccHitEntries + kAccVoxEntries + v, __double2ll_rn((double)e.x * kVoxScale));
+          acc_add(sk.acc + kAccHitEntries + kAccVoxEntries + (blockIdx.x % kGreyReplicas) * PM_GRID_VOXELS + v,
+                  __double2ll_rn((double)e.x * kVoxScale));
         } else {
           unsigned long long *p = sk.acc + kAccHitEntries + 3 * v;
           acc_add(p + 0, __double2ll_rn((double)e.x * kVoxScale));
@@ -141,20 +142,20 @@ struct SmemAcc {
 __device__ __forceinline__ void store_photon(const Sink &sk, SmemAcc &sa, int type, int id, v3 loc, v3 e) {
   if (!sk.acc || type == 0) return;
   int vx = clampi(voxel_x(loc.x)), vy = clampi(voxel_x(loc.y)), vz = clampi(voxel_z(loc.z));
-  int a, b, on_slab;
-  switch (id) {
-    case 0: on_slab = vx == PM_GRID_N - 1; a = vy; b = vz; break;
-    case 2: on_slab = vx == 0;             a = vy; b = vz; break;
-    case 1: on_slab = vy == 0;             a = vx; b = vz; break;
-    case 3: on_slab = vy == PM_GRID_N - 1; a = vx; b = vz; break;
-    case 4: on_slab = vz == PM_GRID_N - 1; a = vx; b = vy; break;
-    default: on_slab = -1; a = b = 0; break;
-  }
+  // wall id -> slab axis / slab index / in-plane coordinates, as splatEnergy hard-codes them (selects, no branches)
+  const int ax = (id == 0 || id == 2) ? 0 : ((id == 1 || id == 3) ? 1 : 2);
+  const int slab = (id == 0 || id == 3 || id == 4) ? PM_GRID_N - 1 : 0;
+  const int vfix = ax == 0 ? vx : (ax == 1 ? vy : vz);
+  const int a = ax == 0 ? vy : vx, b = ax == 2 ? vy : vz;
+  const int on_slab = (unsigned)id > 4u ? -1 : (vfix == slab ? 1 : 0);
   if (on_slab == 1) {   // the common case: keyed energy sum, the 6x6 stencil is applied once per voxel in pm_map.cu
-    int en = ((id * PM_GRID_N + a) * PM_GRID_N + b) * 3;
-    sa.add(en + 0, __float2ll_rn(e.x * (float)kHitScale));
-    sa.add(en + 1, __float2ll_rn(e.y * (float)kHitScale));
-    sa.add(en + 2, __float2ll_rn(e.z * (float)kHitScale));
+    int en = ((id * PM_GRID_N + a) * PM_GRID_N + b) * 4;
+    if (e.x == e.y && e.y == e.z) sa.add(en + 3, __float2ll_rn(e.x * (float)kHitScale));
+    else {
+      sa.add(en + 0, __float2ll_rn(e.x * (float)kHitScale));
+      sa.add(en + 1, __float2ll_rn(e.y * (float)kHitScale));
+      sa.add(en + 2, __float2ll_rn(e.z * (float)kHitScale));
+    }
     return;
   }
   // rare: the clamped voxel is off the wall's slab (a wall that is not on the map boundary): expand per photon
@@ -333,7 +334,14 @@ __global__ void __launch_bounds__(kSurfaceThreads, 1) surface_kernel(const __gri
         ray = refract3(sc, ray, P, h.type, h.idx, P, 1.0f);
         P = add(mul(ray, 0.00001f), P);
         org = P; state = ST_CHAIN_F1;
-      } else {                                   // diffuse wall (prev == hit point: hazard H1)
+      } else {                                   // diffuse wall: reflect3(ray, prev, ...) with prev == the hit point
+        // Hazard H1: the wall "normal" is normalize(e_axis * (prev.axis - offset)).  When that offset squares to 0
+        // (the hit point lies exactly on the wall, ~88% of bounces) or is NaN, the normal, the reflected ray and hence
+        // every intersection test of the next raytrace are NaN: no hit, the photon ends.  Skip straight to that outcome.
+        const int wax = h.type == 1 ? sc.pl_axis[h.idx] : -1;
+        const float wd = comp(prev, wax) - sc.pl_off[h.type == 1 ? h.idx : 0];
+        const float wdd = wd * wd;
+        if (h.type == 1 && wax >= 0 && wax <= 2 && (wdd == 0.0f || wdd != wdd)) { state = ST_IDLE; continue; }
         ray = reflect3(sc, ray, prev, h.type, h.idx, P);
         org = P;
         caustics = false; new_point = true; bounces++;

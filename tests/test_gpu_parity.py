@@ -170,9 +170,16 @@ def test_photon_range_sharding_is_exact(pm, oracle):
         m.trace(0.0, media=True)
     m.build_map()
     parts = m.get_accumulators()
-    assert np.array_equal(whole, parts)
+    assert np.array_equal(_fold(pm, whole), _fold(pm, parts))
     assert bits_equal(g_whole, m.get_map())
     m.close()
+
+
+def _fold(pm, acc):
+    """Accumulators with the grey replicas summed (a CTA picks its replica by block index, so only the sum is
+    shard-invariant)."""
+    head = pm.ACC_HIT_ENTRIES + 32 * 32 * 32 * 3
+    return np.concatenate([acc[:head], acc[head:].reshape(-1, 32 * 32 * 32).sum(0)])
 
 
 def test_legacy_abi_frame(pm, oracle):
