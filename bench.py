@@ -268,6 +268,7 @@ def main():
     for _ in range(max(a.warmup, 3)):
         step()
     barrier()
+    m.enable_timing(True)                         # CUDA-event pairs around every kernel, on the launching stream
     launches0 = m.launch_count()
     t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_beg.record()
@@ -276,6 +277,8 @@ def main():
     t_end.record()
     barrier()
     launches = m.launch_count() - launches0
+    kernel_times = m.timings()
+    m.enable_timing(False)
     total_ms = t_beg.elapsed_time(t_end)
     if world > 1:
         tt = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
@@ -321,10 +324,22 @@ def main():
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md 6.65 TB/s)"
-        trace_ms = float(stages[0])
         n_local = last - first
-        trace_bytes = 12.0 * n_local              # algorithmic: one float3 direction per photon
-        achieved = trace_bytes / (trace_ms * 1e-3) / 1e9
+        kern = {k: {"avg_ms": v[0] / v[1], "launches": v[1]} for k, v in kernel_times.items() if v[1]}
+        dom = max(kern, key=lambda k: kern[k]["avg_ms"] * kern[k]["launches"])
+        # algorithmic (compulsory) HBM bytes per launch, DESIGN.md "kernels": one float3 direction per photon for the two
+        # trace kernels; one uchar4 + one float4 per pixel for the render kernel
+        alg = {"volume_kernel": 12.0 * n_local, "surface_kernel": 12.0 * n_local, "render_kernel": 20.0 * W * rows}
+        dom_bytes = alg.get(dom, 0.0)
+        dom_ms = kern[dom]["avg_ms"]
+        achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+        traffic = None
+        try:   # DRAM bytes per launch from the committed ncu --set full capture of the same configuration
+            prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            if prof.get("photons") == NP and world == 1:
+                traffic = prof["dram_bytes_per_launch"].get(dom)
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": ms_per_step, "unit": "ms", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
@@ -337,11 +352,13 @@ def main():
             "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": C.sizeof(pmb200.Scene),
                     "d2h_bytes_per_step": W * H * 4 + W * H * 16, "steps": e2e_steps,
                     "what": "pm_frame_host: scene struct in, emit+render, uchar4 + float4 frames copied to pinned host memory"},
-            "roofline": {"kernel": "trace_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": trace_bytes, "avg_launch_ms": trace_ms,
-                         "note": "Mode A trace keeps no photon records: 12 B/photon of compulsory HBM traffic; the kernel is "
-                                 "FP32/FP64-issue bound (see DESIGN.md, profiles/)"},
+            "kernels": kern,
+            "roofline": {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_ms,
+                         "note": "Mode A keeps no photon records, so the compulsory HBM traffic of the trace kernels is one 12 B "
+                                 "direction per photon: they are instruction-issue bound (ncu: issue slots ~83% busy), not "
+                                 "HBM bound; see DESIGN.md 'rooflines' and profiles/"},
             "clocks": clocks,
         }
         if not a.no_cpu_baseline and world == 1:

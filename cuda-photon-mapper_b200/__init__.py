@@ -73,6 +73,8 @@ def lib():
             "pm_render_host": (i32, [vp, f32, b, b, i32, i32, vp, vp]),
             "pm_frame_host": (i32, [vp, f32, b, b, b, i32, i32, vp, vp]),
             "pm_launch_count": (i64, [vp]),
+            "pm_enable_timing": (i32, [vp, b]), "pm_kernel_count": (i32, []), "pm_kernel_name": (C.c_char_p, [i32]),
+            "pm_get_timings": (i32, [vp, vp, vp]),
             "launch_init_random_numbers_kernel": (None, []),
             "launch_emit_photons_kernel": (None, [vp, C.c_uint, C.c_uint, f32, b, b]),
             "launch_photon_mapping_kernel": (None, [vp, C.c_uint, C.c_uint, f32, b, b]),
@@ -265,6 +267,16 @@ class PhotonMapper:
 
     def launch_count(self):
         return self.L.pm_launch_count(self.h)
+
+    def enable_timing(self, on=True):
+        self._ck(self.L.pm_enable_timing(self.h, on))
+
+    def timings(self):
+        """{kernel name: (total ms, launches)} since the last call (synchronises the stream)."""
+        n = self.L.pm_kernel_count()
+        ms = np.zeros(n, np.float64); cnt = np.zeros(n, np.int64)
+        self._ck(self.L.pm_get_timings(self.h, _ptr(ms), _ptr(cnt)))
+        return {self.L.pm_kernel_name(k).decode(): (float(ms[k]), int(cnt[k])) for k in range(n)}
 
 
 # -- the reference's three launchers, verbatim names (process-global default context) --------------------

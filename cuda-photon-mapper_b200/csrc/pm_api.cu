@@ -47,6 +47,33 @@ struct pm_context {
   int64_t fb_pixels = 0;
 
   int64_t launches = 0;
+
+  // optional per-kernel CUDA-event timing (pm_enable_timing): pairs recorded on the context's stream
+  bool timing = false;
+  struct Span { cudaEvent_t a, b; int kind; };
+  std::vector<Span> spans;
+  size_t spans_used = 0;
+};
+
+enum { K_MWC_TABLE = 0, K_VOLUME, K_SURFACE, K_BUILD_MAP, K_BUILD_TABLES, K_RENDER, K_COUNT };
+static const char *const kKernelNames[K_COUNT] = {"mwc_table_kernel", "volume_kernel", "surface_kernel", "build_map_kernel",
+                                                   "build_tables_kernel", "render_kernel"};
+
+// RAII span: records an event pair around one kernel launch when timing is on
+struct SpanGuard {
+  pm_context *c; int idx = -1;
+  SpanGuard(pm_context *ctx, int kind) : c(ctx) {
+    if (!c->timing) return;
+    if (c->spans_used == c->spans.size()) {
+      pm_context::Span s; s.kind = kind;
+      if (cudaEventCreate(&s.a) != cudaSuccess || cudaEventCreate(&s.b) != cudaSuccess) return;
+      c->spans.push_back(s);
+    }
+    idx = (int)c->spans_used++;
+    c->spans[idx].kind = kind;
+    cudaEventRecord(c->spans[idx].a, c->stream);
+  }
+  ~SpanGuard() { if (idx >= 0) cudaEventRecord(c->spans[idx].b, c->stream); }
 };
 
 #define CK(ctx, call)                                                                          \
@@ -179,7 +206,28 @@ int pm_destroy(pm_context *c) {
   cudaFree(c->d_table); cudaFree(c->d_acc); cudaFree(c->d_grid); cudaFree(c->d_vol); cudaFree(c->d_surf);
   cudaFree(c->d_jump); cudaFree(c->d_rec_pos); cudaFree(c->d_rec_pow); cudaFree(c->d_rec_dir); cudaFree(c->d_rec_count);
   cudaFree(c->d_fb_u8); cudaFree(c->d_fb_f32);
+  for (auto &sp : c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
   delete c;
+  return PM_OK;
+}
+
+int pm_enable_timing(pm_context *c, bool on) {
+  if (!c) return PM_ERR_ARG;
+  c->timing = on; c->spans_used = 0;
+  return PM_OK;
+}
+int pm_kernel_count(void) { return K_COUNT; }
+const char *pm_kernel_name(int kind) { return kind >= 0 && kind < K_COUNT ? kKernelNames[kind] : ""; }
+int pm_get_timings(pm_context *c, double *total_ms, int64_t *launches) {
+  ARG(c, c && total_ms && launches, "null argument");
+  CK(c, cudaStreamSynchronize(c->stream));
+  for (int k = 0; k < K_COUNT; k++) { total_ms[k] = 0.0; launches[k] = 0; }
+  for (size_t i = 0; i < c->spans_used; i++) {
+    float ms = 0.0f;
+    CK(c, cudaEventElapsedTime(&ms, c->spans[i].a, c->spans[i].b));
+    total_ms[c->spans[i].kind] += ms; launches[c->spans[i].kind]++;
+  }
+  c->spans_used = 0;
   return PM_OK;
 }
 
@@ -252,7 +300,10 @@ int pm_get_mwc_state(const pm_context *c, uint32_t *w, uint32_t *z) {
 int pm_init_random_table(pm_context *c) {
   ARG(c, c != nullptr, "null context");
   CK(c, cudaSetDevice(c->device));
-  CK(c, launch_mwc_table(c->d_table, c->n_photons, c->mwc_w, c->mwc_z, c->d_jump, c->stream));
+  {
+    SpanGuard g(c, K_MWC_TABLE);
+    CK(c, launch_mwc_table(c->d_table, c->n_photons, c->mwc_w, c->mwc_z, c->d_jump, c->stream));
+  }
   c->launches++;
   unsigned long long draws = 3ull * (unsigned long long)c->n_photons;
   c->mwc_z = h_mwc_advance(0, c->mwc_z, draws);
@@ -311,9 +362,18 @@ int pm_trace(pm_context *c, float t, unsigned flags) {
   CK(c, cudaSetDevice(c->device));
   c->dsc = make_device_scene(c->scene, t);
   cudaError_t terr = cudaSuccess;
-  c->launches += launch_trace(c->dsc, c->d_table, c->first, c->last, flags, c->mwc_w, c->mwc_z, c->d_jump,
-                              (unsigned long long *)c->d_acc, c->d_rec_pos, c->d_rec_pow, c->d_rec_dir, c->d_rec_count,
-                              c->rec_cap, c->num_sms, c->stream, &terr);
+  if (flags & PM_TRACE_MEDIA) {
+    SpanGuard g(c, K_VOLUME);
+    c->launches += launch_trace_volume(c->dsc, c->d_table, c->first, c->last, flags, c->mwc_w, c->mwc_z, c->d_jump,
+                                       (unsigned long long *)c->d_acc, c->d_rec_pos, c->d_rec_pow, c->d_rec_dir, c->d_rec_count,
+                                       c->rec_cap, c->num_sms, c->stream, &terr);
+  }
+  CK(c, terr);
+  {
+    SpanGuard g(c, K_SURFACE);
+    c->launches += launch_trace_surface(c->dsc, c->d_table, c->first, c->last, flags, (unsigned long long *)c->d_acc, c->d_rec_pos,
+                                        c->d_rec_pow, c->d_rec_dir, c->d_rec_count, c->rec_cap, c->num_sms, c->stream, &terr);
+  }
   CK(c, terr);
   if (flags & PM_TRACE_MEDIA) {   // the medium scattering consumed 9 draws per photon of the WHOLE job
     unsigned long long draws = 9ull * (unsigned long long)c->n_photons;
@@ -341,8 +401,14 @@ int pm_get_accumulators_host(pm_context *c, int64_t *out) {
 int pm_build_map(pm_context *c) {
   ARG(c, c != nullptr, "null context");
   CK(c, cudaSetDevice(c->device));
-  CK(c, launch_build_map(c->d_acc, c->energy_scale, c->d_grid, c->stream));
-  CK(c, launch_build_tables(c->d_grid, c->d_vol, c->d_surf, c->stream));
+  {
+    SpanGuard g(c, K_BUILD_MAP);
+    CK(c, launch_build_map(c->d_acc, c->energy_scale, c->d_grid, c->stream));
+  }
+  {
+    SpanGuard g(c, K_BUILD_TABLES);
+    CK(c, launch_build_tables(c->d_grid, c->d_vol, c->d_surf, c->stream));
+  }
   c->launches += 2;
   c->tables_valid = true;
   return PM_OK;
@@ -428,7 +494,10 @@ int pm_render(pm_context *c, float t, bool interp, bool media, int width, int he
   if (!c->tables_valid) { c->err = "pm_render before pm_build_map / pm_set_map_host"; return PM_ERR_STATE; }
   CK(c, cudaSetDevice(c->device));
   c->dsc = make_device_scene(c->scene, t);
-  CK(c, launch_render(c->dsc, c->d_vol, c->d_surf, width, height, y0, y1, interp, media, (uchar4 *)dev_rgba, (float4 *)dev_rgbf, c->stream));
+  {
+    SpanGuard g(c, K_RENDER);
+    CK(c, launch_render(c->dsc, c->d_vol, c->d_surf, width, height, y0, y1, interp, media, (uchar4 *)dev_rgba, (float4 *)dev_rgbf, c->stream));
+  }
   if (y1 > y0) c->launches++;
   return PM_OK;
 }

@@ -18,10 +18,13 @@ inline uint32_t host_powmod(uint32_t a, unsigned long long e, uint32_t m) {
 
 // pm_trace.cu
 cudaError_t launch_mwc_table(float4 *table, long long n, uint32_t w0, uint32_t z0, const MwcJump *J, cudaStream_t st);
-// returns the number of kernels launched; *err receives the CUDA status
-int launch_trace(const DeviceScene &sc, const float4 *table, long long first, long long last, unsigned flags, uint32_t w0,
-                 uint32_t z0, const MwcJump *J, unsigned long long *acc, float4 *rec_pos, float4 *rec_pow, float4 *rec_dir,
-                 unsigned long long *rec_count, long long rec_cap, int num_sms, cudaStream_t st, cudaError_t *err);
+// each returns the number of kernels launched; *err receives the CUDA status
+int launch_trace_volume(const DeviceScene &sc, const float4 *table, long long first, long long last, unsigned flags, uint32_t w0,
+                        uint32_t z0, const MwcJump *J, unsigned long long *acc, float4 *rec_pos, float4 *rec_pow, float4 *rec_dir,
+                        unsigned long long *rec_count, long long rec_cap, int num_sms, cudaStream_t st, cudaError_t *err);
+int launch_trace_surface(const DeviceScene &sc, const float4 *table, long long first, long long last, unsigned flags,
+                         unsigned long long *acc, float4 *rec_pos, float4 *rec_pow, float4 *rec_dir, unsigned long long *rec_count,
+                         long long rec_cap, int num_sms, cudaStream_t st, cudaError_t *err);
 
 // pm_map.cu
 cudaError_t launch_build_map(const long long *acc, float energy_scale, float *grid, cudaStream_t st);

@@ -370,34 +370,45 @@ cudaError_t launch_mwc_table(float4 *table, long long n, uint32_t w0, uint32_t z
   return cudaGetLastError();
 }
 
-int launch_trace(const DeviceScene &sc, const float4 *table, long long first, long long last, unsigned flags, uint32_t w0,
-                 uint32_t z0, const MwcJump *J, unsigned long long *acc, float4 *rec_pos, float4 *rec_pow, float4 *rec_dir,
-                 unsigned long long *rec_count, long long rec_cap, int num_sms, cudaStream_t st, cudaError_t *err) {
-  *err = cudaSuccess;
-  long long n = last - first;
-  if (n <= 0) return 0;
+static Sink make_sink(unsigned flags, unsigned long long *acc, float4 *rec_pos, float4 *rec_pow, float4 *rec_dir,
+                      unsigned long long *rec_count, long long rec_cap) {
   Sink sk;
   sk.acc = (flags & PM_TRACE_NO_MAP) ? nullptr : acc;
   sk.rec_pos = rec_pos; sk.rec_pow = rec_pow; sk.rec_dir = rec_dir; sk.rec_count = rec_count; sk.rec_cap = rec_cap;
-  int launches = 0;
-  if (flags & PM_TRACE_MEDIA) {
-    long long want = (n + 255) / 256, cap = (long long)num_sms * 8;
-    unsigned blocks = (unsigned)(want < cap ? want : cap);
-    unsigned long long steps = 9ull * blocks * 256ull;
-    volume_kernel<<<blocks, 256, 0, st>>>(sc, table, first, last, flags, w0, z0, J, host_powmod(18000u, steps, mwc_modulus(1)),
-                                          host_powmod(36969u, steps, mwc_modulus(0)), sk);
-    launches++;
-    if ((*err = cudaGetLastError()) != cudaSuccess) return launches;
-  }
+  return sk;
+}
+
+int launch_trace_volume(const DeviceScene &sc, const float4 *table, long long first, long long last, unsigned flags, uint32_t w0,
+                        uint32_t z0, const MwcJump *J, unsigned long long *acc, float4 *rec_pos, float4 *rec_pow, float4 *rec_dir,
+                        unsigned long long *rec_count, long long rec_cap, int num_sms, cudaStream_t st, cudaError_t *err) {
+  *err = cudaSuccess;
+  long long n = last - first;
+  if (n <= 0) return 0;
+  Sink sk = make_sink(flags, acc, rec_pos, rec_pow, rec_dir, rec_count, rec_cap);
+  long long want = (n + 255) / 256, cap = (long long)num_sms * 8;
+  unsigned blocks = (unsigned)(want < cap ? want : cap);
+  unsigned long long steps = 9ull * blocks * 256ull;
+  volume_kernel<<<blocks, 256, 0, st>>>(sc, table, first, last, flags, w0, z0, J, host_powmod(18000u, steps, mwc_modulus(1)),
+                                        host_powmod(36969u, steps, mwc_modulus(0)), sk);
+  *err = cudaGetLastError();
+  return 1;
+}
+
+int launch_trace_surface(const DeviceScene &sc, const float4 *table, long long first, long long last, unsigned flags,
+                         unsigned long long *acc, float4 *rec_pos, float4 *rec_pow, float4 *rec_dir, unsigned long long *rec_count,
+                         long long rec_cap, int num_sms, cudaStream_t st, cudaError_t *err) {
+  *err = cudaSuccess;
+  long long n = last - first;
+  if (n <= 0) return 0;
+  Sink sk = make_sink(flags, acc, rec_pos, rec_pow, rec_dir, rec_count, rec_cap);
   *err = cudaFuncSetAttribute(surface_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSurfaceSmem);
-  if (*err != cudaSuccess) return launches;
+  if (*err != cudaSuccess) return 0;
   long long warps_needed = (n + 31) / 32;
   long long ctas = (warps_needed + (kSurfaceThreads / 32) - 1) / (kSurfaceThreads / 32);
   unsigned grid = (unsigned)(ctas < num_sms ? ctas : num_sms);
   surface_kernel<<<grid, kSurfaceThreads, kSurfaceSmem, st>>>(sc, table, first, last, flags, sk);
-  launches++;
   *err = cudaGetLastError();
-  return launches;
+  return 1;
 }
 
 }  // namespace pm

@@ -122,8 +122,14 @@ int pm_render_host(pm_context *ctx, float animTime, bool interpolateFlag, bool p
 int pm_frame_host(pm_context *ctx, float animTime, bool emitFlag, bool interpolateFlag, bool participatingMediaFlag,
                   int width, int height, pm_uchar4 *host_rgba, float *host_rgbf);
 
-/* instrumentation: number of kernels this context has launched so far */
-int64_t pm_launch_count(const pm_context *ctx);
+/* instrumentation: number of kernels this context has launched so far, and optional per-kernel CUDA-event timing
+ * (event pairs recorded on the context's stream around each launch; pm_get_timings synchronises, fills
+ * total_ms[k] / launches[k] for k < pm_kernel_count() since the last call, and resets) */
+int64_t     pm_launch_count(const pm_context *ctx);
+int         pm_enable_timing(pm_context *ctx, bool on);
+int         pm_kernel_count(void);
+const char *pm_kernel_name(int kind);
+int         pm_get_timings(pm_context *ctx, double *total_ms, int64_t *launches);
 
 #ifdef __cplusplus
 }
