@@ -195,12 +195,6 @@ def time_reference_cuda(a, table_host, dev_rgba):
                     % (a.photons, a.height)}
 
 
-class _CudaArray:
-    """Wrap a raw device pointer for torch.as_tensor (zero copy) via __cuda_array_interface__."""
-    def __init__(self, ptr, n, typestr):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
-
-
 def main():
     a = parse()
     if a.impl == "reference":
@@ -210,6 +204,7 @@ def main():
     import torch
     import torch.distributed as dist
     import pmb200
+    from pmb200 import dist as pmdist
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -230,15 +225,15 @@ def main():
     m.set_scene(scene)
     m.set_energy_scale(10000.0 / NP)
     m.init_random_numbers()                       # once, outside the timed region (callbacksPBO.cpp:55-58)
-    first, last = NP * rank // world, NP * (rank + 1) // world
+    first, last = pmdist.photon_shard(NP, rank, world)
     m.set_photon_range(first, last)
-    rows = H // world
-    y0, y1 = rank * rows, (rank + 1) * rows
+    y0, y1 = pmdist.row_band(H, rank, world)
+    rows = y1 - y0
 
     rgba = torch.zeros((H, W, 4), dtype=torch.uint8, device="cuda")
     rgbf = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
     acc_ptr, acc_n = m.accumulators()
-    acc = torch.as_tensor(_CudaArray(acc_ptr, acc_n, "<i8"), device="cuda")
+    acc = pmdist.device_tensor(acc_ptr, acc_n, "<i8")
 
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(a.steps)]
 
@@ -247,15 +242,13 @@ def main():
         m.clear_map()
         m.trace(0.0, media=True)
         if e: e[1].record()
-        if world > 1:
-            dist.all_reduce(acc)                  # exact: int64 sum
+        pmdist.allreduce_accumulators(acc)        # exact: int64 sum over NVLink (no-op at N=1)
         if e: e[2].record()
         m.build_map()
         if e: e[3].record()
         m.render_device(W, H, 0.0, False, True, rgba=rgba, rgbf=rgbf, y0=y0, y1=y1)
-        if world > 1:
-            dist.all_gather_into_tensor(rgba.view(-1), rgba[y0:y1].reshape(-1))
-            dist.all_gather_into_tensor(rgbf.view(-1), rgbf[y0:y1].reshape(-1))
+        pmdist.gather_frame(rgba, y0, y1)
+        pmdist.gather_frame(rgbf, y0, y1)
         if e: e[4].record()
 
     def barrier():

@@ -1,0 +1,56 @@
+"""pmb200.dist -- multi-GPU plumbing (one process per GPU, torch.distributed; NCCL over NVLink on the GPU box,
+gloo in the CPU tests).  The path shards naturally:
+
+  * photons: rank r traces the contiguous index range photon_shard(n, r, world) of the SAME random table, so the
+    union of the shards is exactly the single-GPU photon set (the MWC stream is index-addressed);
+  * one exchange: the int64 fixed-point accumulators are summed across ranks (all-reduce).  Integer addition is
+    associative, so the summed accumulators -- and the float photon map built from them -- are bit-identical for
+    every world size;
+  * pixels: rank r renders the row band row_band(h, r, world); bands are all-gathered into the full frame.
+"""
+import torch
+import torch.distributed as dist
+
+
+def photon_shard(n_photons, rank, world):
+    """Contiguous, disjoint, exhaustive split of [0, n_photons)."""
+    return n_photons * rank // world, n_photons * (rank + 1) // world
+
+
+def row_band(height, rank, world):
+    """Contiguous row band [y0, y1) of rank `rank`; height must divide evenly so bands all-gather in place."""
+    if height % world:
+        raise ValueError("frame height %d does not split into %d equal row bands" % (height, world))
+    rows = height // world
+    return rank * rows, (rank + 1) * rows
+
+
+class _RawCuda:
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def device_tensor(ptr, n, typestr="<i8"):
+    """Zero-copy torch view of a raw device allocation owned by libpmb200 (e.g. the accumulators)."""
+    return torch.as_tensor(_RawCuda(ptr, n, typestr), device="cuda")
+
+
+def allreduce_accumulators(acc):
+    """Sum the exact accumulators across ranks (no-op for a single process)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+    return acc
+
+
+def gather_frame(frame, y0, y1):
+    """All-gather the row bands of a [H, W, C] frame in place (every rank ends with the whole frame)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return frame
+    band = frame[y0:y1].reshape(-1)
+    if dist.get_backend() == "nccl":
+        dist.all_gather_into_tensor(frame.view(-1), band)
+    else:
+        parts = [torch.empty_like(band) for _ in range(dist.get_world_size())]
+        dist.all_gather(parts, band.clone())
+        frame.view(-1).copy_(torch.cat(parts))
+    return frame
