@@ -68,7 +68,13 @@ def lib():
             "pm_map_device": (i32, [vp, C.POINTER(vp)]),
             "pm_set_record_capacity": (i32, [vp, i64]), "pm_record_count": (i32, [vp, C.POINTER(i64)]),
             "pm_get_records_host": (i32, [vp, vp, i64]),
-            "pm_record_buffers": (i32, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
+            "pm_record_buffers": (i32, [vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i64)]),
+            "pm_knn_build": (i32, [vp, i32]), "pm_knn_build_points": (i32, [vp, i32, vp, vp, i64]),
+            "pm_knn_size": (i32, [vp, i32, C.POINTER(i64), C.POINTER(C.c_int32)]),
+            "pm_knn_query": (i32, [vp, i32, vp, i64, i32, f32, vp, vp, vp]),
+            "pm_knn_radiance": (i32, [vp, i32, vp, i64, i32, f32, vp]),
+            "pm_knn_sorted_host": (i32, [vp, i32, vp, vp, i64]),
+            "pm_knn_level_host": (i32, [vp, i32, i32, C.POINTER(i64), vp]),
             "pm_render": (i32, [vp, f32, b, b, i32, i32, i32, i32, vp, vp]),
             "pm_render_host": (i32, [vp, f32, b, b, i32, i32, vp, vp]),
             "pm_frame_host": (i32, [vp, f32, b, b, b, i32, i32, vp, vp]),
@@ -243,10 +249,42 @@ class PhotonMapper:
         self._ck(self.L.pm_get_records_host(self.h, _ptr(out), n))
         return out
 
-    def record_buffers(self):
-        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
-        self._ck(self.L.pm_record_buffers(self.h, C.byref(a), C.byref(b), C.byref(c)))
-        return a.value, b.value, c.value
+    def record_buffers(self, which=0):
+        """(pos_meta ptr, power_index ptr, dir ptr or None, count) of the surface (0) or volume (1) record set."""
+        a, b, c, n = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int64()
+        self._ck(self.L.pm_record_buffers(self.h, which, C.byref(a), C.byref(b), C.byref(c), C.byref(n)))
+        return a.value, b.value, c.value, n.value
+
+    # -- Mode B: photon-map build + k-nearest-photon search ---------------------------------------------------
+    def knn_build(self, which=0):
+        self._ck(self.L.pm_knn_build(self.h, which))
+
+    def knn_build_points(self, which, pos4, power4, n):
+        """pos4 / power4: DEVICE float4 arrays (torch tensors or addresses) that outlive the map."""
+        self._ck(self.L.pm_knn_build_points(self.h, which, _ptr(pos4), _ptr(power4), n))
+
+    def knn_size(self, which=0):
+        n, lv = C.c_int64(), C.c_int32()
+        self._ck(self.L.pm_knn_size(self.h, which, C.byref(n), C.byref(lv)))
+        return n.value, lv.value
+
+    def knn_query(self, which, queries4, nq, k, max_r2, idx, d2, cnt):
+        self._ck(self.L.pm_knn_query(self.h, which, _ptr(queries4), nq, k, max_r2, _ptr(idx), _ptr(d2), _ptr(cnt)))
+
+    def knn_radiance(self, which, queries4, nq, k, max_r2, rgb4):
+        self._ck(self.L.pm_knn_radiance(self.h, which, _ptr(queries4), nq, k, max_r2, _ptr(rgb4)))
+
+    def knn_sorted(self, which, n):
+        keys = np.empty(n, np.uint32); perm = np.empty(n, np.uint32)
+        self._ck(self.L.pm_knn_sorted_host(self.h, which, _ptr(keys), _ptr(perm), n))
+        return keys, perm
+
+    def knn_level(self, which, level):
+        n = C.c_int64()
+        self._ck(self.L.pm_knn_level_host(self.h, which, level, C.byref(n), None))
+        boxes = np.empty((6, n.value), np.float32)
+        self._ck(self.L.pm_knn_level_host(self.h, which, level, C.byref(n), _ptr(boxes)))
+        return boxes
 
     # -- stages 3-5 -------------------------------------------------------------------------------------
     def render_device(self, w, h, t=0.0, interp=False, media=False, rgba=None, rgbf=None, y0=0, y1=None):

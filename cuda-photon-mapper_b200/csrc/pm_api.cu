@@ -38,9 +38,14 @@ struct pm_context {
   float4 *d_vol = nullptr, *d_surf = nullptr;
   bool tables_valid = false;
 
+  // photon records: [0] surface set (appended, cursor d_rec_count), [1] volume set (fixed slots)
   float4 *d_rec_pos = nullptr, *d_rec_pow = nullptr, *d_rec_dir = nullptr;
   unsigned long long *d_rec_count = nullptr;
   int64_t rec_cap = 0;
+  float4 *d_vrec_pos = nullptr, *d_vrec_pow = nullptr;
+  int64_t vrec_cap = 0, vrec_count = 0;
+
+  KnnMap knn[2];                   // Mode B maps: surface, volume
 
   uchar4 *d_fb_u8 = nullptr;
   float4 *d_fb_f32 = nullptr;
@@ -205,7 +210,8 @@ int pm_destroy(pm_context *c) {
   cudaSetDevice(c->device);
   cudaFree(c->d_table); cudaFree(c->d_acc); cudaFree(c->d_grid); cudaFree(c->d_vol); cudaFree(c->d_surf);
   cudaFree(c->d_jump); cudaFree(c->d_rec_pos); cudaFree(c->d_rec_pow); cudaFree(c->d_rec_dir); cudaFree(c->d_rec_count);
-  cudaFree(c->d_fb_u8); cudaFree(c->d_fb_f32);
+  cudaFree(c->d_fb_u8); cudaFree(c->d_fb_f32); cudaFree(c->d_vrec_pos); cudaFree(c->d_vrec_pow);
+  knn_free(c->knn[0]); knn_free(c->knn[1]);
   for (auto &sp : c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
   delete c;
   return PM_OK;
@@ -336,6 +342,7 @@ int pm_clear_map(pm_context *c) {
   CK(c, cudaSetDevice(c->device));
   CK(c, cudaMemsetAsync(c->d_acc, 0, sizeof(long long) * kAccEntries, c->stream));
   if (c->d_rec_count) CK(c, cudaMemsetAsync(c->d_rec_count, 0, sizeof(unsigned long long), c->stream));
+  c->vrec_count = 0;
   c->tables_valid = false;
   return PM_OK;
 }
@@ -363,10 +370,21 @@ int pm_trace(pm_context *c, float t, unsigned flags) {
   c->dsc = make_device_scene(c->scene, t);
   cudaError_t terr = cudaSuccess;
   if (flags & PM_TRACE_MEDIA) {
+    if (flags & PM_TRACE_RECORDS) {   // the volume set has a fixed slot per (photon, step)
+      int64_t need = 3 * (c->last - c->first);
+      if (need > c->vrec_cap) {
+        CK(c, cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_vrec_pos); cudaFree(c->d_vrec_pow); c->d_vrec_pos = c->d_vrec_pow = nullptr; c->vrec_cap = 0;
+        CK(c, cudaMalloc(&c->d_vrec_pos, sizeof(float4) * (size_t)need));
+        CK(c, cudaMalloc(&c->d_vrec_pow, sizeof(float4) * (size_t)need));
+        c->vrec_cap = need;
+      }
+      c->vrec_count = need;
+    }
     SpanGuard g(c, K_VOLUME);
     c->launches += launch_trace_volume(c->dsc, c->d_table, c->first, c->last, flags, c->mwc_w, c->mwc_z, c->d_jump,
-                                       (unsigned long long *)c->d_acc, c->d_rec_pos, c->d_rec_pow, c->d_rec_dir, c->d_rec_count,
-                                       c->rec_cap, c->num_sms, c->stream, &terr);
+                                       (unsigned long long *)c->d_acc, c->d_vrec_pos, c->d_vrec_pow, nullptr, c->d_rec_count,
+                                       c->vrec_cap, c->num_sms, c->stream, &terr);
   }
   CK(c, terr);
   {
@@ -436,34 +454,61 @@ int pm_map_device(pm_context *c, float **dev_grid) {
   return PM_OK;
 }
 
-int pm_record_count(pm_context *c, int64_t *n) {
-  ARG(c, c && n, "null argument");
-  CK(c, cudaSetDevice(c->device));
+static int surface_record_count(pm_context *c, int64_t *n) {
   unsigned long long cnt = 0;
   CK(c, cudaMemcpyAsync(&cnt, c->d_rec_count, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));
   *n = (int64_t)cnt;
   return PM_OK;
 }
-int pm_record_buffers(pm_context *c, float **pos, float **pow, float **dir) {
-  if (!c) return PM_ERR_ARG;
-  if (pos) *pos = (float *)c->d_rec_pos;
-  if (pow) *pow = (float *)c->d_rec_pow;
-  if (dir) *dir = (float *)c->d_rec_dir;
+int pm_record_count(pm_context *c, int64_t *n) {
+  ARG(c, c && n, "null argument");
+  CK(c, cudaSetDevice(c->device));
+  int64_t s = 0;
+  int rc = surface_record_count(c, &s);
+  if (rc != PM_OK) return rc;
+  *n = s + c->vrec_count;
+  return PM_OK;
+}
+int pm_record_buffers(pm_context *c, int which, float **pos, float **pow, float **dir, int64_t *count) {
+  ARG(c, c && (which == PM_MAP_SURFACE || which == PM_MAP_VOLUME), "bad map id");
+  if (which == PM_MAP_SURFACE) {
+    if (pos) *pos = (float *)c->d_rec_pos;
+    if (pow) *pow = (float *)c->d_rec_pow;
+    if (dir) *dir = (float *)c->d_rec_dir;
+    if (count) {
+      int rc = surface_record_count(c, count);
+      if (rc != PM_OK) return rc;
+      if (*count > c->rec_cap) { c->err = "record buffers overflowed (raise pm_set_record_capacity)"; return PM_ERR_STATE; }
+    }
+  } else {
+    if (pos) *pos = (float *)c->d_vrec_pos;
+    if (pow) *pow = (float *)c->d_vrec_pow;
+    if (dir) *dir = nullptr;
+    if (count) *count = c->vrec_count;
+  }
   return PM_OK;
 }
 int pm_get_records_host(pm_context *c, pm_record *out, int64_t max_records) {
   ARG(c, c && out, "null argument");
-  int64_t n = 0;
-  int rc = pm_record_count(c, &n);
+  CK(c, cudaSetDevice(c->device));
+  int64_t ns = 0;
+  int rc = surface_record_count(c, &ns);
   if (rc != PM_OK) return rc;
-  if (n > c->rec_cap) { c->err = "record buffers overflowed (raise pm_set_record_capacity)"; return PM_ERR_STATE; }
+  if (ns > c->rec_cap) { c->err = "record buffers overflowed (raise pm_set_record_capacity)"; return PM_ERR_STATE; }
+  const int64_t nv = c->vrec_count, n = ns + nv;
   ARG(c, n <= max_records, "host buffer too small");
-  std::vector<float4> pos((size_t)n), pw((size_t)n), dir((size_t)n);
-  CK(c, cudaMemcpy(pos.data(), c->d_rec_pos, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost));
-  CK(c, cudaMemcpy(pw.data(), c->d_rec_pow, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost));
-  CK(c, cudaMemcpy(dir.data(), c->d_rec_dir, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost));
-  std::vector<unsigned long long> key((size_t)n);   // (photon index, call ordinal, slot)
+  std::vector<float4> pos((size_t)n), pw((size_t)n), dir((size_t)n, make_float4(0.f, 0.f, 0.f, 0.f));
+  if (ns) {
+    CK(c, cudaMemcpy(pos.data(), c->d_rec_pos, sizeof(float4) * (size_t)ns, cudaMemcpyDeviceToHost));
+    CK(c, cudaMemcpy(pw.data(), c->d_rec_pow, sizeof(float4) * (size_t)ns, cudaMemcpyDeviceToHost));
+    CK(c, cudaMemcpy(dir.data(), c->d_rec_dir, sizeof(float4) * (size_t)ns, cudaMemcpyDeviceToHost));
+  }
+  if (nv) {
+    CK(c, cudaMemcpy(pos.data() + ns, c->d_vrec_pos, sizeof(float4) * (size_t)nv, cudaMemcpyDeviceToHost));
+    CK(c, cudaMemcpy(pw.data() + ns, c->d_vrec_pow, sizeof(float4) * (size_t)nv, cudaMemcpyDeviceToHost));
+  }
+  std::vector<unsigned long long> key((size_t)n);   // (photon index, call ordinal)
   std::vector<int64_t> order((size_t)n);
   for (int64_t i = 0; i < n; i++) {
     uint32_t meta, idx;
@@ -484,6 +529,80 @@ int pm_get_records_host(pm_context *c, pm_record *out, int64_t max_records) {
     r.dir[0] = dir[i].x; r.dir[1] = dir[i].y; r.dir[2] = dir[i].z;
     r.energy[0] = pw[i].x; r.energy[1] = pw[i].y; r.energy[2] = pw[i].z;
   }
+  return PM_OK;
+}
+
+// ---- Mode B ----------------------------------------------------------------------------------------------
+int pm_knn_build_points(pm_context *c, int which, const float *pos4, const float *pow4, int64_t n) {
+  ARG(c, c && (which == PM_MAP_SURFACE || which == PM_MAP_VOLUME), "bad map id");
+  ARG(c, n >= 0 && (n == 0 || pos4), "null points");
+  CK(c, cudaSetDevice(c->device));
+  int launches = 0;
+  cudaError_t e = knn_build(c->knn[which], (const float4 *)pos4, (const float4 *)pow4, n, 0, c->stream, &launches);
+  c->launches += launches;
+  CK(c, e);
+  return PM_OK;
+}
+int pm_knn_build(pm_context *c, int which) {
+  ARG(c, c && (which == PM_MAP_SURFACE || which == PM_MAP_VOLUME), "bad map id");
+  CK(c, cudaSetDevice(c->device));
+  float *pos = nullptr, *pw = nullptr; int64_t n = 0;
+  int rc = pm_record_buffers(c, which, &pos, &pw, nullptr, &n);
+  if (rc != PM_OK) return rc;
+  int launches = 0;
+  // surface map: wall hits only (sphere hits carry no energy in the reference either, PMK:1176)
+  cudaError_t e = knn_build(c->knn[which], (const float4 *)pos, (const float4 *)pw, n, which == PM_MAP_SURFACE ? 1 : 0, c->stream, &launches);
+  c->launches += launches;
+  CK(c, e);
+  return PM_OK;
+}
+int pm_knn_size(pm_context *c, int which, int64_t *n, int32_t *levels) {
+  ARG(c, c && (which == PM_MAP_SURFACE || which == PM_MAP_VOLUME), "bad map id");
+  if (n) *n = c->knn[which].n;
+  if (levels) *levels = c->knn[which].levels;
+  return PM_OK;
+}
+static int knn_query_common(pm_context *c, int which, const float *q4, int64_t nq, int k, float max_r2, int32_t *idx, float *d2,
+                            int32_t *cnt, float *rgb4) {
+  ARG(c, c && (which == PM_MAP_SURFACE || which == PM_MAP_VOLUME), "bad map id");
+  ARG(c, k >= 1 && k <= 128, "k must be in [1, 128]");
+  ARG(c, nq >= 0 && (nq == 0 || q4), "null queries");
+  ARG(c, !(max_r2 < 0.0f), "negative radius");
+  CK(c, cudaSetDevice(c->device));
+  if (rgb4 && !c->knn[which].power && c->knn[which].n > 0) { c->err = "map was built without powers"; return PM_ERR_STATE; }
+  CK(c, knn_query(c->knn[which], (const float4 *)q4, nq, k, max_r2, idx, d2, cnt, which == PM_MAP_VOLUME, (float4 *)rgb4, c->num_sms, c->stream));
+  if (nq > 0) c->launches++;
+  return PM_OK;
+}
+int pm_knn_query(pm_context *c, int which, const float *q4, int64_t nq, int k, float max_r2, int32_t *idx, float *d2, int32_t *cnt) {
+  ARG(c, c && idx && d2 && cnt, "null output");
+  return knn_query_common(c, which, q4, nq, k, max_r2, idx, d2, cnt, nullptr);
+}
+int pm_knn_radiance(pm_context *c, int which, const float *q4, int64_t nq, int k, float max_r2, float *rgb4) {
+  ARG(c, c && rgb4, "null output");
+  return knn_query_common(c, which, q4, nq, k, max_r2, nullptr, nullptr, nullptr, rgb4);
+}
+int pm_knn_sorted_host(pm_context *c, int which, uint32_t *keys, uint32_t *perm, int64_t n) {
+  ARG(c, c && (which == PM_MAP_SURFACE || which == PM_MAP_VOLUME), "bad map id");
+  const KnnMap &m = c->knn[which];
+  ARG(c, n >= 0 && n <= m.n_sorted_pad, "more entries than were sorted");
+  CK(c, cudaSetDevice(c->device));
+  CK(c, cudaStreamSynchronize(c->stream));
+  if (keys && n) CK(c, cudaMemcpy(keys, m.keys[m.sorted], sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost));
+  if (perm && n) CK(c, cudaMemcpy(perm, m.vals[m.sorted], sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost));
+  return PM_OK;
+}
+int pm_knn_level_host(pm_context *c, int which, int level, int64_t *count, float *boxes6) {
+  ARG(c, c && (which == PM_MAP_SURFACE || which == PM_MAP_VOLUME), "bad map id");
+  const KnnMap &m = c->knn[which];
+  ARG(c, level >= 0 && level < m.levels, "no such level");
+  CK(c, cudaSetDevice(c->device));
+  CK(c, cudaStreamSynchronize(c->stream));
+  if (count) *count = m.cnt[level];
+  if (boxes6)
+    for (int a = 0; a < 6; a++)
+      CK(c, cudaMemcpy(boxes6 + (size_t)a * m.cnt[level], m.boxes + m.off[level] + (size_t)a * m.pad[level], sizeof(float) * (size_t)m.cnt[level],
+                       cudaMemcpyDeviceToHost));
   return PM_OK;
 }
 

@@ -34,4 +34,26 @@ cudaError_t launch_build_tables(const float *grid, float4 *vol_table, float4 *su
 cudaError_t launch_render(const DeviceScene &sc, const float4 *vol_table, const float4 *surf_table, int width, int height,
                           int y0, int y1, bool interp, bool media, uchar4 *rgba, float4 *rgbf, cudaStream_t st);
 
+// pm_knn.cu -- Mode B photon map: sorted points + implicit 32-wide LBVH (see the file header)
+struct KnnMap {
+  long long n = 0;                 // points in the map (after filtering)
+  int levels = 0;                  // box levels, level 0 = leaves of 32 points
+  long long cnt[8] = {0}, pad[8] = {0};
+  size_t off[8] = {0};             // float offset of each level's six box arrays inside `boxes`
+  float *boxes = nullptr; size_t cap_boxes = 0;
+  uint32_t *keys[2] = {nullptr, nullptr}, *vals[2] = {nullptr, nullptr};
+  size_t cap_keys[2] = {0, 0}, cap_vals[2] = {0, 0};
+  uint32_t *ghist = nullptr; size_t cap_ghist = 0;
+  float4 *spos = nullptr; size_t cap_spos = 0;
+  unsigned long long *d_count = nullptr;
+  int sorted = 0;                  // which of keys[]/vals[] holds the sorted pairs
+  long long n_sorted_pad = 0;
+  const float4 *power = nullptr;   // rgb power per ORIGINAL index (not owned)
+  const float4 *src_pos = nullptr; // positions per ORIGINAL index (not owned)
+};
+cudaError_t knn_build(KnnMap &m, const float4 *pos, const float4 *power, long long n, int filter, cudaStream_t st, int *launches);
+cudaError_t knn_query(const KnnMap &m, const float4 *queries, long long nq, int k, float max_r2, int32_t *idx, float *d2, int32_t *cnt,
+                      int volume, float4 *rgb, int num_sms, cudaStream_t st);
+void knn_free(KnnMap &m);
+
 }  // namespace pm

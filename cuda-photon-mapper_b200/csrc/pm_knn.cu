@@ -1,0 +1,525 @@
+// pm_knn.cu -- Mode B photon map (sm_100a): Morton keys -> hand-written LSD radix sort -> implicit 32-wide LBVH ->
+// warp-cooperative k-nearest-photon search.
+//
+// The reference has no counterpart (its photon map is a dense voxel grid); the definition of every stage is
+// the CPU oracle oracle/knn_oracle.c, and k-NN index sets are required to match it bit for bit.
+//
+// Layout / algorithm (all sizes for n photons):
+//   keys[n']        30-bit Morton code of the position clamped to the map's world box (10 bits/axis, x lowest), n' = n
+//                   rounded up to the sort tile; records that are not wall hits and the padding get key 0xFFFFFFFF
+//   radix sort      4 passes x 8-bit digits over (key, index) pairs: per-tile histogram -> exclusive scan of the
+//                   digit-major histogram table -> stable scatter (ranks from warp match_any + per-warp digit counters)
+//   spos[n]         float4 (x, y, z, bits(original record index)) in sorted order: a leaf = 32 consecutive rows = one
+//                   coalesced 512-byte load by one warp
+//   tree            implicit and 32-wide: level 0 = leaves, level l+1 groups 32 entities of level l; only axis-aligned
+//                   boxes are stored, as six float arrays per level, so the 32 lanes of a warp test the 32 children of a
+//                   node with six coalesced loads.  The two top levels (<= 1056 boxes, 25 KB) are staged into shared
+//                   memory once per CTA with a TMA bulk copy (cp.async.bulk + mbarrier).
+//   query           one warp per query.  Depth-first, nearest child first (warp min-reduction over the lanes' box
+//                   distances), pruned by the current k-th distance.  Candidates of a leaf that beat the current k-th
+//                   key are appended to a per-warp shared-memory buffer; every 32 candidates the buffer is sorted (bitonic,
+//                   shuffles) and merged into the sorted top-K list that lives in registers (K/32 keys per lane).
+//                   Keys are (bits(d2) << 32 | original index): the k smallest keys are exactly the oracle's answer.
+//                   Pruning is conservative in FP32: a box's distance is computed with the same association as a point's,
+//                   so by monotonicity of rounding it never exceeds the distance of any point inside it.
+#include <cuda/std/limits>
+
+#include "pm_kernels.cuh"
+
+namespace pm {
+
+// ---------------------------------------------------------------------------------------------------------
+// Morton keys
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t spread10(uint32_t v) {
+  v &= 1023u;
+  v = (v | (v << 16)) & 0x030000FFu;
+  v = (v | (v << 8)) & 0x0300F00Fu;
+  v = (v | (v << 4)) & 0x030C30C3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+__device__ __forceinline__ uint32_t quant10(float p, float lo, float inv_extent) {
+  float f = (p - lo) * inv_extent * 1024.0f;
+  if (!(f > 0.0f)) return 0u;
+  if (f >= 1023.0f) return 1023u;
+  return (uint32_t)f;
+}
+__device__ __forceinline__ uint32_t morton30(float x, float y, float z) {
+  return spread10(quant10(x, -1.5f, 1.0f / 3.0f)) | (spread10(quant10(y, -1.5f, 1.0f / 3.0f)) << 1) |
+         (spread10(quant10(z, 0.0f, 1.0f / 6.0f)) << 2);
+}
+
+// filter: 0 = every row is a point; 1 = keep only wall hits (meta type == 1) of a record buffer
+__global__ void __launch_bounds__(256) morton_kernel(const float4 *__restrict__ pos, long long n, long long n_pad, int filter,
+                                                     uint32_t *__restrict__ keys, uint32_t *__restrict__ vals,
+                                                     unsigned long long *__restrict__ n_valid) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pad) return;
+  uint32_t key = 0xFFFFFFFFu;
+  if (i < n) {
+    float4 p = pos[i];
+    bool keep = true;
+    if (filter) { int seq, kind, type, id; unpack_meta(__float_as_uint(p.w), seq, kind, type, id); keep = (type == 1); }
+    if (keep) key = morton30(p.x, p.y, p.z);
+  }
+  keys[i] = key; vals[i] = (uint32_t)i;
+  unsigned m = __ballot_sync(__activemask(), key != 0xFFFFFFFFu);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_valid, (unsigned long long)__popc(m));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// radix sort: (key, value) pairs, 8-bit digits, stable
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kSortThreads = 256, kSortRows = 16, kSortTile = kSortThreads * kSortRows;   // 4096 pairs per CTA
+
+__global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const uint32_t *__restrict__ keys, int shift, uint32_t nb,
+                                                                  uint32_t *__restrict__ ghist) {
+  __shared__ uint32_t sh[256];
+  sh[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t *k = keys + (size_t)blockIdx.x * kSortTile;
+#pragma unroll
+  for (int r = 0; r < kSortRows; r++) atomicAdd(&sh[(k[r * kSortThreads + threadIdx.x] >> shift) & 255u], 1u);
+  __syncthreads();
+  ghist[(size_t)threadIdx.x * nb + blockIdx.x] = sh[threadIdx.x];   // digit-major: a flat exclusive scan gives the offsets
+}
+
+// in-place exclusive scan of m counters by one CTA (m = 256 * tiles: 1 M entries at 16 M keys)
+__global__ void __launch_bounds__(1024) scan_kernel(uint32_t *__restrict__ a, size_t m) {
+  __shared__ uint32_t part[1024];
+  const size_t per = (m + 1023) / 1024, lo = per * threadIdx.x, hi = lo + per < m ? lo + per : m;
+  uint32_t s = 0;
+  for (size_t i = lo; i < hi; i++) s += a[i];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {   // Hillis-Steele over the 1024 partial sums
+    uint32_t v = threadIdx.x >= off ? part[threadIdx.x - off] : 0u;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  uint32_t run = threadIdx.x ? part[threadIdx.x - 1] : 0u;
+  for (size_t i = lo; i < hi; i++) { uint32_t v = a[i]; a[i] = run; run += v; }
+}
+
+__global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                                                                     uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
+                                                                     int shift, uint32_t nb, const uint32_t *__restrict__ gbase) {
+  __shared__ uint32_t wh[kSortThreads / 32][256];   // per-warp digit counters, then per-warp output offsets
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < (kSortThreads / 32) * 256; i += kSortThreads) (&wh[0][0])[i] = 0;
+  __syncthreads();
+  // tile order (== stable order): warp w, row r, lane  ->  (w * rows + r) * 32 + lane
+  const size_t base = (size_t)blockIdx.x * kSortTile + (size_t)w * kSortRows * 32 + lane;
+  uint32_t key[kSortRows], val[kSortRows], rank[kSortRows];
+#pragma unroll
+  for (int r = 0; r < kSortRows; r++) { key[r] = keys_in[base + r * 32]; val[r] = vals_in[base + r * 32]; }
+#pragma unroll
+  for (int r = 0; r < kSortRows; r++) {
+    uint32_t d = (key[r] >> shift) & 255u;
+    unsigned peers = __match_any_sync(0xffffffffu, d);
+    int leader = __ffs(peers) - 1;
+    uint32_t old = 0;
+    if (lane == leader) { old = wh[w][d]; wh[w][d] = old + __popc(peers); }
+    old = __shfl_sync(0xffffffffu, old, leader);
+    rank[r] = old + __popc(peers & ((1u << lane) - 1u));
+    __syncwarp();
+  }
+  __syncthreads();
+  {   // thread d: exclusive scan over the warps, starting at this tile's global offset for digit d
+    uint32_t run = gbase[(size_t)threadIdx.x * nb + blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < kSortThreads / 32; i++) { uint32_t t = wh[i][threadIdx.x]; wh[i][threadIdx.x] = run; run += t; }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < kSortRows; r++) {
+    uint32_t d = (key[r] >> shift) & 255u;
+    uint32_t p = wh[w][d] + rank[r];
+    keys_out[p] = key[r]; vals_out[p] = val[r];
+  }
+}
+
+// sorted rows: (x, y, z, bits(original index))
+__global__ void __launch_bounds__(256) permute_kernel(const float4 *__restrict__ pos, const uint32_t *__restrict__ vals, long long n,
+                                                      float4 *__restrict__ spos) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t v = vals[i];
+  float4 p = pos[v];
+  spos[i] = make_float4(p.x, p.y, p.z, __uint_as_float(v));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// boxes: one warp per parent, lane = child
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// level 0: boxes of the leaves (32 sorted photons each).  out = six arrays of length p_out (entries >= n_out stay empty)
+__global__ void __launch_bounds__(256) leaf_box_kernel(const float4 *__restrict__ spos, long long n, long long n_out, long long p_out,
+                                                       float *__restrict__ out) {
+  long long e = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (e >= p_out) return;
+  const float inf = cuda::std::numeric_limits<float>::infinity();
+  float lx = inf, ly = inf, lz = inf, hx = -inf, hy = -inf, hz = -inf;
+  long long i = e * 32 + lane;
+  if (e < n_out && i < n) { float4 p = spos[i]; lx = hx = p.x; ly = hy = p.y; lz = hz = p.z; }
+  lx = warp_min(lx); ly = warp_min(ly); lz = warp_min(lz); hx = warp_max(hx); hy = warp_max(hy); hz = warp_max(hz);
+  if (lane == 0) { out[e] = lx; out[p_out + e] = ly; out[2 * p_out + e] = lz; out[3 * p_out + e] = hx; out[4 * p_out + e] = hy; out[5 * p_out + e] = hz; }
+}
+__global__ void __launch_bounds__(256) node_box_kernel(const float *__restrict__ in, long long n_in, long long p_in, long long n_out,
+                                                       long long p_out, float *__restrict__ out) {
+  long long e = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (e >= p_out) return;
+  const float inf = cuda::std::numeric_limits<float>::infinity();
+  float lx = inf, ly = inf, lz = inf, hx = -inf, hy = -inf, hz = -inf;
+  long long c = e * 32 + lane;
+  if (e < n_out && c < n_in) { lx = in[c]; ly = in[p_in + c]; lz = in[2 * p_in + c]; hx = in[3 * p_in + c]; hy = in[4 * p_in + c]; hz = in[5 * p_in + c]; }
+  lx = warp_min(lx); ly = warp_min(ly); lz = warp_min(lz); hx = warp_max(hx); hy = warp_max(hy); hz = warp_max(hz);
+  if (lane == 0) { out[e] = lx; out[p_out + e] = ly; out[2 * p_out + e] = lz; out[3 * p_out + e] = hx; out[4 * p_out + e] = hy; out[5 * p_out + e] = hz; }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// k-NN query
+// ---------------------------------------------------------------------------------------------------------
+typedef unsigned long long u64;
+constexpr u64 kMaxKey = ~0ull;
+
+__device__ __forceinline__ void cmpx(u64 &a, u64 other, bool keep_min) { a = (keep_min == (other < a)) ? other : a; }
+
+// bitonic sort of one key per lane, ascending by lane
+__device__ __forceinline__ u64 warp_sort32(u64 v, int lane) {
+#pragma unroll
+  for (int size = 2; size <= 32; size <<= 1)
+#pragma unroll
+    for (int stride = size >> 1; stride; stride >>= 1) {
+      u64 o = __shfl_xor_sync(0xffffffffu, v, stride);
+      bool asc = (lane & size) == 0, lower = (lane & stride) == 0;
+      cmpx(v, o, asc == lower);
+    }
+  return v;
+}
+
+// top-K list: K = 32*KL keys, global position i lives in slot i/32 of lane i%32, ascending
+template <int KL>
+struct TopK {
+  u64 s[KL];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int i = 0; i < KL; i++) s[i] = kMaxKey;
+  }
+  // merge 32 candidates (one per lane, any order, kMaxKey = none) keeping the K smallest
+  __device__ __forceinline__ void merge(u64 cand, int lane) {
+    cand = warp_sort32(cand, lane);
+    u64 rev = __shfl_sync(0xffffffffu, cand, 31 - lane);
+    s[KL - 1] = rev < s[KL - 1] ? rev : s[KL - 1];   // lower half of (list, padded candidates): a bitonic sequence
+#pragma unroll
+    for (int st = KL / 2; st; st >>= 1)              // strides >= 32: between slots of the same lane
+#pragma unroll
+      for (int i = 0; i < KL; i++)
+        if ((i & st) == 0) { u64 a = s[i], b = s[i | st]; s[i] = a < b ? a : b; s[i | st] = a < b ? b : a; }
+#pragma unroll
+    for (int stride = 16; stride; stride >>= 1)      // strides < 32: between lanes of the same slot
+#pragma unroll
+      for (int i = 0; i < KL; i++) { u64 o = __shfl_xor_sync(0xffffffffu, s[i], stride); cmpx(s[i], o, (lane & stride) == 0); }
+  }
+  __device__ __forceinline__ u64 at(int pos) const {   // warp-uniform pos
+    u64 v = s[0];
+#pragma unroll
+    for (int i = 1; i < KL; i++) v = (pos >> 5) == i ? s[i] : v;
+    return __shfl_sync(0xffffffffu, v, pos & 31);
+  }
+};
+
+struct TreeView {
+  const float4 *spos;
+  long long n;            // points
+  int levels;             // number of box levels (level 0 = leaves); 0 when n == 0
+  long long cnt[8];       // entities per level
+  long long pad[8];       // padded (multiple of 32) array length per level
+  const float *box[8];    // six arrays of length pad[l] each
+  int staged_from;        // levels >= staged_from are read from shared memory
+  long long staged_floats;
+};
+
+constexpr int kQueryThreads = 256;
+constexpr int kMaxStagedFloats = 6 * (1024 + 32);
+
+__device__ __forceinline__ float box_dist2(float lx, float ly, float lz, float hx, float hy, float hz, float qx, float qy, float qz) {
+  float dx = fmaxf(fmaxf(lx - qx, 0.0f), qx - hx), dy = fmaxf(fmaxf(ly - qy, 0.0f), qy - hy), dz = fmaxf(fmaxf(lz - qz, 0.0f), qz - hz);
+  return (dx * dx + dy * dy) + dz * dz;
+}
+
+// The search itself, for one warp and one query point; returns with `top` holding the k smallest keys.
+template <int KL>
+__device__ __forceinline__ void knn_search(const TreeView &tv, const float *__restrict__ sbox, u64 *__restrict__ pend, float qx, float qy,
+                                           float qz, int k, float max_r2, int lane, TopK<KL> &top) {
+  top.init();
+  float thr_d2 = max_r2;        // prune boxes farther than this; candidates need d2 <= max_r2 and key < thr_key
+  u64 thr_key = kMaxKey;
+  int npend = 0;
+  if (tv.n <= 0) return;
+
+  auto leaf = [&](long long e) {
+    long long i = e * 32 + lane;
+    u64 key = kMaxKey;
+    if (i < tv.n) {
+      float4 p = __ldg(tv.spos + i);
+      float dx = p.x - qx, dy = p.y - qy, dz = p.z - qz;
+      float d2 = (dx * dx + dy * dy) + dz * dz;
+      if (d2 <= max_r2) key = ((u64)__float_as_uint(d2) << 32) | __float_as_uint(p.w);
+    }
+    bool pass = key < thr_key;
+    unsigned m = __ballot_sync(0xffffffffu, pass);
+    if (!m) return;
+    if (pass) pend[npend + __popc(m & ((1u << lane) - 1u))] = key;
+    npend += __popc(m);
+    __syncwarp();
+    if (npend >= 32) {
+      top.merge(pend[lane], lane);
+      u64 rest = lane + 32 < npend ? pend[lane + 32] : kMaxKey;
+      __syncwarp();
+      pend[lane] = rest;
+      npend -= 32;
+      __syncwarp();
+      thr_key = top.at(k - 1);
+      if (thr_key != kMaxKey) thr_d2 = fminf(max_r2, __uint_as_float((uint32_t)(thr_key >> 32)));
+    }
+  };
+
+  const int topl = tv.levels - 1;   // the root groups the entities of this level
+  if (topl == 0) {                  // <= 32 leaves... handled by the generic walk below with a virtual root
+  }
+  // per-level traversal state is warp-uniform; level l's (node, visited mask) is parked in lane l's registers
+  long long my_node = 0; unsigned my_mask = 0;
+  int level = tv.levels;            // "virtual" level above the top: its single node 0 has the top-level entities as children
+  for (;;) {
+    // children of node `j` at `level` are entities 32*j .. 32*j+31 of level-1
+    long long j = __shfl_sync(0xffffffffu, my_node, level);
+    unsigned visited = __shfl_sync(0xffffffffu, my_mask, level);
+    int cl = level - 1;
+    long long e = j * 32 + lane;
+    float d = cuda::std::numeric_limits<float>::infinity();
+    if (e < tv.cnt[cl] && !((visited >> lane) & 1u)) {
+      float lx, ly, lz, hx, hy, hz;
+      if (cl >= tv.staged_from) {
+        const float *b = sbox; for (int l = tv.staged_from; l < cl; l++) b += 6 * tv.pad[l];
+        long long p = tv.pad[cl];
+        lx = b[e]; ly = b[p + e]; lz = b[2 * p + e]; hx = b[3 * p + e]; hy = b[4 * p + e]; hz = b[5 * p + e];
+      } else {
+        const float *b = tv.box[cl]; long long p = tv.pad[cl];
+        lx = __ldg(b + e); ly = __ldg(b + p + e); lz = __ldg(b + 2 * p + e); hx = __ldg(b + 3 * p + e); hy = __ldg(b + 4 * p + e); hz = __ldg(b + 5 * p + e);
+      }
+      d = box_dist2(lx, ly, lz, hx, hy, hz, qx, qy, qz);
+    }
+    uint32_t bits = __float_as_uint(d);
+    bool ok = d <= thr_d2 && bits < 0x7f800000u;
+    uint32_t mn = __reduce_min_sync(0xffffffffu, ok ? bits : 0xffffffffu);
+    if (mn == 0xffffffffu) {          // nothing (left) to visit under this node: pop
+      level++;
+      if (level > tv.levels) break;
+      continue;
+    }
+    int c = __ffs(__ballot_sync(0xffffffffu, ok && bits == mn)) - 1;
+    if (lane == level) my_mask |= 1u << c;
+    long long child = j * 32 + c;
+    if (cl == 0) leaf(child);
+    else { level = cl; if (lane == level) { my_node = child; my_mask = 0; } }
+  }
+  if (npend > 0) {
+    top.merge(lane < npend ? pend[lane] : kMaxKey, lane);
+    __syncwarp();
+  }
+}
+
+// stage the top box levels into shared memory with one TMA bulk copy per CTA
+__device__ __forceinline__ void stage_top_levels(const TreeView &tv, float *sbox, unsigned long long *bar) {
+  if (tv.staged_floats <= 0) return;
+  const uint32_t bytes = (uint32_t)(tv.staged_floats * sizeof(float));
+  const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(bar), dst_a = (uint32_t)__cvta_generic_to_shared(sbox);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_a),
+                 "l"(tv.box[tv.staged_from]), "r"(bytes), "r"(bar_a)
+                 : "memory");
+  }
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar_a) : "memory");
+  }
+}
+
+// mode 0: write indices / distances / counts.  mode 1: radiance estimate (sum of powers / disc area or ball volume)
+template <int KL>
+__global__ void __launch_bounds__(kQueryThreads) knn_query_kernel(const __grid_constant__ TreeView tv, const float4 *__restrict__ queries,
+                                                                  long long nq, int k, float max_r2, int32_t *__restrict__ out_idx,
+                                                                  float *__restrict__ out_d2, int32_t *__restrict__ out_cnt,
+                                                                  const float4 *__restrict__ power, int volume, float4 *__restrict__ out_rgb) {
+  __shared__ __align__(128) float sbox[kMaxStagedFloats];
+  __shared__ __align__(8) unsigned long long bar;
+  __shared__ u64 pend_all[kQueryThreads / 32][64];
+  stage_top_levels(tv, sbox, &bar);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  u64 *pend = pend_all[w];
+  const long long warps = (long long)gridDim.x * (kQueryThreads / 32);
+  for (long long q = (long long)blockIdx.x * (kQueryThreads / 32) + w; q < nq; q += warps) {
+    float4 qp = __ldg(queries + q);
+    TopK<KL> top;
+    knn_search<KL>(tv, sbox, pend, qp.x, qp.y, qp.z, k, max_r2, lane, top);
+    if (out_rgb) {
+      float r = 0.0f, g = 0.0f, b = 0.0f, rk2 = 0.0f; int cnt = 0;
+#pragma unroll
+      for (int i = 0; i < KL; i++) {
+        int pos = i * 32 + lane;
+        if (pos < k && top.s[i] != kMaxKey) {
+          float4 pw = __ldg(power + (uint32_t)(top.s[i] & 0xffffffffu));
+          r += pw.x; g += pw.y; b += pw.z; cnt++;
+          rk2 = fmaxf(rk2, __uint_as_float((uint32_t)(top.s[i] >> 32)));
+        }
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        r += __shfl_xor_sync(0xffffffffu, r, o); g += __shfl_xor_sync(0xffffffffu, g, o); b += __shfl_xor_sync(0xffffffffu, b, o);
+        rk2 = fmaxf(rk2, __shfl_xor_sync(0xffffffffu, rk2, o));
+      }
+      if (lane == 0) {
+        const float PI = 3.14159265358979323846f;
+        float den = volume ? (4.0f / 3.0f) * PI * rk2 * __fsqrt_rn(rk2) : PI * rk2;
+        float inv = den > 0.0f ? __fdiv_rn(1.0f, den) : 0.0f;
+        out_rgb[q] = make_float4(r * inv, g * inv, b * inv, rk2);
+      }
+    } else {
+      int cnt = 0;
+#pragma unroll
+      for (int i = 0; i < KL; i++) {
+        int pos = i * 32 + lane;
+        if (pos < k) {
+          bool have = top.s[i] != kMaxKey;
+          out_idx[q * k + pos] = have ? (int32_t)(uint32_t)(top.s[i] & 0xffffffffu) : -1;
+          out_d2[q * k + pos] = have ? __uint_as_float((uint32_t)(top.s[i] >> 32)) : cuda::std::numeric_limits<float>::infinity();
+          cnt += have ? 1 : 0;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      if (lane == 0) out_cnt[q] = cnt;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side of the build / query
+// ---------------------------------------------------------------------------------------------------------
+static cudaError_t ensure(void **p, size_t *cap, size_t bytes) {
+  if (bytes <= *cap) return cudaSuccess;
+  cudaFree(*p); *p = nullptr; *cap = 0;
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e == cudaSuccess) *cap = bytes;
+  return e;
+}
+
+#define KCK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
+
+cudaError_t knn_build(KnnMap &m, const float4 *pos, const float4 *power, long long n, int filter, cudaStream_t st, int *launches) {
+  m.n = 0; m.levels = 0; m.power = power; m.src_pos = pos;
+  if (n <= 0) return cudaSuccess;
+  const long long tiles = (n + kSortTile - 1) / kSortTile, n_pad = tiles * kSortTile;
+  KCK(ensure((void **)&m.keys[0], &m.cap_keys[0], sizeof(uint32_t) * n_pad));
+  KCK(ensure((void **)&m.keys[1], &m.cap_keys[1], sizeof(uint32_t) * n_pad));
+  KCK(ensure((void **)&m.vals[0], &m.cap_vals[0], sizeof(uint32_t) * n_pad));
+  KCK(ensure((void **)&m.vals[1], &m.cap_vals[1], sizeof(uint32_t) * n_pad));
+  KCK(ensure((void **)&m.ghist, &m.cap_ghist, sizeof(uint32_t) * 256 * tiles));
+  KCK(ensure((void **)&m.spos, &m.cap_spos, sizeof(float4) * n));
+  if (!m.d_count) KCK(cudaMalloc(&m.d_count, sizeof(unsigned long long)));
+  KCK(cudaMemsetAsync(m.d_count, 0, sizeof(unsigned long long), st));
+  morton_kernel<<<(unsigned)((n_pad + 255) / 256), 256, 0, st>>>(pos, n, n_pad, filter, m.keys[0], m.vals[0], m.d_count);
+  (*launches)++;
+  int cur = 0;
+  for (int pass = 0; pass < 4; pass++) {
+    radix_hist_kernel<<<(unsigned)tiles, kSortThreads, 0, st>>>(m.keys[cur], pass * 8, (uint32_t)tiles, m.ghist);
+    scan_kernel<<<1, 1024, 0, st>>>(m.ghist, (size_t)256 * tiles);
+    radix_scatter_kernel<<<(unsigned)tiles, kSortThreads, 0, st>>>(m.keys[cur], m.vals[cur], m.keys[cur ^ 1], m.vals[cur ^ 1], pass * 8,
+                                                                    (uint32_t)tiles, m.ghist);
+    cur ^= 1;
+    *launches += 3;
+  }
+  m.sorted = cur;
+  KCK(cudaGetLastError());
+  unsigned long long nv = 0;
+  KCK(cudaMemcpyAsync(&nv, m.d_count, sizeof(nv), cudaMemcpyDeviceToHost, st));
+  KCK(cudaStreamSynchronize(st));   // the number of kept points sizes the tree
+  m.n = (long long)nv; m.n_sorted_pad = n_pad;
+  if (m.n == 0) return cudaSuccess;
+  permute_kernel<<<(unsigned)((m.n + 255) / 256), 256, 0, st>>>(pos, m.vals[cur], m.n, m.spos);
+  (*launches)++;
+  // level geometry
+  long long cnt = (m.n + 31) / 32; int L = 0; size_t total = 0;
+  for (;;) {
+    m.cnt[L] = cnt; m.pad[L] = (cnt + 31) / 32 * 32; m.off[L] = total; total += 6 * (size_t)m.pad[L];
+    L++;
+    if (cnt <= 32) break;
+    cnt = (cnt + 31) / 32;
+  }
+  m.levels = L;
+  KCK(ensure((void **)&m.boxes, &m.cap_boxes, sizeof(float) * total));
+  leaf_box_kernel<<<(unsigned)((m.pad[0] * 32 + 255) / 256), 256, 0, st>>>(m.spos, m.n, m.cnt[0], m.pad[0], m.boxes + m.off[0]);
+  (*launches)++;
+  for (int l = 1; l < L; l++) {
+    node_box_kernel<<<(unsigned)((m.pad[l] * 32 + 255) / 256), 256, 0, st>>>(m.boxes + m.off[l - 1], m.cnt[l - 1], m.pad[l - 1], m.cnt[l],
+                                                                             m.pad[l], m.boxes + m.off[l]);
+    (*launches)++;
+  }
+  return cudaGetLastError();
+}
+
+static TreeView make_view(const KnnMap &m) {
+  TreeView tv;
+  memset(&tv, 0, sizeof(tv));
+  tv.spos = m.spos; tv.n = m.n; tv.levels = m.levels;
+  for (int l = 0; l < m.levels; l++) { tv.cnt[l] = m.cnt[l]; tv.pad[l] = m.pad[l]; tv.box[l] = m.boxes + m.off[l]; }
+  // stage the top two levels (they are contiguous at the end of the box allocation) if they fit
+  tv.staged_from = m.levels; tv.staged_floats = 0;
+  for (int l = m.levels - 1; l >= 0 && l >= m.levels - 2; l--) {
+    long long f = tv.staged_floats + 6 * m.pad[l];
+    if (f > kMaxStagedFloats) break;
+    tv.staged_floats = f; tv.staged_from = l;
+  }
+  return tv;
+}
+
+cudaError_t knn_query(const KnnMap &m, const float4 *queries, long long nq, int k, float max_r2, int32_t *idx, float *d2, int32_t *cnt,
+                      int volume, float4 *rgb, int num_sms, cudaStream_t st) {
+  if (nq <= 0) return cudaSuccess;
+  TreeView tv = make_view(m);
+  long long want = (nq + kQueryThreads / 32 - 1) / (kQueryThreads / 32), cap = (long long)num_sms * 16;
+  unsigned grid = (unsigned)(want < cap ? want : cap);
+  const float4 *pw = m.power;
+  if (k <= 32) knn_query_kernel<1><<<grid, kQueryThreads, 0, st>>>(tv, queries, nq, k, max_r2, idx, d2, cnt, pw, volume, rgb);
+  else if (k <= 64) knn_query_kernel<2><<<grid, kQueryThreads, 0, st>>>(tv, queries, nq, k, max_r2, idx, d2, cnt, pw, volume, rgb);
+  else knn_query_kernel<4><<<grid, kQueryThreads, 0, st>>>(tv, queries, nq, k, max_r2, idx, d2, cnt, pw, volume, rgb);
+  return cudaGetLastError();
+}
+
+void knn_free(KnnMap &m) {
+  cudaFree(m.keys[0]); cudaFree(m.keys[1]); cudaFree(m.vals[0]); cudaFree(m.vals[1]); cudaFree(m.ghist); cudaFree(m.spos);
+  cudaFree(m.boxes); cudaFree(m.d_count);
+  m = KnnMap();
+}
+
+}  // namespace pm

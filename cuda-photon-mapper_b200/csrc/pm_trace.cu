@@ -40,8 +40,8 @@ __global__ void __launch_bounds__(256) mwc_table_kernel(float4 *__restrict__ tab
 // ------------------------------------------------------------------------------------------------------
 struct Sink {
   unsigned long long *acc;       // kAccEntries, or nullptr (PM_TRACE_NO_MAP)
-  float4 *rec_pos, *rec_pow, *rec_dir;
-  unsigned long long *rec_count; // global append cursor
+  float4 *rec_pos, *rec_pow, *rec_dir;   // surface records: appended (surface_kernel) / volume records: slot = 3*(index-first)+step
+  unsigned long long *rec_count; // global append cursor (surface records)
   long long rec_cap;
 };
 
@@ -109,7 +109,13 @@ __global__ void __launch_bounds__(256) volume_kernel(const __grid_constant__ Dev
           acc_add(p + 2, __double2ll_rn((double)e.z * kVoxScale));
         }
       }
-      if (rec) append_record(sk, i, 1, -1, -1, index, P, V(0.0f, 0.0f, 0.0f), e);
+      if (rec) {   // volume records have a fixed slot: deterministic order, coalesced, no atomics
+        long long slot = 3 * (gi - first) + i;
+        if (slot < sk.rec_cap) {
+          sk.rec_pos[slot] = make_float4(P.x, P.y, P.z, __uint_as_float(pack_meta(i, 1, -1, -1)));
+          sk.rec_pow[slot] = make_float4(e.x, e.y, e.z, __int_as_float(index));
+        }
+      }
       const float4 tr = i == 0 ? t0 : (i == 1 ? t1 : t2);
       v3 r;
       r.x = rand_float(s, tr.x);

@@ -101,12 +101,34 @@ int pm_get_map_host(pm_context *ctx, float *host_grid /* 32*32*32*3 */);
 int pm_set_map_host(pm_context *ctx, const float *host_grid);      /* inject a photon map (parity tests) */
 int pm_map_device(pm_context *ctx, float **dev_grid);
 
-/* photon records (valid after pm_trace with PM_TRACE_RECORDS) */
+/* photon records (valid after pm_trace with PM_TRACE_RECORDS).  Two SoA float4 buffer sets: PM_MAP_SURFACE holds the
+ * storePhoton calls (surface + shadow photons, appended with warp-aggregated atomics, capacity = max_records),
+ * PM_MAP_VOLUME the storeVolumePhoton calls (fixed slot 3*(index-first)+step, sized by the library). */
+#define PM_MAP_SURFACE 0
+#define PM_MAP_VOLUME  1
 int pm_set_record_capacity(pm_context *ctx, int64_t max_records);
-int pm_record_count(pm_context *ctx, int64_t *n);                  /* synchronises */
+int pm_record_count(pm_context *ctx, int64_t *n);                  /* both sets; synchronises */
 int pm_get_records_host(pm_context *ctx, pm_record *host_out, int64_t max_records);   /* canonical (index, call) order */
-int pm_record_buffers(pm_context *ctx, float **dev_pos_meta /* float4[] */, float **dev_power_index /* float4[] */,
-                      float **dev_dir /* float4[] */);
+int pm_record_buffers(pm_context *ctx, int which, float **dev_pos_meta /* float4[] */, float **dev_power_index /* float4[] */,
+                      float **dev_dir /* float4[] or NULL */, int64_t *count /* synchronises */);
+
+/* stage 2 (Mode B): photon-map build = Morton keys + radix sort + implicit 32-wide LBVH, and stage 4: k-nearest-photon
+ * search.  The reference has no counterpart; the definition is oracle/knn_oracle.c (brute force, (d2, index) order).
+ * pm_knn_build uses the record buffers of the last PM_TRACE_RECORDS trace (surface map: wall hits only);
+ * pm_knn_build_points builds over any DEVICE point set (float4 xyz+ignored, float4 power rgb+ignored; the arrays must
+ * stay alive while the map is used) -- e.g. all-gathered records of several GPUs. */
+int pm_knn_build(pm_context *ctx, int which);
+int pm_knn_build_points(pm_context *ctx, int which, const float *dev_pos4, const float *dev_power4, int64_t n);
+int pm_knn_size(pm_context *ctx, int which, int64_t *n_points, int32_t *n_levels);
+/* nq DEVICE queries (float4, w ignored); per query up to k photons with d2 <= max_r2 (INFINITY: pure k-NN), ascending
+ * (d2, index): dev_idx[nq*k] (original indices, -1 = none), dev_d2[nq*k], dev_cnt[nq].  k <= 128. */
+int pm_knn_query(pm_context *ctx, int which, const float *dev_queries4, int64_t nq, int k, float max_r2,
+                 int32_t *dev_idx, float *dev_d2, int32_t *dev_cnt);
+/* radiance estimate per query: dev_rgb4[q] = (sum of the found powers / (pi r_k^2) [surface] or (4/3 pi r_k^3) [volume], r_k^2) */
+int pm_knn_radiance(pm_context *ctx, int which, const float *dev_queries4, int64_t nq, int k, float max_r2, float *dev_rgb4);
+/* build products for the parity tests: sorted Morton keys + permutation (host), box arrays of one level (host) */
+int pm_knn_sorted_host(pm_context *ctx, int which, uint32_t *host_keys, uint32_t *host_perm, int64_t n);
+int pm_knn_level_host(pm_context *ctx, int which, int level, int64_t *count, float *host_boxes6 /* [6][count] or NULL */);
 
 /* stages 3-5: eye rays, photon-map gather, volumetric ray-march (PMK:926-1017, :1409-1462).
  * Renders rows [y0,y1) of a width x height frame.  dev_rgba (uchar4, may be NULL) and dev_rgbf (float4 =

@@ -1,0 +1,123 @@
+/* oracle/knn_oracle.c -- TEST INFRASTRUCTURE: CPU oracle for the Mode B photon-map pipeline (Morton keys, stable
+ * key sort, brute-force k-nearest-photon search, radiance estimate).
+ *
+ * The reference has NO counterpart for these stages (its photon map is a dense voxel grid), so there is
+ * nothing of the reference's to pin them against: PARITY UNPINNED BY THE REFERENCE.  The oracle is instead the
+ * definition itself, written the slow obvious way (last row):
+ *   - Morton key: 10 bits per axis over the map's world box (PMK:21-23), bit-interleaved x (lowest), y, z;
+ *   - sort oracle: stable sort on the key;
+ *   - k-NN: over ALL photons, d2 = (dx*dx + dy*dy) + dz*dz in FP32 without contraction, order by (d2, index)
+ *     ascending, keep those with d2 <= max_r2, take k.  Index sets must match bit-exactly.
+ *   - radiance estimate: sum of the k photon powers divided by pi*r_k^2 (surface) or 4/3*pi*r_k^3 (volume), r_k the
+ *     distance of the k-th photon found; summed in (d2, index) order in double.
+ * The only point-based estimator the reference's author ever wrote is the fixed-radius cone filter of the legacy file
+ * (photonMappingKernel - Copy.cu:191-208); it is kept as an optional weight below for relating Mode B back to it.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* expand 10 bits to every third bit */
+static inline uint32_t spread10(uint32_t v) {
+  v &= 1023u;
+  v = (v | (v << 16)) & 0x030000FFu;
+  v = (v | (v << 8)) & 0x0300F00Fu;
+  v = (v | (v << 4)) & 0x030C30C3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+static inline uint32_t quant10(float p, float lo, float inv_extent) {
+  float f = (p - lo) * inv_extent * 1024.0f;
+  if (!(f > 0.0f)) return 0u;        /* negatives and NaN -> cell 0 */
+  if (f >= 1023.0f) return 1023u;
+  return (uint32_t)f;
+}
+/* world box of the photon map: x,y in [-1.5,1.5], z in [0,6]; positions outside are clamped to the border cells */
+uint32_t pmo_morton30(const float p[3]) {
+  uint32_t x = quant10(p[0], -1.5f, 1.0f / 3.0f), y = quant10(p[1], -1.5f, 1.0f / 3.0f), z = quant10(p[2], 0.0f, 1.0f / 6.0f);
+  return spread10(x) | (spread10(y) << 1) | (spread10(z) << 2);
+}
+void pmo_morton30_many(const float *pos4, long n, uint32_t *keys) {
+  for (long i = 0; i < n; i++) keys[i] = pmo_morton30(pos4 + 4 * i);
+}
+
+typedef struct { uint32_t key; uint32_t idx; } kv_t;
+static int kv_cmp(const void *a, const void *b) {
+  const kv_t *x = (const kv_t *)a, *y = (const kv_t *)b;
+  if (x->key != y->key) return x->key < y->key ? -1 : 1;
+  return x->idx < y->idx ? -1 : (x->idx > y->idx ? 1 : 0);   /* index as tie-break == stable */
+}
+/* stable sort of (key, index 0..n-1) pairs: perm[i] = original index of the i-th smallest */
+void pmo_stable_sort_perm(const uint32_t *keys, long n, uint32_t *perm) {
+  kv_t *kv = (kv_t *)malloc(sizeof(kv_t) * (size_t)n);
+  for (long i = 0; i < n; i++) { kv[i].key = keys[i]; kv[i].idx = (uint32_t)i; }
+  qsort(kv, (size_t)n, sizeof(kv_t), kv_cmp);
+  for (long i = 0; i < n; i++) perm[i] = kv[i].idx;
+  free(kv);
+}
+
+static inline float dist2(const float *a, const float *b) {
+  float dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
+  return (dx * dx + dy * dy) + dz * dz;
+}
+static inline uint64_t knn_key(float d2, uint32_t idx) {
+  uint32_t bits;
+  memcpy(&bits, &d2, 4);
+  return ((uint64_t)bits << 32) | idx;   /* d2 >= 0: its bit pattern orders like its value */
+}
+
+/* Brute force.  pos4: n photons as float4 (xyz + ignored w); queries: nq float4.  For each query writes up to k indices
+ * (ascending (d2, index)) to out_idx[q*k..], their d2 to out_d2, and the number found to out_cnt[q]; unused slots get
+ * index -1 / d2 = +inf.  A photon qualifies if d2 <= max_r2 (pass INFINITY for pure k-NN); NaN distances never qualify. */
+void pmo_knn_bruteforce(const float *pos4, long n, const float *queries4, long nq, int k, float max_r2,
+                        int32_t *out_idx, float *out_d2, int32_t *out_cnt) {
+#pragma omp parallel
+  {
+    uint64_t *best = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)(k > 0 ? k : 1));
+#pragma omp for schedule(dynamic, 16)
+    for (long q = 0; q < nq; q++) {
+      int cnt = 0;
+      const float *qp = queries4 + 4 * q;
+      for (long i = 0; i < n; i++) {
+        float d2 = dist2(pos4 + 4 * i, qp);
+        if (!(d2 <= max_r2)) continue;
+        uint64_t key = knn_key(d2, (uint32_t)i);
+        if (cnt == k && key >= best[k - 1]) continue;
+        int j = cnt < k ? cnt : k - 1;           /* insertion into the sorted prefix */
+        while (j > 0 && best[j - 1] > key) { best[j] = best[j - 1]; j--; }
+        best[j] = key;
+        if (cnt < k) cnt++;
+      }
+      for (int j = 0; j < k; j++) {
+        if (j < cnt) {
+          uint32_t bits = (uint32_t)(best[j] >> 32);
+          float d2;
+          memcpy(&d2, &bits, 4);
+          out_idx[q * k + j] = (int32_t)(uint32_t)(best[j] & 0xffffffffu);
+          out_d2[q * k + j] = d2;
+        } else { out_idx[q * k + j] = -1; out_d2[q * k + j] = INFINITY; }
+      }
+      out_cnt[q] = cnt;
+    }
+    free(best);
+  }
+}
+
+/* Radiance estimate from a k-NN result: sum of powers (power4: rgb + ignored w) over the found photons in (d2,index)
+ * order, in double, divided by the disc area pi*r_k^2 (volume == 0) or the ball volume 4/3*pi*r_k^3 (volume != 0),
+ * r_k^2 = the largest d2 found; cnt == 0 or r_k == 0 gives 0. */
+void pmo_knn_estimate(const float *power4, const int32_t *idx, const float *d2, const int32_t *cnt, long nq, int k,
+                      int volume, float *out_rgb3) {
+  const double PI = 3.14159265358979323846;
+  for (long q = 0; q < nq; q++) {
+    double s[3] = {0, 0, 0};
+    int c = cnt[q];
+    for (int j = 0; j < c; j++) {
+      const float *p = power4 + 4 * (long)idx[q * k + j];
+      s[0] += p[0]; s[1] += p[1]; s[2] += p[2];
+    }
+    double r2 = c > 0 ? (double)d2[q * k + c - 1] : 0.0, den = volume ? (4.0 / 3.0) * PI * r2 * sqrt(r2) : PI * r2;
+    for (int ch = 0; ch < 3; ch++) out_rgb3[3 * q + ch] = den > 0.0 ? (float)(s[ch] / den) : 0.0f;
+  }
+}

@@ -55,6 +55,10 @@ class Oracle:
         L.pmo_render.argtypes = [C.POINTER(Scene), C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.pmo_raytrace.restype = C.c_int
+        L.pmo_morton30_many.argtypes = [C.c_void_p, C.c_long, C.c_void_p]
+        L.pmo_stable_sort_perm.argtypes = [C.c_void_p, C.c_long, C.c_void_p]
+        L.pmo_knn_bruteforce.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.pmo_knn_estimate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_void_p]
 
     # -- scene -----------------------------------------------------------------------------------
     def default_scene(self, sz_img=512, animate=1):
@@ -133,3 +137,31 @@ class Oracle:
         p = np.asarray(p, np.float32); c = np.zeros(3, np.float32)
         self.lib.pmo_gather(_p(grid), _p(p), C.c_int(type_), C.c_int(id_), C.c_int(int(interp)), _p(c))
         return c
+
+    # -- Mode B oracle (oracle/knn_oracle.c) ------------------------------------------------------------------
+    def morton30(self, pos4):
+        pos4 = np.ascontiguousarray(pos4, np.float32)
+        keys = np.empty(pos4.shape[0], np.uint32)
+        self.lib.pmo_morton30_many(_p(pos4), pos4.shape[0], _p(keys))
+        return keys
+
+    def stable_sort_perm(self, keys):
+        keys = np.ascontiguousarray(keys, np.uint32)
+        perm = np.empty(keys.shape[0], np.uint32)
+        self.lib.pmo_stable_sort_perm(_p(keys), keys.shape[0], _p(perm))
+        return perm
+
+    def knn_bruteforce(self, pos4, queries4, k, max_r2=np.inf):
+        pos4 = np.ascontiguousarray(pos4, np.float32); queries4 = np.ascontiguousarray(queries4, np.float32)
+        nq = queries4.shape[0]
+        idx = np.empty((nq, k), np.int32); d2 = np.empty((nq, k), np.float32); cnt = np.empty(nq, np.int32)
+        self.lib.pmo_knn_bruteforce(_p(pos4), pos4.shape[0], _p(queries4), nq, k, C.c_float(max_r2), _p(idx), _p(d2), _p(cnt))
+        return idx, d2, cnt
+
+    def knn_estimate(self, power4, idx, d2, cnt, volume):
+        power4 = np.ascontiguousarray(power4, np.float32)
+        nq, k = idx.shape
+        out = np.empty((nq, 3), np.float32)
+        self.lib.pmo_knn_estimate(_p(power4), _p(np.ascontiguousarray(idx)), _p(np.ascontiguousarray(d2)), _p(np.ascontiguousarray(cnt)),
+                                  nq, k, int(volume), _p(out))
+        return out
