@@ -60,9 +60,10 @@ struct pm_context {
   size_t spans_used = 0;
 };
 
-enum { K_MWC_TABLE = 0, K_VOLUME, K_SURFACE, K_BUILD_MAP, K_BUILD_TABLES, K_RENDER, K_COUNT };
+enum { K_MWC_TABLE = 0, K_VOLUME, K_SURFACE, K_BUILD_MAP, K_BUILD_TABLES, K_RENDER, K_KNN_BUILD, K_KNN_QUERY, K_KNN_RENDER, K_COUNT };
 static const char *const kKernelNames[K_COUNT] = {"mwc_table_kernel", "volume_kernel", "surface_kernel", "build_map_kernel",
-                                                   "build_tables_kernel", "render_kernel"};
+                                                   "build_tables_kernel", "render_kernel", "knn_build (all kernels)",
+                                                   "knn_query_kernel", "knn_render_kernel"};
 
 // RAII span: records an event pair around one kernel launch when timing is on
 struct SpanGuard {
@@ -538,7 +539,11 @@ int pm_knn_build_points(pm_context *c, int which, const float *pos4, const float
   ARG(c, n >= 0 && (n == 0 || pos4), "null points");
   CK(c, cudaSetDevice(c->device));
   int launches = 0;
-  cudaError_t e = knn_build(c->knn[which], (const float4 *)pos4, (const float4 *)pow4, n, 0, c->stream, &launches);
+  cudaError_t e;
+  {
+    SpanGuard g(c, K_KNN_BUILD);
+    e = knn_build(c->knn[which], (const float4 *)pos4, (const float4 *)pow4, n, 0, c->stream, &launches);
+  }
   c->launches += launches;
   CK(c, e);
   return PM_OK;
@@ -551,7 +556,11 @@ int pm_knn_build(pm_context *c, int which) {
   if (rc != PM_OK) return rc;
   int launches = 0;
   // surface map: wall hits only (sphere hits carry no energy in the reference either, PMK:1176)
-  cudaError_t e = knn_build(c->knn[which], (const float4 *)pos, (const float4 *)pw, n, which == PM_MAP_SURFACE ? 1 : 0, c->stream, &launches);
+  cudaError_t e;
+  {
+    SpanGuard g(c, K_KNN_BUILD);
+    e = knn_build(c->knn[which], (const float4 *)pos, (const float4 *)pw, n, which == PM_MAP_SURFACE ? 1 : 0, c->stream, &launches);
+  }
   c->launches += launches;
   CK(c, e);
   return PM_OK;
@@ -570,7 +579,10 @@ static int knn_query_common(pm_context *c, int which, const float *q4, int64_t n
   ARG(c, !(max_r2 < 0.0f), "negative radius");
   CK(c, cudaSetDevice(c->device));
   if (rgb4 && !c->knn[which].power && c->knn[which].n > 0) { c->err = "map was built without powers"; return PM_ERR_STATE; }
-  CK(c, knn_query(c->knn[which], (const float4 *)q4, nq, k, max_r2, idx, d2, cnt, which == PM_MAP_VOLUME, (float4 *)rgb4, c->num_sms, c->stream));
+  {
+    SpanGuard g(c, K_KNN_QUERY);
+    CK(c, knn_query(c->knn[which], (const float4 *)q4, nq, k, max_r2, idx, d2, cnt, which == PM_MAP_VOLUME, (float4 *)rgb4, c->num_sms, c->stream));
+  }
   if (nq > 0) c->launches++;
   return PM_OK;
 }
@@ -581,6 +593,22 @@ int pm_knn_query(pm_context *c, int which, const float *q4, int64_t nq, int k, f
 int pm_knn_radiance(pm_context *c, int which, const float *q4, int64_t nq, int k, float max_r2, float *rgb4) {
   ARG(c, c && rgb4, "null output");
   return knn_query_common(c, which, q4, nq, k, max_r2, nullptr, nullptr, nullptr, rgb4);
+}
+int pm_render_knn(pm_context *c, float t, bool media, int width, int height, int y0, int y1, int k, float max_r2, float w_surface,
+                  float w_volume, pm_uchar4 *dev_rgba, float *dev_rgbf) {
+  ARG(c, c != nullptr, "null context");
+  ARG(c, width > 0 && height > 0 && y0 >= 0 && y0 <= y1 && y1 <= height, "bad frame geometry");
+  ARG(c, k >= 1 && k <= 128, "k must be in [1, 128]");
+  if ((c->knn[0].n > 0 && !c->knn[0].power) || (media && c->knn[1].n > 0 && !c->knn[1].power)) { c->err = "maps were built without powers"; return PM_ERR_STATE; }
+  CK(c, cudaSetDevice(c->device));
+  c->dsc = make_device_scene(c->scene, t);
+  {
+    SpanGuard g(c, K_KNN_RENDER);
+    CK(c, knn_render(c->dsc, c->knn[0], c->knn[1], k, max_r2, w_surface, w_volume, width, height, y0, y1, media, (uchar4 *)dev_rgba,
+                     (float4 *)dev_rgbf, c->num_sms, c->stream));
+  }
+  if (y1 > y0) c->launches++;
+  return PM_OK;
 }
 int pm_knn_sorted_host(pm_context *c, int which, uint32_t *keys, uint32_t *perm, int64_t n) {
   ARG(c, c && (which == PM_MAP_SURFACE || which == PM_MAP_VOLUME), "bad map id");

@@ -365,6 +365,30 @@ __device__ __forceinline__ void stage_top_levels(const TreeView &tv, float *sbox
   }
 }
 
+// radiance estimate from a finished search: (sum of the found powers / (pi r_k^2) or (4/3 pi r_k^3), r_k^2), on every lane
+template <int KL>
+__device__ __forceinline__ float4 knn_radiance(const TopK<KL> &top, int k, const float4 *__restrict__ power, int volume, int lane) {
+  float r = 0.0f, g = 0.0f, b = 0.0f, rk2 = 0.0f;
+#pragma unroll
+  for (int i = 0; i < KL; i++) {
+    int pos = i * 32 + lane;
+    if (pos < k && top.s[i] != kMaxKey) {
+      float4 pw = __ldg(power + (uint32_t)(top.s[i] & 0xffffffffu));
+      r += pw.x; g += pw.y; b += pw.z;
+      rk2 = fmaxf(rk2, __uint_as_float((uint32_t)(top.s[i] >> 32)));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    r += __shfl_xor_sync(0xffffffffu, r, o); g += __shfl_xor_sync(0xffffffffu, g, o); b += __shfl_xor_sync(0xffffffffu, b, o);
+    rk2 = fmaxf(rk2, __shfl_xor_sync(0xffffffffu, rk2, o));
+  }
+  const float PI = 3.14159265358979323846f;
+  float den = volume ? (4.0f / 3.0f) * PI * rk2 * __fsqrt_rn(rk2) : PI * rk2;
+  float inv = den > 0.0f ? __fdiv_rn(1.0f, den) : 0.0f;
+  return make_float4(r * inv, g * inv, b * inv, rk2);
+}
+
 // mode 0: write indices / distances / counts.  mode 1: radiance estimate (sum of powers / disc area or ball volume)
 template <int KL>
 __global__ void __launch_bounds__(kQueryThreads) knn_query_kernel(const __grid_constant__ TreeView tv, const float4 *__restrict__ queries,
@@ -383,27 +407,8 @@ __global__ void __launch_bounds__(kQueryThreads) knn_query_kernel(const __grid_c
     TopK<KL> top;
     knn_search<KL>(tv, sbox, pend, qp.x, qp.y, qp.z, k, max_r2, lane, top);
     if (out_rgb) {
-      float r = 0.0f, g = 0.0f, b = 0.0f, rk2 = 0.0f; int cnt = 0;
-#pragma unroll
-      for (int i = 0; i < KL; i++) {
-        int pos = i * 32 + lane;
-        if (pos < k && top.s[i] != kMaxKey) {
-          float4 pw = __ldg(power + (uint32_t)(top.s[i] & 0xffffffffu));
-          r += pw.x; g += pw.y; b += pw.z; cnt++;
-          rk2 = fmaxf(rk2, __uint_as_float((uint32_t)(top.s[i] >> 32)));
-        }
-      }
-#pragma unroll
-      for (int o = 16; o; o >>= 1) {
-        r += __shfl_xor_sync(0xffffffffu, r, o); g += __shfl_xor_sync(0xffffffffu, g, o); b += __shfl_xor_sync(0xffffffffu, b, o);
-        rk2 = fmaxf(rk2, __shfl_xor_sync(0xffffffffu, rk2, o));
-      }
-      if (lane == 0) {
-        const float PI = 3.14159265358979323846f;
-        float den = volume ? (4.0f / 3.0f) * PI * rk2 * __fsqrt_rn(rk2) : PI * rk2;
-        float inv = den > 0.0f ? __fdiv_rn(1.0f, den) : 0.0f;
-        out_rgb[q] = make_float4(r * inv, g * inv, b * inv, rk2);
-      }
+      float4 est = knn_radiance<KL>(top, k, power, volume, lane);
+      if (lane == 0) out_rgb[q] = est;
     } else {
       int cnt = 0;
 #pragma unroll
@@ -419,6 +424,71 @@ __global__ void __launch_bounds__(kQueryThreads) knn_query_kernel(const __grid_c
 #pragma unroll
       for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
       if (lane == 0) out_cnt[q] = cnt;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Mode B frame: one warp per pixel.  Eye ray and mirror/glass chain as in render_kernel (PMK:926-983), then the
+// reference's voxel gathers are replaced by k-nearest-photon estimates: ten ray-march samples in the volume map
+// (PMK:937-965) and one estimate at the wall hit in the surface map (PMK:987-999), composited as the reference does
+// (media: rgb = sum of the march terms + 0.15 * wall term).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned char quantise_u8(float v) {   // PMK:1451-1453 with the device's saturating cast
+  double d = (double)v * 255.0;
+  d = d > 255.0 ? 255.0 : d;
+  return d > 0.0 ? (unsigned char)__double2uint_rz(d) : (unsigned char)0;
+}
+
+template <int KL>
+__global__ void __launch_bounds__(kQueryThreads) knn_render_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ TreeView tvs,
+                                                                   const __grid_constant__ TreeView tvv, const float4 *__restrict__ pow_s,
+                                                                   const float4 *__restrict__ pow_v, int k, float max_r2, float w_surf,
+                                                                   float w_vol, int width, int height, int y0, int y1, int media,
+                                                                   uchar4 *__restrict__ rgba, float4 *__restrict__ rgbf) {
+  extern __shared__ __align__(128) unsigned char dyn[];
+  float *sbox_s = (float *)dyn, *sbox_v = sbox_s + kMaxStagedFloats;
+  u64 *pend_all = (u64 *)(sbox_v + kMaxStagedFloats);
+  unsigned long long *bars = (unsigned long long *)(pend_all + (kQueryThreads / 32) * 64);
+  stage_top_levels(tvs, sbox_s, bars + 0);
+  if (media) stage_top_levels(tvv, sbox_v, bars + 1);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  u64 *pend = pend_all + w * 64;
+  const long long warps = (long long)gridDim.x * (kQueryThreads / 32);
+  const long long p0 = (long long)y0 * width, p1 = (long long)y1 * width;
+  for (long long pix = p0 + (long long)blockIdx.x * (kQueryThreads / 32) + w; pix < p1; pix += warps) {
+    int px = (int)(pix % width), py = (int)(pix / width);
+    float x = (float)px + sc.cam_ox, y = (float)py + sc.cam_oy;
+    v3 rgb = V(0.0f, 0.0f, 0.0f);
+    const v3 origin = V(0.0f, 0.0f, 0.0f);
+    v3 ray = V((float)((double)__fdiv_rn(x, sc.sz_img) - 0.5), (float)(-((double)__fdiv_rn(y, sc.sz_img) - 0.5)), 1.0f);
+    TopK<KL> top;
+    if (media) {
+      v3 prev = origin;
+#pragma unroll 1
+      for (int i = 0; i < 10; i++) {
+        prev = add(mul(ray, 0.6f), prev);
+        knn_search<KL>(tvv, sbox_v, pend, prev.x, prev.y, prev.z, k, max_r2, lane, top);
+        float4 e = knn_radiance<KL>(top, k, pow_v, 1, lane);
+        rgb = add(rgb, mul(V(e.x, e.y, e.z), w_vol));
+      }
+    }
+    Hit h; h.hit = 0; h.type = 0; h.idx = 0; h.dist = -1.0f;
+    raytrace(sc, ray, origin, h);
+    if (h.hit) {
+      v3 P = mul(ray, h.dist);
+      if (h.type == 0 && h.idx == 1) follow_specular(sc, ray, origin, h, P, 1);
+      else if (h.type == 0 && h.idx == 0) follow_specular(sc, ray, origin, h, P, 0);
+      if (h.hit && h.type == 1) {   // warp-uniform: every lane traced the same ray
+        knn_search<KL>(tvs, sbox_s, pend, P.x, P.y, P.z, k, max_r2, lane, top);
+        float4 e = knn_radiance<KL>(top, k, pow_s, 0, lane);
+        v3 c = mul(V(e.x, e.y, e.z), w_surf);
+        rgb = media ? add(rgb, mul(c, 0.15f)) : add(rgb, c);
+      }
+    }
+    if (lane == 0) {
+      if (rgbf) rgbf[pix] = make_float4(rgb.x, rgb.y, rgb.z, 1.0f);
+      if (rgba) rgba[pix] = make_uchar4(quantise_u8(rgb.x), quantise_u8(rgb.y), quantise_u8(rgb.z), 0);
     }
   }
 }
@@ -513,6 +583,25 @@ cudaError_t knn_query(const KnnMap &m, const float4 *queries, long long nq, int 
   if (k <= 32) knn_query_kernel<1><<<grid, kQueryThreads, 0, st>>>(tv, queries, nq, k, max_r2, idx, d2, cnt, pw, volume, rgb);
   else if (k <= 64) knn_query_kernel<2><<<grid, kQueryThreads, 0, st>>>(tv, queries, nq, k, max_r2, idx, d2, cnt, pw, volume, rgb);
   else knn_query_kernel<4><<<grid, kQueryThreads, 0, st>>>(tv, queries, nq, k, max_r2, idx, d2, cnt, pw, volume, rgb);
+  return cudaGetLastError();
+}
+
+cudaError_t knn_render(const DeviceScene &sc, const KnnMap &ms, const KnnMap &mv, int k, float max_r2, float w_surf, float w_vol, int width,
+                       int height, int y0, int y1, bool media, uchar4 *rgba, float4 *rgbf, int num_sms, cudaStream_t st) {
+  long long n = (long long)(y1 - y0) * width;
+  if (n <= 0) return cudaSuccess;
+  TreeView tvs = make_view(ms), tvv = make_view(mv);
+  long long want = (n + kQueryThreads / 32 - 1) / (kQueryThreads / 32), cap = (long long)num_sms * 16;
+  unsigned grid = (unsigned)(want < cap ? want : cap);
+  size_t smem = sizeof(float) * 2 * kMaxStagedFloats + sizeof(u64) * (kQueryThreads / 32) * 64 + 2 * sizeof(unsigned long long);
+#define LAUNCH_RENDER(KL)                                                                                                  \
+  do {                                                                                                                     \
+    KCK(cudaFuncSetAttribute(knn_render_kernel<KL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
+    knn_render_kernel<KL><<<grid, kQueryThreads, smem, st>>>(sc, tvs, tvv, ms.power, mv.power, k, max_r2, w_surf, w_vol, width, height, y0, \
+                                                              y1, media ? 1 : 0, rgba, rgbf);                               \
+  } while (0)
+  if (k <= 32) LAUNCH_RENDER(1); else if (k <= 64) LAUNCH_RENDER(2); else LAUNCH_RENDER(4);
+#undef LAUNCH_RENDER
   return cudaGetLastError();
 }
 

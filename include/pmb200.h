@@ -126,6 +126,11 @@ int pm_knn_query(pm_context *ctx, int which, const float *dev_queries4, int64_t 
                  int32_t *dev_idx, float *dev_d2, int32_t *dev_cnt);
 /* radiance estimate per query: dev_rgb4[q] = (sum of the found powers / (pi r_k^2) [surface] or (4/3 pi r_k^3) [volume], r_k^2) */
 int pm_knn_radiance(pm_context *ctx, int which, const float *dev_queries4, int64_t nq, int k, float max_r2, float *dev_rgb4);
+/* stages 3+4+5, Mode B: rows [y0,y1) of a frame whose wall term is a k-NN estimate in the surface map and whose ten
+ * ray-march terms are k-NN estimates in the volume map (media only), weighted by w_surface / w_volume and composited
+ * like the reference (media: march sum + 0.15 * wall term).  Both maps must have been built with powers. */
+int pm_render_knn(pm_context *ctx, float animTime, bool participatingMediaFlag, int width, int height, int y0, int y1, int k,
+                  float max_r2, float w_surface, float w_volume, pm_uchar4 *dev_rgba, float *dev_rgbf);
 /* build products for the parity tests: sorted Morton keys + permutation (host), box arrays of one level (host) */
 int pm_knn_sorted_host(pm_context *ctx, int which, uint32_t *host_keys, uint32_t *host_perm, int64_t n);
 int pm_knn_level_host(pm_context *ctx, int which, int level, int64_t *count, float *host_boxes6 /* [6][count] or NULL */);

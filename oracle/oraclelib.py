@@ -55,6 +55,7 @@ class Oracle:
         L.pmo_render.argtypes = [C.POINTER(Scene), C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.pmo_raytrace.restype = C.c_int
+        L.pmo_eye_geometry.argtypes = [C.POINTER(Scene), C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.pmo_morton30_many.argtypes = [C.c_void_p, C.c_long, C.c_void_p]
         L.pmo_stable_sort_perm.argtypes = [C.c_void_p, C.c_long, C.c_void_p]
         L.pmo_knn_bruteforce.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -113,6 +114,12 @@ class Oracle:
         u8 = np.zeros((h, w, 4), np.uint8) if want_u8 else None
         self.lib.pmo_render(C.byref(scene), t, _p(grid), w, h, y0, y1, int(interp), int(media), _p(rgb), _p(u8))
         return rgb, u8
+
+    def eye_geometry(self, scene, w, h, t=0.0):
+        """(hit[h,w,8] = (hit, type, id, px, py, pz, 0, 0), march[h,w,10,3]) -- eye-ray geometry for the Mode B oracle."""
+        hit = np.zeros((h, w, 8), np.float32); march = np.zeros((h, w, 10, 3), np.float32)
+        self.lib.pmo_eye_geometry(C.byref(scene), t, w, h, 0, h, _p(hit), _p(march))
+        return hit, march
 
     # -- probes --------------------------------------------------------------------------------------
     def voxel(self, p):

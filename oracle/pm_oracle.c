@@ -456,6 +456,35 @@ void pmo_render(const pm_scene *scene, float t, const float *grid, int width, in
     }
 }
 
+/* Eye-ray geometry for the Mode B renderer's oracle: per pixel the final hit after the mirror/glass chain (hit flag,
+ * type, id, point) and the ten ray-march sample points of PMK:937-965.  out_hit: 8 floats per pixel
+ * (hit, type, id, px, py, pz, 0, 0); out_march: 30 floats per pixel. */
+void pmo_eye_geometry(const pm_scene *scene, float t, int width, int height, int y0, int y1, float *out_hit, float *out_march) {
+  pm_scene sc = *scene;
+  pmo_position_objects(&sc, t);
+  for (int y = y0; y < y1; y++)
+    for (int x = 0; x < width; x++) {
+      float fx = (float)x + sc.cam_ox, fy = (float)y + sc.cam_oy;
+      v3 origin = V(0.0f, 0.0f, 0.0f), P = V(0.0f, 0.0f, 0.0f);
+      v3 ray = V((float)((double)(fx / (float)sc.sz_img) - 0.5), (float)(-((double)(fy / (float)sc.sz_img) - 0.5)), 1.0f);
+      size_t i = (size_t)y * width + x;
+      v3 prev = origin;
+      for (int k = 0; k < N_MARCH; k++) {
+        prev = add(mul(ray, 0.6f), prev);
+        if (out_march) { out_march[30 * i + 3 * k] = prev.x; out_march[30 * i + 3 * k + 1] = prev.y; out_march[30 * i + 3 * k + 2] = prev.z; }
+      }
+      hit_t h; h.hit = 0; h.type = 0; h.idx = 0; h.dist = -1.0f;
+      raytrace(&sc, ray, origin, &h);
+      if (h.hit) {
+        P = mul(ray, h.dist);
+        if (h.type == 0 && h.idx == 1) follow_specular(&sc, &ray, origin, &h, &P, 1);
+        else if (h.type == 0 && h.idx == 0) follow_specular(&sc, &ray, origin, &h, &P, 0);
+      }
+      float *o = out_hit + 8 * i;
+      o[0] = (float)h.hit; o[1] = (float)h.type; o[2] = (float)h.idx; o[3] = P.x; o[4] = P.y; o[5] = P.z; o[6] = 0.0f; o[7] = 0.0f;
+    }
+}
+
 /* ---- single-routine probes for unit-level parity ------------------------------------------------------- */
 int pmo_raytrace(const pm_scene *sc, const float ray[3], const float org[3], float *dist, int *type, int *idx) {
   hit_t h; h.hit = 0; h.type = -1; h.idx = -1; h.dist = -1.0f;

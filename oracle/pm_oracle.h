@@ -30,6 +30,8 @@ long pmo_emit(const pm_scene *scene, float t, const float *table, int n0, int n1
 void pmo_render(const pm_scene *scene, float t, const float *grid, int width, int height, int y0, int y1,
                 int interp, int media, float *rgb, uint8_t *rgba);
 
+void pmo_eye_geometry(const pm_scene *scene, float t, int width, int height, int y0, int y1, float *out_hit, float *out_march);
+
 int  pmo_raytrace(const pm_scene *sc, const float ray[3], const float org[3], float *dist, int *type, int *idx);
 void pmo_integrate_volume(const float *grid, const float p[3], float rgb[3]);
 void pmo_gather(const float *grid, const float p[3], int type, int id, int interp, float rgb[3]);

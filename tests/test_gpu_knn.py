@@ -164,3 +164,65 @@ def test_knn_on_traced_photons(pm, oracle, media):
         scale = np.abs(est).max()
         assert np.abs(got[:, :3] - est).max() <= 2e-5 * scale
     m.close()
+
+
+@pytest.mark.parametrize("media", [False, True])
+def test_render_knn_vs_oracle(pm, oracle, media):
+    """Mode B frame (pm_render_knn) against the oracle composition: eye-ray geometry from pm_oracle.c, brute-force k-NN
+    estimates from knn_oracle.c, composited as documented in include/pmb200.h.  Tolerance 5e-5 of the frame maximum
+    (FP32 lane-order power sums vs double)."""
+    import torch
+    from pmb200 import dist as pd
+    n, w, h, k = 20000, 64, 48, 50
+    w_s, w_v = 2.0e-4, 3.0e-2
+    osc = oracle.default_scene(sz_img=48)
+    osc.cam_ox = -8.0
+    m = pm.PhotonMapper(n_photons=n)
+    m.set_scene(copy_scene(pm.Scene, osc))
+    m.init_random_numbers()
+    m.set_record_capacity(16 * n)
+    m.clear_map()
+    m.trace(0.0, media=media, records=True, no_map=True)
+    m.knn_build(0)
+    if media:
+        m.knn_build(1)
+    rgbf = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
+    rgba = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+    m.render_knn(w, h, 0.0, media, k, float("inf"), w_s, w_v, rgba=rgba, rgbf=rgbf, y0=0, y1=20)
+    m.render_knn(w, h, 0.0, media, k, float("inf"), w_s, w_v, rgba=rgba, rgbf=rgbf, y0=20, y1=h)
+    m.sync()
+
+    def records(which):
+        pos_p, pow_p, _, cnt = m.record_buffers(which)
+        pos = pd.device_tensor(pos_p, cnt * 4, "<f4").cpu().numpy().reshape(cnt, 4).copy()
+        pw = pd.device_tensor(pow_p, cnt * 4, "<f4").cpu().numpy().reshape(cnt, 4).copy()
+        return pos, pw
+
+    hit, march = oracle.eye_geometry(osc, w, h, 0.0)
+    spos, spow = records(0)
+    meta = spos[:, 3].copy().view(np.uint32)
+    spos[((meta >> 5) & 3).astype(np.int32) - 1 != 1, :3] = np.nan
+    q = np.zeros((h * w, 4), np.float32); q[:, :3] = hit.reshape(-1, 8)[:, 3:6]
+    idx, d2, cnt = oracle.knn_bruteforce(spos, q, k)
+    surf = oracle.knn_estimate(spow, idx, d2, cnt, volume=False) * np.float32(w_s)
+    on_wall = (hit.reshape(-1, 8)[:, 0] != 0) & (hit.reshape(-1, 8)[:, 1] == 1)
+    surf[~on_wall] = 0
+    want = np.zeros((h * w, 3), np.float32)
+    if media:
+        vpos, vpow = records(1)
+        for s in range(10):
+            q[:, :3] = march.reshape(-1, 10, 3)[:, s]
+            idx, d2, cnt = oracle.knn_bruteforce(vpos, q, k)
+            want += oracle.knn_estimate(vpow, idx, d2, cnt, volume=True) * np.float32(w_v)
+        want += surf * np.float32(0.15)
+    else:
+        want += surf
+    got = rgbf.cpu().numpy().reshape(-1, 4)
+    scale = np.abs(want).max()
+    assert scale > 0
+    assert np.abs(got[:, :3] - want).max() <= 5e-5 * scale
+    assert np.all(got[:, 3] == 1.0)
+    u8 = rgba.cpu().numpy().reshape(-1, 4)
+    expect_u8 = np.clip(np.nan_to_num(got[:, :3].astype(np.float64) * 255.0, nan=0.0), 0, 255).astype(np.uint8)
+    assert np.array_equal(u8[:, :3], expect_u8) and np.all(u8[:, 3] == 0)
+    m.close()
