@@ -46,6 +46,7 @@ struct pm_context {
   int64_t vrec_cap = 0, vrec_count = 0;
 
   KnnMap knn[2];                   // Mode B maps: surface, volume
+  int knn_curve = PM_CURVE_HILBERT;
 
   uchar4 *d_fb_u8 = nullptr;
   float4 *d_fb_f32 = nullptr;
@@ -542,7 +543,7 @@ int pm_knn_build_points(pm_context *c, int which, const float *pos4, const float
   cudaError_t e;
   {
     SpanGuard g(c, K_KNN_BUILD);
-    e = knn_build(c->knn[which], (const float4 *)pos4, (const float4 *)pow4, n, 0, c->stream, &launches);
+    e = knn_build(c->knn[which], (const float4 *)pos4, (const float4 *)pow4, n, 0, c->knn_curve, c->stream, &launches);
   }
   c->launches += launches;
   CK(c, e);
@@ -559,10 +560,15 @@ int pm_knn_build(pm_context *c, int which) {
   cudaError_t e;
   {
     SpanGuard g(c, K_KNN_BUILD);
-    e = knn_build(c->knn[which], (const float4 *)pos, (const float4 *)pw, n, which == PM_MAP_SURFACE ? 1 : 0, c->stream, &launches);
+    e = knn_build(c->knn[which], (const float4 *)pos, (const float4 *)pw, n, which == PM_MAP_SURFACE ? 1 : 0, c->knn_curve, c->stream, &launches);
   }
   c->launches += launches;
   CK(c, e);
+  return PM_OK;
+}
+int pm_knn_set_curve(pm_context *c, int curve) {
+  ARG(c, c && (curve == PM_CURVE_MORTON || curve == PM_CURVE_HILBERT), "bad curve id");
+  c->knn_curve = curve;
   return PM_OK;
 }
 int pm_knn_size(pm_context *c, int which, int64_t *n, int32_t *levels) {

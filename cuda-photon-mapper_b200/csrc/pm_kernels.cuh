@@ -44,6 +44,7 @@ struct KnnMap {
   uint32_t *keys[2] = {nullptr, nullptr}, *vals[2] = {nullptr, nullptr};
   size_t cap_keys[2] = {0, 0}, cap_vals[2] = {0, 0};
   uint32_t *ghist = nullptr; size_t cap_ghist = 0;
+  uint32_t *scan_sums = nullptr; size_t cap_scan_sums = 0;
   float4 *spos = nullptr; size_t cap_spos = 0;
   unsigned long long *d_count = nullptr;
   int sorted = 0;                  // which of keys[]/vals[] holds the sorted pairs
@@ -51,7 +52,7 @@ struct KnnMap {
   const float4 *power = nullptr;   // rgb power per ORIGINAL index (not owned)
   const float4 *src_pos = nullptr; // positions per ORIGINAL index (not owned)
 };
-cudaError_t knn_build(KnnMap &m, const float4 *pos, const float4 *power, long long n, int filter, cudaStream_t st, int *launches);
+cudaError_t knn_build(KnnMap &m, const float4 *pos, const float4 *power, long long n, int filter, int curve, cudaStream_t st, int *launches);
 cudaError_t knn_query(const KnnMap &m, const float4 *queries, long long nq, int k, float max_r2, int32_t *idx, float *d2, int32_t *cnt,
                       int volume, float4 *rgb, int num_sms, cudaStream_t st);
 cudaError_t knn_render(const DeviceScene &sc, const KnnMap &ms, const KnnMap &mv, int k, float max_r2, float w_surf, float w_vol, int width,

@@ -50,8 +50,26 @@ __device__ __forceinline__ uint32_t morton30(float x, float y, float z) {
          (spread10(quant10(z, 0.0f, 1.0f / 6.0f)) << 2);
 }
 
+// the same cell along the 3-D Hilbert curve (Skilling's transpose algorithm); identical integer code in oracle/knn_oracle.c
+__device__ __forceinline__ uint32_t hilbert30(float x, float y, float z) {
+  uint32_t X0 = quant10(x, -1.5f, 1.0f / 3.0f), X1 = quant10(y, -1.5f, 1.0f / 3.0f), X2 = quant10(z, 0.0f, 1.0f / 6.0f);
+#pragma unroll
+  for (uint32_t Q = 1u << 9; Q > 1; Q >>= 1) {
+    const uint32_t P = Q - 1;
+    if (X0 & Q) X0 ^= P;                                   // i = 0: the swap with itself is the identity
+    if (X1 & Q) X0 ^= P; else { uint32_t t = (X0 ^ X1) & P; X0 ^= t; X1 ^= t; }
+    if (X2 & Q) X0 ^= P; else { uint32_t t = (X0 ^ X2) & P; X0 ^= t; X2 ^= t; }
+  }
+  X1 ^= X0; X2 ^= X1;
+  uint32_t t = 0;
+#pragma unroll
+  for (uint32_t Q = 1u << 9; Q > 1; Q >>= 1) if (X2 & Q) t ^= Q - 1;
+  X0 ^= t; X1 ^= t; X2 ^= t;
+  return (spread10(X0) << 2) | (spread10(X1) << 1) | spread10(X2);
+}
+
 // filter: 0 = every row is a point; 1 = keep only wall hits (meta type == 1) of a record buffer
-__global__ void __launch_bounds__(256) morton_kernel(const float4 *__restrict__ pos, long long n, long long n_pad, int filter,
+__global__ void __launch_bounds__(256) morton_kernel(const float4 *__restrict__ pos, long long n, long long n_pad, int filter, int curve,
                                                      uint32_t *__restrict__ keys, uint32_t *__restrict__ vals,
                                                      unsigned long long *__restrict__ n_valid) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -61,11 +79,11 @@ __global__ void __launch_bounds__(256) morton_kernel(const float4 *__restrict__ 
     float4 p = pos[i];
     bool keep = true;
     if (filter) { int seq, kind, type, id; unpack_meta(__float_as_uint(p.w), seq, kind, type, id); keep = (type == 1); }
-    if (keep) key = morton30(p.x, p.y, p.z);
+    if (keep) key = curve ? hilbert30(p.x, p.y, p.z) : morton30(p.x, p.y, p.z);
   }
   keys[i] = key; vals[i] = (uint32_t)i;
-  unsigned m = __ballot_sync(__activemask(), key != 0xFFFFFFFFu);
-  if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_valid, (unsigned long long)__popc(m));
+  int kept = __syncthreads_count(key != 0xFFFFFFFFu);   // n_pad is a multiple of the block size: no thread has returned
+  if (threadIdx.x == 0 && kept) atomicAdd(n_valid, (unsigned long long)kept);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -85,22 +103,66 @@ __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const uint32_t
   ghist[(size_t)threadIdx.x * nb + blockIdx.x] = sh[threadIdx.x];   // digit-major: a flat exclusive scan gives the offsets
 }
 
-// in-place exclusive scan of m counters by one CTA (m = 256 * tiles: 1 M entries at 16 M keys)
-__global__ void __launch_bounds__(1024) scan_kernel(uint32_t *__restrict__ a, size_t m) {
-  __shared__ uint32_t part[1024];
-  const size_t per = (m + 1023) / 1024, lo = per * threadIdx.x, hi = lo + per < m ? lo + per : m;
-  uint32_t s = 0;
-  for (size_t i = lo; i < hi; i++) s += a[i];
-  part[threadIdx.x] = s;
+// in-place exclusive scan of m counters (m = 256 * tiles: 1 M entries at 16 M keys) in three coalesced steps:
+// per-chunk sums -> scan of the chunk sums by one CTA -> per-chunk scan with the chunk's offset
+constexpr int kScanChunk = 2048, kScanThreads = 256;   // 8 counters per thread
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *total, uint32_t *sh /* >= 32 */) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+  if (lane == 31) sh[w] = inc;
   __syncthreads();
-  for (int off = 1; off < 1024; off <<= 1) {   // Hillis-Steele over the 1024 partial sums
-    uint32_t v = threadIdx.x >= off ? part[threadIdx.x - off] : 0u;
+  if (w == 0) {
+    uint32_t s = lane < nw ? sh[lane] : 0u, si = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, si, o); if (lane >= o) si += t; }
+    sh[lane] = si - s;                 // exclusive offsets of the warps
+    if (lane == 31 && total) *total = si;
+  }
+  __syncthreads();
+  uint32_t r = inc - v + sh[w];
+  __syncthreads();
+  return r;
+}
+__global__ void __launch_bounds__(kScanThreads) scan_sums_kernel(const uint32_t *__restrict__ a, size_t m, uint32_t *__restrict__ sums) {
+  __shared__ uint32_t red[kScanThreads / 32];
+  size_t base = (size_t)blockIdx.x * kScanChunk;
+  uint32_t v = 0;
+#pragma unroll
+  for (int i = 0; i < kScanChunk / kScanThreads; i++) { size_t j = base + i * kScanThreads + threadIdx.x; v += j < m ? a[j] : 0u; }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) { uint32_t t = 0; for (int i = 0; i < kScanThreads / 32; i++) t += red[i]; sums[blockIdx.x] = t; }
+}
+__global__ void __launch_bounds__(1024) scan_top_kernel(uint32_t *__restrict__ sums, int n) {   // n <= a few thousand
+  __shared__ uint32_t sh[32];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    int j = base + threadIdx.x;
+    uint32_t v = j < n ? sums[j] : 0u, total = 0;
+    uint32_t ex = block_exclusive_scan(v, &total, sh);
+    uint32_t c = carry;
+    if (j < n) sums[j] = ex + c;
     __syncthreads();
-    part[threadIdx.x] += v;
+    if (threadIdx.x == 1023) carry = c + ex + v;
     __syncthreads();
   }
-  uint32_t run = threadIdx.x ? part[threadIdx.x - 1] : 0u;
-  for (size_t i = lo; i < hi; i++) { uint32_t v = a[i]; a[i] = run; run += v; }
+}
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(uint32_t *__restrict__ a, size_t m, const uint32_t *__restrict__ sums) {
+  __shared__ uint32_t sh[32];
+  size_t base = (size_t)blockIdx.x * kScanChunk + (size_t)threadIdx.x * (kScanChunk / kScanThreads);
+  uint32_t v[kScanChunk / kScanThreads], s = 0;
+#pragma unroll
+  for (int i = 0; i < kScanChunk / kScanThreads; i++) { v[i] = base + i < m ? a[base + i] : 0u; s += v[i]; }
+  uint32_t run = block_exclusive_scan(s, nullptr, sh) + sums[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < kScanChunk / kScanThreads; i++) { if (base + i < m) a[base + i] = run; run += v[i]; }
 }
 
 __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
@@ -195,6 +257,12 @@ __global__ void __launch_bounds__(256) node_box_kernel(const float *__restrict__
 // ---------------------------------------------------------------------------------------------------------
 typedef unsigned long long u64;
 constexpr u64 kMaxKey = ~0ull;
+#ifdef PM_KNN_STATS
+__device__ unsigned long long g_knn_stats[8];   // 0 leaves, 1 nodes, 2 candidates passed, 3 merges, 4 queries
+#define KSTAT(i, v) do { if (lane == 0) atomicAdd(&g_knn_stats[i], (unsigned long long)(v)); } while (0)
+#else
+#define KSTAT(i, v) do { } while (0)
+#endif
 
 __device__ __forceinline__ void cmpx(u64 &a, u64 other, bool keep_min) { a = (keep_min == (other < a)) ? other : a; }
 
@@ -270,6 +338,7 @@ __device__ __forceinline__ void knn_search(const TreeView &tv, const float *__re
   u64 thr_key = kMaxKey;
   int npend = 0;
   if (tv.n <= 0) return;
+  KSTAT(4, 1);
 
   auto leaf = [&](long long e) {
     long long i = e * 32 + lane;
@@ -282,11 +351,13 @@ __device__ __forceinline__ void knn_search(const TreeView &tv, const float *__re
     }
     bool pass = key < thr_key;
     unsigned m = __ballot_sync(0xffffffffu, pass);
+    KSTAT(0, 1); KSTAT(2, __popc(m));
     if (!m) return;
     if (pass) pend[npend + __popc(m & ((1u << lane) - 1u))] = key;
     npend += __popc(m);
     __syncwarp();
     if (npend >= 32) {
+      KSTAT(3, 1);
       top.merge(pend[lane], lane);
       u64 rest = lane + 32 < npend ? pend[lane + 32] : kMaxKey;
       __syncwarp();
@@ -323,6 +394,7 @@ __device__ __forceinline__ void knn_search(const TreeView &tv, const float *__re
       }
       d = box_dist2(lx, ly, lz, hx, hy, hz, qx, qy, qz);
     }
+    KSTAT(1, 1);
     uint32_t bits = __float_as_uint(d);
     bool ok = d <= thr_d2 && bits < 0x7f800000u;
     uint32_t mn = __reduce_min_sync(0xffffffffu, ok ? bits : 0xffffffffu);
@@ -506,7 +578,7 @@ static cudaError_t ensure(void **p, size_t *cap, size_t bytes) {
 
 #define KCK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
 
-cudaError_t knn_build(KnnMap &m, const float4 *pos, const float4 *power, long long n, int filter, cudaStream_t st, int *launches) {
+cudaError_t knn_build(KnnMap &m, const float4 *pos, const float4 *power, long long n, int filter, int curve, cudaStream_t st, int *launches) {
   m.n = 0; m.levels = 0; m.power = power; m.src_pos = pos;
   if (n <= 0) return cudaSuccess;
   const long long tiles = (n + kSortTile - 1) / kSortTile, n_pad = tiles * kSortTile;
@@ -515,19 +587,26 @@ cudaError_t knn_build(KnnMap &m, const float4 *pos, const float4 *power, long lo
   KCK(ensure((void **)&m.vals[0], &m.cap_vals[0], sizeof(uint32_t) * n_pad));
   KCK(ensure((void **)&m.vals[1], &m.cap_vals[1], sizeof(uint32_t) * n_pad));
   KCK(ensure((void **)&m.ghist, &m.cap_ghist, sizeof(uint32_t) * 256 * tiles));
+  KCK(ensure((void **)&m.scan_sums, &m.cap_scan_sums, sizeof(uint32_t) * ((256 * tiles + kScanChunk - 1) / kScanChunk + 1)));
   KCK(ensure((void **)&m.spos, &m.cap_spos, sizeof(float4) * n));
   if (!m.d_count) KCK(cudaMalloc(&m.d_count, sizeof(unsigned long long)));
   KCK(cudaMemsetAsync(m.d_count, 0, sizeof(unsigned long long), st));
-  morton_kernel<<<(unsigned)((n_pad + 255) / 256), 256, 0, st>>>(pos, n, n_pad, filter, m.keys[0], m.vals[0], m.d_count);
+  morton_kernel<<<(unsigned)((n_pad + 255) / 256), 256, 0, st>>>(pos, n, n_pad, filter, curve, m.keys[0], m.vals[0], m.d_count);
   (*launches)++;
   int cur = 0;
   for (int pass = 0; pass < 4; pass++) {
     radix_hist_kernel<<<(unsigned)tiles, kSortThreads, 0, st>>>(m.keys[cur], pass * 8, (uint32_t)tiles, m.ghist);
-    scan_kernel<<<1, 1024, 0, st>>>(m.ghist, (size_t)256 * tiles);
+    {
+      size_t cnt = (size_t)256 * tiles;
+      int chunks = (int)((cnt + kScanChunk - 1) / kScanChunk);
+      scan_sums_kernel<<<chunks, kScanThreads, 0, st>>>(m.ghist, cnt, m.scan_sums);
+      scan_top_kernel<<<1, 1024, 0, st>>>(m.scan_sums, chunks);
+      scan_apply_kernel<<<chunks, kScanThreads, 0, st>>>(m.ghist, cnt, m.scan_sums);
+    }
     radix_scatter_kernel<<<(unsigned)tiles, kSortThreads, 0, st>>>(m.keys[cur], m.vals[cur], m.keys[cur ^ 1], m.vals[cur ^ 1], pass * 8,
                                                                     (uint32_t)tiles, m.ghist);
     cur ^= 1;
-    *launches += 3;
+    *launches += 5;
   }
   m.sorted = cur;
   KCK(cudaGetLastError());
@@ -605,8 +684,16 @@ cudaError_t knn_render(const DeviceScene &sc, const KnnMap &ms, const KnnMap &mv
   return cudaGetLastError();
 }
 
+#ifdef PM_KNN_STATS
+extern "C" void pm_debug_knn_stats(unsigned long long *out, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_knn_stats, sizeof(unsigned long long) * 8);
+  if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_knn_stats, z, sizeof(z)); }
+}
+#endif
+
 void knn_free(KnnMap &m) {
-  cudaFree(m.keys[0]); cudaFree(m.keys[1]); cudaFree(m.vals[0]); cudaFree(m.vals[1]); cudaFree(m.ghist); cudaFree(m.spos);
+  cudaFree(m.keys[0]); cudaFree(m.keys[1]); cudaFree(m.vals[0]); cudaFree(m.vals[1]); cudaFree(m.ghist); cudaFree(m.scan_sums); cudaFree(m.spos);
   cudaFree(m.boxes); cudaFree(m.d_count);
   m = KnnMap();
 }

@@ -117,6 +117,9 @@ int pm_record_buffers(pm_context *ctx, int which, float **dev_pos_meta /* float4
  * pm_knn_build uses the record buffers of the last PM_TRACE_RECORDS trace (surface map: wall hits only);
  * pm_knn_build_points builds over any DEVICE point set (float4 xyz+ignored, float4 power rgb+ignored; the arrays must
  * stay alive while the map is used) -- e.g. all-gathered records of several GPUs. */
+#define PM_CURVE_MORTON  0   /* 30-bit Morton (Z-order) key of the 10-bit cell coordinates */
+#define PM_CURVE_HILBERT 1   /* the same cell along the 3-D Hilbert curve (default: tighter leaf / node boxes) */
+int pm_knn_set_curve(pm_context *ctx, int curve);
 int pm_knn_build(pm_context *ctx, int which);
 int pm_knn_build_points(pm_context *ctx, int which, const float *dev_pos4, const float *dev_power4, int64_t n);
 int pm_knn_size(pm_context *ctx, int which, int64_t *n_points, int32_t *n_levels);

@@ -38,8 +38,30 @@ uint32_t pmo_morton30(const float p[3]) {
   uint32_t x = quant10(p[0], -1.5f, 1.0f / 3.0f), y = quant10(p[1], -1.5f, 1.0f / 3.0f), z = quant10(p[2], 0.0f, 1.0f / 6.0f);
   return spread10(x) | (spread10(y) << 1) | (spread10(z) << 2);
 }
+/* The same 10-bit cell coordinates along the 3-D Hilbert curve (Skilling's transpose algorithm, AIP Conf. Proc. 707,
+ * 2004): the sort key the product uses by default.  Runs of consecutive points of a Z-curve straddle octant boundaries,
+ * so the bounding boxes of fixed-size runs (the tree's leaves and nodes) are loose; Hilbert runs are always connected. */
+uint32_t pmo_hilbert30(const float p[3]) {
+  uint32_t X[3] = {quant10(p[0], -1.5f, 1.0f / 3.0f), quant10(p[1], -1.5f, 1.0f / 3.0f), quant10(p[2], 0.0f, 1.0f / 6.0f)};
+  const uint32_t M = 1u << 9;
+  for (uint32_t Q = M; Q > 1; Q >>= 1) {
+    uint32_t P = Q - 1;
+    for (int i = 0; i < 3; i++) {
+      if (X[i] & Q) X[0] ^= P;
+      else { uint32_t t = (X[0] ^ X[i]) & P; X[0] ^= t; X[i] ^= t; }
+    }
+  }
+  X[1] ^= X[0]; X[2] ^= X[1];
+  uint32_t t = 0;
+  for (uint32_t Q = M; Q > 1; Q >>= 1) if (X[2] & Q) t ^= Q - 1;
+  X[0] ^= t; X[1] ^= t; X[2] ^= t;
+  return (spread10(X[0]) << 2) | (spread10(X[1]) << 1) | spread10(X[2]);   /* X[0] holds the most significant bit of each triple */
+}
 void pmo_morton30_many(const float *pos4, long n, uint32_t *keys) {
   for (long i = 0; i < n; i++) keys[i] = pmo_morton30(pos4 + 4 * i);
+}
+void pmo_hilbert30_many(const float *pos4, long n, uint32_t *keys) {
+  for (long i = 0; i < n; i++) keys[i] = pmo_hilbert30(pos4 + 4 * i);
 }
 
 typedef struct { uint32_t key; uint32_t idx; } kv_t;

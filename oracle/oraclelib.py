@@ -57,6 +57,7 @@ class Oracle:
         L.pmo_raytrace.restype = C.c_int
         L.pmo_eye_geometry.argtypes = [C.POINTER(Scene), C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.pmo_morton30_many.argtypes = [C.c_void_p, C.c_long, C.c_void_p]
+        L.pmo_hilbert30_many.argtypes = [C.c_void_p, C.c_long, C.c_void_p]
         L.pmo_stable_sort_perm.argtypes = [C.c_void_p, C.c_long, C.c_void_p]
         L.pmo_knn_bruteforce.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
         L.pmo_knn_estimate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_void_p]
@@ -150,6 +151,12 @@ class Oracle:
         pos4 = np.ascontiguousarray(pos4, np.float32)
         keys = np.empty(pos4.shape[0], np.uint32)
         self.lib.pmo_morton30_many(_p(pos4), pos4.shape[0], _p(keys))
+        return keys
+
+    def hilbert30(self, pos4):
+        pos4 = np.ascontiguousarray(pos4, np.float32)
+        keys = np.empty(pos4.shape[0], np.uint32)
+        self.lib.pmo_hilbert30_many(_p(pos4), pos4.shape[0], _p(keys))
         return keys
 
     def stable_sort_perm(self, keys):

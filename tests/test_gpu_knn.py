@@ -29,9 +29,10 @@ def _points(n, kind, seed):
     return out
 
 
-def _build(pm, which, pts, power=None):
+def _build(pm, which, pts, power=None, curve=1):
     import torch
     m = pm.PhotonMapper(n_photons=16)
+    m.knn_set_curve(curve)
     tp = torch.from_numpy(pts).cuda()
     tw = torch.from_numpy(power).cuda() if power is not None else None
     m.knn_build_points(which, tp, tw, pts.shape[0])
@@ -39,12 +40,14 @@ def _build(pm, which, pts, power=None):
     return m, tp, tw
 
 
+@pytest.mark.parametrize("curve", [0, 1])
 @pytest.mark.parametrize("n,kind", [(1, "uniform"), (33, "uniform"), (4097, "walls"), (200000, "uniform"), (50000, "outside")])
-def test_morton_keys_and_stable_sort(pm, oracle, n, kind):
+def test_sort_keys_and_stable_sort(pm, oracle, n, kind, curve):
+    """Morton (curve 0) and Hilbert (curve 1, default) keys bit-exact; the radix sort equals a stable sort."""
     pts = _points(n, kind, 1)
-    m, _, _ = _build(pm, 0, pts)
+    m, _, _ = _build(pm, 0, pts, curve=curve)
     keys, perm = m.knn_sorted(0, n)
-    okeys = oracle.morton30(pts)
+    okeys = oracle.hilbert30(pts) if curve else oracle.morton30(pts)
     operm = oracle.stable_sort_perm(okeys)
     assert np.array_equal(perm, operm)
     assert np.array_equal(keys, okeys[operm])
@@ -78,9 +81,9 @@ def test_tree_boxes_are_tight_and_nested(pm, oracle):
     m.close()
 
 
-def _check_knn(pm, oracle, pts, queries, k, max_r2=np.inf):
+def _check_knn(pm, oracle, pts, queries, k, max_r2=np.inf, curve=1):
     import torch
-    m, tp, _ = _build(pm, 0, pts)
+    m, tp, _ = _build(pm, 0, pts, curve=curve)
     nq = queries.shape[0]
     tq = torch.from_numpy(queries).cuda()
     idx = torch.empty((nq, k), dtype=torch.int32, device="cuda")
@@ -106,7 +109,7 @@ def test_knn_bit_exact(pm, oracle, n, kind, k):
     q[:50, :3] = pts[rng.integers(0, n, 50), :3]          # queries exactly on photons (d2 = 0 ties)
     q[50:60, :3] = rng.normal(0, 100, (10, 3))            # far outside
     q[60, :3] = np.nan                                    # NaN query finds nothing
-    _check_knn(pm, oracle, pts, q, k)
+    _check_knn(pm, oracle, pts, q, k, curve=(n + k) % 2)  # both sort curves get exercised
 
 
 @pytest.mark.parametrize("max_r2", [0.0, 1e-3, 0.05])
