@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip timing the reference CUDA kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-mode-b", action="store_true", help="skip the Mode B (k-NN photon map) sub-benchmarks")
     return ap.parse_args()
 
 
@@ -193,6 +194,58 @@ def time_reference_cuda(a, table_host, dev_rgba):
     return {"ms_per_frame": e.value + r.value, "emit_ms": e.value, "render_ms": r.value, "steps": 3, "warmup": 1,
             "what": "photonMappingKernel.cu recompiled for sm_100a (nrPhotons=%d, szImg=%d), its own launchers, CUDA events"
                     % (a.photons, a.height)}
+
+
+def mode_b_numbers(pmb200, torch, a, device):
+    """Mode B (k-NN photon map) sub-benchmarks on one GPU: BASELINE configs 3 and 4.  Reported beside the headline."""
+    out = {}
+    W, H = a.width, a.height
+
+    def ev(fn, reps, warm=1):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    for name, n, k, media in (("config3_surface_4M_k100", 4194304, 100, False), ("config4_volumetric_%dM_k50" % (a.photons >> 20), a.photons, 50, True)):
+        m = pmb200.PhotonMapper(device=device, n_photons=n)
+        m.set_stream(torch.cuda.current_stream().cuda_stream)
+        sc = pmb200.default_scene(sz_img=H); sc.cam_ox = -(W - H) / 2.0
+        m.set_scene(sc)
+        m.init_random_numbers()
+        m.set_record_capacity(int(2.6 * n) + 4096)
+
+        def trace():
+            m.clear_map(); m.trace(0.0, media=media, records=True, no_map=True)
+        r = {"photons": n, "k": k, "media": media, "trace_with_records_ms": ev(trace, 3)}
+        r["build_surface_ms"] = ev(lambda: m.knn_build(0), 3)
+        n_rec = m.record_buffers(0)[3]
+        r["surface_points"] = m.knn_size(0)[0]
+        build_ms, build_pts = r["build_surface_ms"], n_rec
+        if media:
+            r["build_volume_ms"] = ev(lambda: m.knn_build(1), 3)
+            r["volume_points"] = m.knn_size(1)[0]
+            build_ms += r["build_volume_ms"]; build_pts += r["volume_points"]
+        # algorithmic bytes of the build per sorted record (DESIGN.md): 16 read + 8 key/index written, 4 passes x (4 histogram
+        # read + 8 read + 8 written), 4 + 16 + 16 for the permuted rows, boxes negligible
+        r["build_GBps_algorithmic"] = build_pts * (24 + 4 * 20 + 36) / (build_ms * 1e-3) / 1e9
+        rgba = torch.zeros((H, W, 4), dtype=torch.uint8, device="cuda")
+        rgbf = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
+        ws, wv = 2.0e-4 * 10000.0 / n, 4.0e-3 * 10000.0 / n
+        r["render_knn_ms"] = ev(lambda: m.render_knn(W, H, 0.0, media, k, float("inf"), ws, wv, rgba=rgba, rgbf=rgbf), 2)
+        r["queries"] = W * H * (11 if media else 1)
+        r["gather_queries_per_s"] = r["queries"] / (r["render_knn_ms"] * 1e-3)
+        r["ms_per_frame"] = r["trace_with_records_ms"] + build_ms + r["render_knn_ms"]
+        out[name] = r
+        m.close()
+        del rgba, rgbf
+        torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -361,6 +414,11 @@ def main():
                                         "emit_ms_scaled": d["emit_ms_scaled"], "render_ms_scaled": d["render_ms_scaled"]}
             except Exception as ex:   # the baseline is reported, never required for the measurement itself
                 line["cpu_baseline"] = {"value": None, "unit": "ms", "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
+        if not a.no_mode_b and world == 1:
+            try:
+                line["mode_b"] = mode_b_numbers(pmb200, torch, a, local)
+            except Exception as ex:
+                line["mode_b"] = {"failed": repr(ex)}
         if not a.no_ref_cuda and world == 1:
             try:
                 line["reference_cuda_kernel"] = time_reference_cuda(a, m.get_random_table(), rgba)

@@ -74,6 +74,7 @@ def lib():
             "pm_knn_query": (i32, [vp, i32, vp, i64, i32, f32, vp, vp, vp]),
             "pm_knn_radiance": (i32, [vp, i32, vp, i64, i32, f32, vp]),
             "pm_render_knn": (i32, [vp, f32, b, i32, i32, i32, i32, i32, f32, f32, f32, vp, vp]),
+            "pm_render_knn_host": (i32, [vp, f32, b, i32, i32, i32, f32, f32, f32, vp, vp]),
             "pm_knn_sorted_host": (i32, [vp, i32, vp, vp, i64]),
             "pm_knn_level_host": (i32, [vp, i32, i32, C.POINTER(i64), vp]),
             "pm_render": (i32, [vp, f32, b, b, i32, i32, i32, i32, vp, vp]),

@@ -616,6 +616,23 @@ int pm_render_knn(pm_context *c, float t, bool media, int width, int height, int
   if (y1 > y0) c->launches++;
   return PM_OK;
 }
+static int ensure_framebuffers(pm_context *c, int64_t pixels);
+int pm_render_knn_host(pm_context *c, float t, bool media, int width, int height, int k, float max_r2, float w_surface, float w_volume,
+                       pm_uchar4 *host_rgba, float *host_rgbf) {
+  ARG(c, c != nullptr, "null context");
+  ARG(c, width > 0 && height > 0, "bad frame geometry");
+  CK(c, cudaSetDevice(c->device));
+  int64_t pixels = (int64_t)width * height;
+  int rc = ensure_framebuffers(c, pixels);
+  if (rc != PM_OK) return rc;
+  rc = pm_render_knn(c, t, media, width, height, 0, height, k, max_r2, w_surface, w_volume, host_rgba ? (pm_uchar4 *)c->d_fb_u8 : nullptr,
+                     host_rgbf ? (float *)c->d_fb_f32 : nullptr);
+  if (rc != PM_OK) return rc;
+  if (host_rgba) CK(c, cudaMemcpyAsync(host_rgba, c->d_fb_u8, sizeof(uchar4) * (size_t)pixels, cudaMemcpyDeviceToHost, c->stream));
+  if (host_rgbf) CK(c, cudaMemcpyAsync(host_rgbf, c->d_fb_f32, sizeof(float4) * (size_t)pixels, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  return PM_OK;
+}
 int pm_knn_sorted_host(pm_context *c, int which, uint32_t *keys, uint32_t *perm, int64_t n) {
   ARG(c, c && (which == PM_MAP_SURFACE || which == PM_MAP_VOLUME), "bad map id");
   const KnnMap &m = c->knn[which];

@@ -134,6 +134,9 @@ int pm_knn_radiance(pm_context *ctx, int which, const float *dev_queries4, int64
  * like the reference (media: march sum + 0.15 * wall term).  Both maps must have been built with powers. */
 int pm_render_knn(pm_context *ctx, float animTime, bool participatingMediaFlag, int width, int height, int y0, int y1, int k,
                   float max_r2, float w_surface, float w_volume, pm_uchar4 *dev_rgba, float *dev_rgbf);
+/* the same through HOST buffers (context-owned device frame buffers, synchronous copy-back) */
+int pm_render_knn_host(pm_context *ctx, float animTime, bool participatingMediaFlag, int width, int height, int k, float max_r2,
+                       float w_surface, float w_volume, pm_uchar4 *host_rgba, float *host_rgbf);
 /* build products for the parity tests: sorted Morton keys + permutation (host), box arrays of one level (host) */
 int pm_knn_sorted_host(pm_context *ctx, int which, uint32_t *host_keys, uint32_t *host_perm, int64_t n);
 int pm_knn_level_host(pm_context *ctx, int which, int level, int64_t *count, float *host_boxes6 /* [6][count] or NULL */);
