@@ -42,6 +42,10 @@ def parse():
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip timing the reference CUDA kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mode-b", action="store_true", help="skip the Mode B (k-NN photon map) sub-benchmarks")
+    ap.add_argument("--mode", default="a", choices=["a", "b"],
+                    help="a (default, headline): the reference's voxel-map estimator; b: k-NN photon map (records all-gathered, "
+                         "tree built on every rank, row bands) -- for Mode B scaling runs")
+    ap.add_argument("--knn", type=int, default=50, help="k of the Mode B estimate")
     return ap.parse_args()
 
 
@@ -290,7 +294,31 @@ def main():
 
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(a.steps)]
 
-    def step(e=None):
+    def step_b(e=None):
+        if e: e[0].record()
+        m.clear_map()
+        m.trace(0.0, media=True, records=True, no_map=True)
+        if e: e[1].record()
+        sp = pmdist.allgather_records(*[m.record_buffers(0)[i] for i in (0, 1, 3)])
+        vp = pmdist.allgather_records(*[m.record_buffers(1)[i] for i in (0, 1, 3)])
+        if e: e[2].record()
+        m.knn_build_points(0, sp[0], sp[1], sp[2], records=True)
+        m.knn_build_points(1, vp[0], vp[1], vp[2], records=True)
+        if e: e[3].record()
+        # the k-NN gather cost varies strongly over the image: interleave 8-row bands across the ranks and sum the frames
+        # (all other rows are zero, so the sum is exact)
+        if world > 1:
+            rgba.zero_(); rgbf.zero_()
+        for b0 in range(8 * rank, H, 8 * world):
+            m.render_knn(W, H, 0.0, True, a.knn, float("inf"), 2.0e-4 * 10000.0 / NP, 4.0e-3 * 10000.0 / NP, rgba=rgba, rgbf=rgbf,
+                         y0=b0, y1=min(b0 + 8, H))
+        if world > 1:
+            dist.all_reduce(rgbf)
+            dist.all_reduce(rgba)
+        if e: e[4].record()
+        step_b.keep = (sp, vp)    # the maps reference the gathered arrays
+
+    def step_a(e=None):
         if e: e[0].record()
         m.clear_map()
         m.trace(0.0, media=True)
@@ -303,6 +331,10 @@ def main():
         pmdist.gather_frame(rgba, y0, y1)
         pmdist.gather_frame(rgbf, y0, y1)
         if e: e[4].record()
+
+    step = step_b if a.mode == "b" else step_a
+    if a.mode == "b":
+        m.set_record_capacity(int(2.6 * (last - first)) + 4096)
 
     def barrier():
         if world > 1:
@@ -340,7 +372,7 @@ def main():
 
     def e2e_step():
         m.set_scene(scene)                        # the frame's only host input: the scene / parameter block
-        if world == 1:
+        if world == 1 and a.mode == "a":
             m.frame(W, H, 0.0, emit=True, interp=False, media=True, out_u8=h_rgba, out_f32=h_rgbf)
         else:
             step()
@@ -387,13 +419,15 @@ def main():
         except Exception:
             pass
         line = {
-            "metric": METRIC, "value": ms_per_step, "unit": "ms", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "metric": METRIC if a.mode == "a" else METRIC.replace("(trace", "Mode B k=%d (trace" % a.knn), "value": ms_per_step, "unit": "ms", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": workload_config(a, {"parallelism": "photon-range x%d + row-band x%d" % (world, world)}),
             "photons_per_s": NP / (ms_per_step * 1e-3), "pixels_per_s": W * H / (ms_per_step * 1e-3),
-            "stages_ms": {"clear+trace": float(stages[0]), "allreduce": float(stages[1]), "build_map+tables": float(stages[2]),
-                          "render(+gather)": float(stages[3])},
+            "stages_ms": ({"clear+trace": float(stages[0]), "allreduce": float(stages[1]), "build_map+tables": float(stages[2]),
+                           "render(+gather)": float(stages[3])} if a.mode == "a" else
+                          {"trace_with_records": float(stages[0]), "allgather_records": float(stages[1]), "build_maps": float(stages[2]),
+                           "knn_render(+gather)": float(stages[3])}),
             "gpu_launches": int(launches),
             "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": C.sizeof(pmb200.Scene),
                     "d2h_bytes_per_step": W * H * 4 + W * H * 16, "steps": e2e_steps,
@@ -407,19 +441,19 @@ def main():
                                  "HBM bound; see DESIGN.md 'rooflines' and profiles/"},
             "clocks": clocks,
         }
-        if not a.no_cpu_baseline and world == 1:
+        if not a.no_cpu_baseline and world == 1 and a.mode == "a":
             try:
                 v, d = cpu_reference_frame_ms(a)
                 line["cpu_baseline"] = {"value": v, "unit": "ms", "cores": d["cores"], "kind": d["kind"], "sample": d["sample"],
                                         "emit_ms_scaled": d["emit_ms_scaled"], "render_ms_scaled": d["render_ms_scaled"]}
             except Exception as ex:   # the baseline is reported, never required for the measurement itself
                 line["cpu_baseline"] = {"value": None, "unit": "ms", "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
-        if not a.no_mode_b and world == 1:
+        if not a.no_mode_b and world == 1 and a.mode == "a":
             try:
                 line["mode_b"] = mode_b_numbers(pmb200, torch, a, local)
             except Exception as ex:
                 line["mode_b"] = {"failed": repr(ex)}
-        if not a.no_ref_cuda and world == 1:
+        if not a.no_ref_cuda and world == 1 and a.mode == "a":
             try:
                 line["reference_cuda_kernel"] = time_reference_cuda(a, m.get_random_table(), rgba)
             except Exception as ex:

@@ -69,7 +69,7 @@ def lib():
             "pm_set_record_capacity": (i32, [vp, i64]), "pm_record_count": (i32, [vp, C.POINTER(i64)]),
             "pm_get_records_host": (i32, [vp, vp, i64]),
             "pm_record_buffers": (i32, [vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i64)]),
-            "pm_knn_set_curve": (i32, [vp, i32]), "pm_knn_build": (i32, [vp, i32]), "pm_knn_build_points": (i32, [vp, i32, vp, vp, i64]),
+            "pm_knn_set_curve": (i32, [vp, i32]), "pm_knn_build": (i32, [vp, i32]), "pm_knn_build_points": (i32, [vp, i32, vp, vp, i64, b]),
             "pm_knn_size": (i32, [vp, i32, C.POINTER(i64), C.POINTER(C.c_int32)]),
             "pm_knn_query": (i32, [vp, i32, vp, i64, i32, f32, vp, vp, vp]),
             "pm_knn_radiance": (i32, [vp, i32, vp, i64, i32, f32, vp]),
@@ -265,9 +265,10 @@ class PhotonMapper:
     def knn_build(self, which=0):
         self._ck(self.L.pm_knn_build(self.h, which))
 
-    def knn_build_points(self, which, pos4, power4, n):
-        """pos4 / power4: DEVICE float4 arrays (torch tensors or addresses) that outlive the map."""
-        self._ck(self.L.pm_knn_build_points(self.h, which, _ptr(pos4), _ptr(power4), n))
+    def knn_build_points(self, which, pos4, power4, n, records=False):
+        """pos4 / power4: DEVICE float4 arrays (torch tensors or addresses) that outlive the map.  records=True: the rows
+        are photon records (e.g. all-gathered from several GPUs); the surface map then keeps wall hits only."""
+        self._ck(self.L.pm_knn_build_points(self.h, which, _ptr(pos4), _ptr(power4), n, records))
 
     def knn_size(self, which=0):
         n, lv = C.c_int64(), C.c_int32()

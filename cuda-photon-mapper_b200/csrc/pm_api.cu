@@ -535,7 +535,7 @@ int pm_get_records_host(pm_context *c, pm_record *out, int64_t max_records) {
 }
 
 // ---- Mode B ----------------------------------------------------------------------------------------------
-int pm_knn_build_points(pm_context *c, int which, const float *pos4, const float *pow4, int64_t n) {
+int pm_knn_build_points(pm_context *c, int which, const float *pos4, const float *pow4, int64_t n, bool records) {
   ARG(c, c && (which == PM_MAP_SURFACE || which == PM_MAP_VOLUME), "bad map id");
   ARG(c, n >= 0 && (n == 0 || pos4), "null points");
   CK(c, cudaSetDevice(c->device));
@@ -543,7 +543,8 @@ int pm_knn_build_points(pm_context *c, int which, const float *pos4, const float
   cudaError_t e;
   {
     SpanGuard g(c, K_KNN_BUILD);
-    e = knn_build(c->knn[which], (const float4 *)pos4, (const float4 *)pow4, n, 0, c->knn_curve, c->stream, &launches);
+    e = knn_build(c->knn[which], (const float4 *)pos4, (const float4 *)pow4, n, (records && which == PM_MAP_SURFACE) ? 1 : 0, c->knn_curve,
+                  c->stream, &launches);
   }
   c->launches += launches;
   CK(c, e);

@@ -54,3 +54,26 @@ def gather_frame(frame, y0, y1):
         dist.all_gather(parts, band.clone())
         frame.view(-1).copy_(torch.cat(parts))
     return frame
+
+
+def allgather_records(pos_ptr, pow_ptr, count):
+    """All-gather one record set (SoA float4 pos_meta / power_index, `count` rows on this rank) from every rank.
+    Returns (pos4, power4, total): contiguous [total, 4] float32 device tensors in rank order -- the input of
+    PhotonMapper.knn_build_points(..., records=True).  Single process: zero-copy views of the local buffers."""
+    world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+    if world == 1:
+        return device_tensor(pos_ptr, count * 4, "<f4").view(count, 4), device_tensor(pow_ptr, count * 4, "<f4").view(count, 4), count
+    counts = torch.zeros(world, dtype=torch.int64, device="cuda")
+    counts[dist.get_rank()] = count
+    dist.all_reduce(counts)
+    counts = [int(c) for c in counts.tolist()]
+    cmax, total = max(counts), sum(counts)
+    out = []
+    for ptr in (pos_ptr, pow_ptr):
+        local = torch.zeros((cmax, 4), dtype=torch.float32, device="cuda")
+        if count:
+            local[:count] = device_tensor(ptr, count * 4, "<f4").view(count, 4)
+        gathered = torch.empty((world, cmax, 4), dtype=torch.float32, device="cuda")
+        dist.all_gather_into_tensor(gathered.view(-1), local.view(-1))
+        out.append(torch.cat([gathered[r, :counts[r]] for r in range(world)]) if min(counts) < cmax else gathered.view(-1, 4))
+    return out[0], out[1], total

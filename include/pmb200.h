@@ -121,7 +121,8 @@ int pm_record_buffers(pm_context *ctx, int which, float **dev_pos_meta /* float4
 #define PM_CURVE_HILBERT 1   /* the same cell along the 3-D Hilbert curve (default: tighter leaf / node boxes) */
 int pm_knn_set_curve(pm_context *ctx, int curve);
 int pm_knn_build(pm_context *ctx, int which);
-int pm_knn_build_points(pm_context *ctx, int which, const float *dev_pos4, const float *dev_power4, int64_t n);
+int pm_knn_build_points(pm_context *ctx, int which, const float *dev_pos4, const float *dev_power4, int64_t n,
+                        bool records /* true: rows are photon records (w = meta); the surface map keeps wall hits only */);
 int pm_knn_size(pm_context *ctx, int which, int64_t *n_points, int32_t *n_levels);
 /* nq DEVICE queries (float4, w ignored); per query up to k photons with d2 <= max_r2 (INFINITY: pure k-NN), ascending
  * (d2, index): dev_idx[nq*k] (original indices, -1 = none), dev_d2[nq*k], dev_cnt[nq].  k <= 128. */
