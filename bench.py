@@ -305,13 +305,12 @@ def main():
         m.knn_build_points(0, sp[0], sp[1], sp[2], records=True)
         m.knn_build_points(1, vp[0], vp[1], vp[2], records=True)
         if e: e[3].record()
-        # the k-NN gather cost varies strongly over the image: interleave 8-row bands across the ranks and sum the frames
-        # (all other rows are zero, so the sum is exact)
+        # the k-NN gather cost varies strongly over the image: rank r renders rows r, r+N, r+2N, ... and the frames are
+        # summed (all other rows are zero, so the sum is exact)
         if world > 1:
             rgba.zero_(); rgbf.zero_()
-        for b0 in range(8 * rank, H, 8 * world):
-            m.render_knn(W, H, 0.0, True, a.knn, float("inf"), 2.0e-4 * 10000.0 / NP, 4.0e-3 * 10000.0 / NP, rgba=rgba, rgbf=rgbf,
-                         y0=b0, y1=min(b0 + 8, H))
+        m.render_knn(W, H, 0.0, True, a.knn, float("inf"), 2.0e-4 * 10000.0 / NP, 4.0e-3 * 10000.0 / NP, rgba=rgba, rgbf=rgbf,
+                     y0=rank, y1=H, y_step=world)
         if world > 1:
             dist.all_reduce(rgbf)
             dist.all_reduce(rgba)

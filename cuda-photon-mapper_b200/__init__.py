@@ -74,6 +74,7 @@ def lib():
             "pm_knn_query": (i32, [vp, i32, vp, i64, i32, f32, vp, vp, vp]),
             "pm_knn_radiance": (i32, [vp, i32, vp, i64, i32, f32, vp]),
             "pm_render_knn": (i32, [vp, f32, b, i32, i32, i32, i32, i32, f32, f32, f32, vp, vp]),
+            "pm_render_knn_rows": (i32, [vp, f32, b, i32, i32, i32, i32, i32, i32, f32, f32, f32, vp, vp]),
             "pm_render_knn_host": (i32, [vp, f32, b, i32, i32, i32, f32, f32, f32, vp, vp]),
             "pm_knn_sorted_host": (i32, [vp, i32, vp, vp, i64]),
             "pm_knn_level_host": (i32, [vp, i32, i32, C.POINTER(i64), vp]),
@@ -282,10 +283,10 @@ class PhotonMapper:
         self._ck(self.L.pm_knn_radiance(self.h, which, _ptr(queries4), nq, k, max_r2, _ptr(rgb4)))
 
     def render_knn(self, w, h, t=0.0, media=False, k=50, max_r2=float("inf"), w_surface=1.0, w_volume=1.0, rgba=None, rgbf=None,
-                   y0=0, y1=None):
-        """Mode B frame into caller-owned DEVICE buffers."""
+                   y0=0, y1=None, y_step=1):
+        """Mode B frame into caller-owned DEVICE buffers: rows y0, y0+y_step, ... < y1."""
         y1 = h if y1 is None else y1
-        self._ck(self.L.pm_render_knn(self.h, t, media, w, h, y0, y1, k, max_r2, w_surface, w_volume, _ptr(rgba), _ptr(rgbf)))
+        self._ck(self.L.pm_render_knn_rows(self.h, t, media, w, h, y0, y1, y_step, k, max_r2, w_surface, w_volume, _ptr(rgba), _ptr(rgbf)))
 
     def knn_sorted(self, which, n):
         keys = np.empty(n, np.uint32); perm = np.empty(n, np.uint32)

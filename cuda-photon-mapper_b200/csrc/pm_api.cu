@@ -603,15 +603,19 @@ int pm_knn_radiance(pm_context *c, int which, const float *q4, int64_t nq, int k
 }
 int pm_render_knn(pm_context *c, float t, bool media, int width, int height, int y0, int y1, int k, float max_r2, float w_surface,
                   float w_volume, pm_uchar4 *dev_rgba, float *dev_rgbf) {
+  return pm_render_knn_rows(c, t, media, width, height, y0, y1, 1, k, max_r2, w_surface, w_volume, dev_rgba, dev_rgbf);
+}
+int pm_render_knn_rows(pm_context *c, float t, bool media, int width, int height, int y0, int y1, int y_step, int k, float max_r2,
+                       float w_surface, float w_volume, pm_uchar4 *dev_rgba, float *dev_rgbf) {
   ARG(c, c != nullptr, "null context");
-  ARG(c, width > 0 && height > 0 && y0 >= 0 && y0 <= y1 && y1 <= height, "bad frame geometry");
+  ARG(c, width > 0 && height > 0 && y0 >= 0 && y0 <= y1 && y1 <= height && y_step >= 1, "bad frame geometry");
   ARG(c, k >= 1 && k <= 128, "k must be in [1, 128]");
   if ((c->knn[0].n > 0 && !c->knn[0].power) || (media && c->knn[1].n > 0 && !c->knn[1].power)) { c->err = "maps were built without powers"; return PM_ERR_STATE; }
   CK(c, cudaSetDevice(c->device));
   c->dsc = make_device_scene(c->scene, t);
   {
     SpanGuard g(c, K_KNN_RENDER);
-    CK(c, knn_render(c->dsc, c->knn[0], c->knn[1], k, max_r2, w_surface, w_volume, width, height, y0, y1, media, (uchar4 *)dev_rgba,
+    CK(c, knn_render(c->dsc, c->knn[0], c->knn[1], k, max_r2, w_surface, w_volume, width, height, y0, y1, y_step, media, (uchar4 *)dev_rgba,
                      (float4 *)dev_rgbf, c->num_sms, c->stream));
   }
   if (y1 > y0) c->launches++;

@@ -56,7 +56,7 @@ cudaError_t knn_build(KnnMap &m, const float4 *pos, const float4 *power, long lo
 cudaError_t knn_query(const KnnMap &m, const float4 *queries, long long nq, int k, float max_r2, int32_t *idx, float *d2, int32_t *cnt,
                       int volume, float4 *rgb, int num_sms, cudaStream_t st);
 cudaError_t knn_render(const DeviceScene &sc, const KnnMap &ms, const KnnMap &mv, int k, float max_r2, float w_surf, float w_vol, int width,
-                       int height, int y0, int y1, bool media, uchar4 *rgba, float4 *rgbf, int num_sms, cudaStream_t st);
+                       int height, int y0, int y1, int y_step, bool media, uchar4 *rgba, float4 *rgbf, int num_sms, cudaStream_t st);
 void knn_free(KnnMap &m);
 
 }  // namespace pm

@@ -516,7 +516,7 @@ template <int KL>
 __global__ void __launch_bounds__(kQueryThreads) knn_render_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ TreeView tvs,
                                                                    const __grid_constant__ TreeView tvv, const float4 *__restrict__ pow_s,
                                                                    const float4 *__restrict__ pow_v, int k, float max_r2, float w_surf,
-                                                                   float w_vol, int width, int height, int y0, int y1, int media,
+                                                                   float w_vol, int width, int height, int y0, int y1, int y_step, int media,
                                                                    uchar4 *__restrict__ rgba, float4 *__restrict__ rgbf) {
   extern __shared__ __align__(128) unsigned char dyn[];
   float *sbox_s = (float *)dyn, *sbox_v = sbox_s + kMaxStagedFloats;
@@ -527,9 +527,10 @@ __global__ void __launch_bounds__(kQueryThreads) knn_render_kernel(const __grid_
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   u64 *pend = pend_all + w * 64;
   const long long warps = (long long)gridDim.x * (kQueryThreads / 32);
-  const long long p0 = (long long)y0 * width, p1 = (long long)y1 * width;
-  for (long long pix = p0 + (long long)blockIdx.x * (kQueryThreads / 32) + w; pix < p1; pix += warps) {
-    int px = (int)(pix % width), py = (int)(pix / width);
+  const long long nrows = (y1 - y0 + y_step - 1) / y_step, npix = nrows * width;   // rows y0, y0+y_step, ... < y1
+  for (long long j = (long long)blockIdx.x * (kQueryThreads / 32) + w; j < npix; j += warps) {
+    int px = (int)(j % width), py = y0 + (int)(j / width) * y_step;
+    const long long pix = (long long)py * width + px;
     float x = (float)px + sc.cam_ox, y = (float)py + sc.cam_oy;
     v3 rgb = V(0.0f, 0.0f, 0.0f);
     const v3 origin = V(0.0f, 0.0f, 0.0f);
@@ -666,8 +667,9 @@ cudaError_t knn_query(const KnnMap &m, const float4 *queries, long long nq, int 
 }
 
 cudaError_t knn_render(const DeviceScene &sc, const KnnMap &ms, const KnnMap &mv, int k, float max_r2, float w_surf, float w_vol, int width,
-                       int height, int y0, int y1, bool media, uchar4 *rgba, float4 *rgbf, int num_sms, cudaStream_t st) {
-  long long n = (long long)(y1 - y0) * width;
+                       int height, int y0, int y1, int y_step, bool media, uchar4 *rgba, float4 *rgbf, int num_sms, cudaStream_t st) {
+  if (y_step < 1) y_step = 1;
+  long long n = (long long)((y1 - y0 + y_step - 1) / y_step) * width;
   if (n <= 0) return cudaSuccess;
   TreeView tvs = make_view(ms), tvv = make_view(mv);
   long long want = (n + kQueryThreads / 32 - 1) / (kQueryThreads / 32), cap = (long long)num_sms * 16;
@@ -677,7 +679,7 @@ cudaError_t knn_render(const DeviceScene &sc, const KnnMap &ms, const KnnMap &mv
   do {                                                                                                                     \
     KCK(cudaFuncSetAttribute(knn_render_kernel<KL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
     knn_render_kernel<KL><<<grid, kQueryThreads, smem, st>>>(sc, tvs, tvv, ms.power, mv.power, k, max_r2, w_surf, w_vol, width, height, y0, \
-                                                              y1, media ? 1 : 0, rgba, rgbf);                               \
+                                                              y1, y_step, media ? 1 : 0, rgba, rgbf);                               \
   } while (0)
   if (k <= 32) LAUNCH_RENDER(1); else if (k <= 64) LAUNCH_RENDER(2); else LAUNCH_RENDER(4);
 #undef LAUNCH_RENDER

@@ -135,6 +135,10 @@ int pm_knn_radiance(pm_context *ctx, int which, const float *dev_queries4, int64
  * like the reference (media: march sum + 0.15 * wall term).  Both maps must have been built with powers. */
 int pm_render_knn(pm_context *ctx, float animTime, bool participatingMediaFlag, int width, int height, int y0, int y1, int k,
                   float max_r2, float w_surface, float w_volume, pm_uchar4 *dev_rgba, float *dev_rgbf);
+/* rows y0, y0+y_step, y0+2*y_step, ... < y1 only: with y0 = rank and y_step = number of GPUs the (strongly position
+ * dependent) gather cost is balanced across GPUs */
+int pm_render_knn_rows(pm_context *ctx, float animTime, bool participatingMediaFlag, int width, int height, int y0, int y1, int y_step,
+                       int k, float max_r2, float w_surface, float w_volume, pm_uchar4 *dev_rgba, float *dev_rgbf);
 /* the same through HOST buffers (context-owned device frame buffers, synchronous copy-back) */
 int pm_render_knn_host(pm_context *ctx, float animTime, bool participatingMediaFlag, int width, int height, int k, float max_r2,
                        float w_surface, float w_volume, pm_uchar4 *host_rgba, float *host_rgbf);

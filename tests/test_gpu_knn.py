@@ -192,7 +192,8 @@ def test_render_knn_vs_oracle(pm, oracle, media):
     rgbf = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
     rgba = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
     m.render_knn(w, h, 0.0, media, k, float("inf"), w_s, w_v, rgba=rgba, rgbf=rgbf, y0=0, y1=20)
-    m.render_knn(w, h, 0.0, media, k, float("inf"), w_s, w_v, rgba=rgba, rgbf=rgbf, y0=20, y1=h)
+    m.render_knn(w, h, 0.0, media, k, float("inf"), w_s, w_v, rgba=rgba, rgbf=rgbf, y0=20, y1=h, y_step=2)   # interleaved rows
+    m.render_knn(w, h, 0.0, media, k, float("inf"), w_s, w_v, rgba=rgba, rgbf=rgbf, y0=21, y1=h, y_step=2)
     m.sync()
 
     def records(which):
