@@ -46,13 +46,16 @@ def parse():
                     help="a (default, headline): the reference's voxel-map estimator; b: k-NN photon map (records all-gathered, "
                          "tree built on every rank, row bands) -- for Mode B scaling runs")
     ap.add_argument("--knn", type=int, default=50, help="k of the Mode B estimate")
+    ap.add_argument("--passes", type=int, default=1,
+                    help="progressive photon mapping (BASELINE config 5): photon passes accumulated per frame, each with a fresh "
+                         "direction table from the continuing MWC stream (Mode A)")
     return ap.parse_args()
 
 
 def workload_config(a, extra=None):
     cfg = {"workload": "BASELINE config 4: default participating-media scene, %d photons, %dx%d, Mode A "
                        "(reference voxel-map estimator), media on, interpolate off" % (a.photons, a.width, a.height),
-           "photons": a.photons, "width": a.width, "height": a.height, "media": True, "interpolate": False,
+           "photons": a.photons, "passes": a.passes, "width": a.width, "height": a.height, "media": True, "interpolate": False,
            "rng": "MWC table (reference stream, jump-ahead)", "energy_scale": 10000.0 / a.photons,
            "cache": "inputs larger than L2: the 12 B/photon direction table (%.0f MB) is streamed every frame"
                     % (a.photons * 12 / 1e6)}
@@ -252,6 +255,36 @@ def mode_b_numbers(pmb200, torch, a, device):
     return out
 
 
+def config2_numbers(pmb200, torch, device):
+    """BASELINE config 2: default participating-media scene, 1M photons, 1024x1024, one B200, ours vs the reference CUDA kernel."""
+    n, W, H = 1048576, 1024, 1024
+    m = pmb200.PhotonMapper(device=device, n_photons=n)
+    m.set_stream(torch.cuda.current_stream().cuda_stream)
+    m.set_scene(pmb200.default_scene(sz_img=H))
+    m.set_energy_scale(10000.0 / n)
+    m.init_random_numbers()
+    rgba = torch.zeros((H, W, 4), dtype=torch.uint8, device="cuda")
+    rgbf = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
+
+    def frame():
+        m.clear_map(); m.trace(0.0, media=True); m.build_map()
+        m.render_device(W, H, 0.0, False, True, rgba=rgba, rgbf=rgbf)
+    for _ in range(5):
+        frame()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(50):
+        frame()
+    e1.record(); torch.cuda.synchronize()
+    out = {"workload": "default media scene, 1048576 photons, 1024x1024, Mode A", "ms_per_frame": e0.elapsed_time(e1) / 50}
+    class A: pass
+    a2 = A(); a2.photons, a2.width, a2.height = n, W, H
+    out["reference_cuda_kernel"] = time_reference_cuda(a2, m.get_random_table(), rgba)
+    m.close()
+    return out
+
+
 def main():
     a = parse()
     if a.impl == "reference":
@@ -280,7 +313,7 @@ def main():
     scene = pmb200.default_scene(sz_img=H)
     scene.cam_ox = -(W - H) / 2.0
     m.set_scene(scene)
-    m.set_energy_scale(10000.0 / NP)
+    m.set_energy_scale(10000.0 / NP / a.passes)
     m.init_random_numbers()                       # once, outside the timed region (callbacksPBO.cpp:55-58)
     first, last = pmdist.photon_shard(NP, rank, world)
     m.set_photon_range(first, last)
@@ -321,6 +354,9 @@ def main():
         if e: e[0].record()
         m.clear_map()
         m.trace(0.0, media=True)
+        for _ in range(a.passes - 1):             # progressive: further passes accumulate into the same exact accumulators
+            m.init_random_numbers()
+            m.trace(0.0, media=True)
         if e: e[1].record()
         pmdist.allreduce_accumulators(acc)        # exact: int64 sum over NVLink (no-op at N=1)
         if e: e[2].record()
@@ -452,6 +488,11 @@ def main():
                 line["mode_b"] = mode_b_numbers(pmb200, torch, a, local)
             except Exception as ex:
                 line["mode_b"] = {"failed": repr(ex)}
+        if not a.no_ref_cuda and world == 1 and a.mode == "a" and a.passes == 1:
+            try:
+                line["config2"] = config2_numbers(pmb200, torch, local)
+            except Exception as ex:
+                line["config2"] = {"failed": repr(ex)}
         if not a.no_ref_cuda and world == 1 and a.mode == "a":
             try:
                 line["reference_cuda_kernel"] = time_reference_cuda(a, m.get_random_table(), rgba)

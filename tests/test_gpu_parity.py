@@ -175,6 +175,30 @@ def test_photon_range_sharding_is_exact(pm, oracle):
     m.close()
 
 
+def test_progressive_passes_accumulate(pm, oracle):
+    """Progressive photon mapping (BASELINE config 5): several passes accumulate into the same map without clearing; every
+    pass re-fills the direction table from the continuing MWC stream, as repeated display() frames of the reference would
+    if the grid were not cleared.  The MWC state stays bit-exact, the map stays within MAP_TOL of the sequential oracle."""
+    n, passes = 6000, 3
+    osc = oracle.default_scene()
+    m = _mapper(pm, n, copy_scene(pm.Scene, osc))
+    m.clear_map()
+    st = (6548, 316)
+    ogrid = np.zeros((32, 32, 32, 3), np.float32)
+    for _ in range(passes):
+        m.init_random_numbers()
+        m.trace(0.0, media=True)
+        table, st = oracle.mwc_table(n, *st)
+        ogrid, _, st = oracle.emit(osc, table, 0, n, 0.0, True, rng=st, grid=ogrid)
+        assert m.get_mwc_state() == st
+    m.set_energy_scale(1.0 / passes)
+    m.build_map()
+    grid = m.get_map()
+    want = ogrid / np.float32(passes)
+    assert np.abs(grid - want).max() <= MAP_TOL * np.abs(want).max()
+    m.close()
+
+
 def _fold(pm, acc):
     """Accumulators with the grey replicas summed (a CTA picks its replica by block index, so only the sum is
     shard-invariant)."""

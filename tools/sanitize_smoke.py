@@ -1,0 +1,26 @@
+#!/usr/bin/env python
+"""tools/sanitize_smoke.py -- small end-to-end run of every kernel, meant to be wrapped in compute-sanitizer:
+    compute-sanitizer --tool memcheck  python tools/sanitize_smoke.py
+    compute-sanitizer --tool racecheck python tools/sanitize_smoke.py
+(the reference has data races by design -- non-atomic += on the grid, shared MWC state; this build must have none)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, pmb200
+
+n, w, h = 20000, 96, 64
+m = pmb200.PhotonMapper(n_photons=n)
+sc = pmb200.default_scene(sz_img=64); sc.cam_ox = -16.0
+m.set_scene(sc)
+m.init_random_numbers()
+m.set_record_capacity(16 * n)
+m.clear_map()
+m.trace(0.3, media=True, records=True)
+m.build_map()
+u8, f32 = m.render(w, h, 0.3, True, True)
+m.knn_build(0); m.knn_build(1)
+rgba = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda"); rgbf = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
+m.render_knn(w, h, 0.3, True, 50, float("inf"), 1e-4, 1e-2, rgba=rgba, rgbf=rgbf)
+m.render_knn(w, h, 0.3, False, 100, 0.01, 1e-4, 1e-2, rgba=rgba, rgbf=rgbf, y0=1, y1=h, y_step=3)
+m.sync()
+print("sanitize smoke ok: map sum %.4f, frame mean %.5f, knn frame mean %.5f" % (float(m.get_map().sum()), float(f32[..., :3].mean()), float(rgbf[..., :3].mean())))
+m.close()
