@@ -319,6 +319,7 @@ struct TreeView {
   const float *box[8];    // six arrays of length pad[l] each
   int staged_from;        // levels >= staged_from are read from shared memory
   long long staged_floats;
+  int staged_off[8];      // float offset of a staged level inside the shared-memory copy
 };
 
 constexpr int kQueryThreads = 256;
@@ -369,9 +370,6 @@ __device__ __forceinline__ void knn_search(const TreeView &tv, const float *__re
     }
   };
 
-  const int topl = tv.levels - 1;   // the root groups the entities of this level
-  if (topl == 0) {                  // <= 32 leaves... handled by the generic walk below with a virtual root
-  }
   // per-level traversal state is warp-uniform; level l's (node, visited mask) is parked in lane l's registers
   long long my_node = 0; unsigned my_mask = 0;
   int level = tv.levels;            // "virtual" level above the top: its single node 0 has the top-level entities as children
@@ -385,7 +383,7 @@ __device__ __forceinline__ void knn_search(const TreeView &tv, const float *__re
     if (e < tv.cnt[cl] && !((visited >> lane) & 1u)) {
       float lx, ly, lz, hx, hy, hz;
       if (cl >= tv.staged_from) {
-        const float *b = sbox; for (int l = tv.staged_from; l < cl; l++) b += 6 * tv.pad[l];
+        const float *b = sbox + tv.staged_off[cl];
         long long p = tv.pad[cl];
         lx = b[e]; ly = b[p + e]; lz = b[2 * p + e]; hx = b[3 * p + e]; hy = b[4 * p + e]; hz = b[5 * p + e];
       } else {
@@ -649,6 +647,10 @@ static TreeView make_view(const KnnMap &m) {
     long long f = tv.staged_floats + 6 * m.pad[l];
     if (f > kMaxStagedFloats) break;
     tv.staged_floats = f; tv.staged_from = l;
+  }
+  {
+    int off = 0;
+    for (int l = tv.staged_from; l < m.levels; l++) { tv.staged_off[l] = off; off += 6 * (int)m.pad[l]; }
   }
   return tv;
 }
