@@ -81,9 +81,9 @@ def test_structural_agreement_with_reference_cuda_kernel(pm, oracle):
     """The reference's own CUDA kernels (photonMappingKernel.cu recompiled for sm_100a, oracle/_ref) on the same table.
     On a B200 its non-atomic `+=` (PMK:1068, :1158, :1177) loses most concurrent deposits -- measured here: its voxel map
     holds only ~27 % of the energy the sequential execution (and this build) deposits -- so its frame is the same picture,
-    darker.  Hence a STRUCTURAL check: its map never holds more energy than ours, and with the overall brightness matched
-    (energy scale = ratio of the map sums) the two frames correlate (>= 0.6; measured 0.75-0.8 -- the lost updates are
-    concentrated on the brightest voxels, so the reference's frame is not a uniformly scaled copy)."""
+    darker.  Hence a STRUCTURAL check: its map never holds more energy than ours, and the two frames correlate (>= 0.6;
+    measured 0.75-0.8 -- the lost updates are concentrated on the brightest voxels and ours saturates there, so the
+    reference's frame is not a uniformly scaled copy)."""
     import torch
     path = os.path.join(ROOT, "oracle", "_ref", "libpmref_cuda_10000.so")
     if not os.path.exists(path):
@@ -108,8 +108,6 @@ def test_structural_agreement_with_reference_cuda_kernel(pm, oracle):
         m.emit(0.0, media=bool(media))
         ours = m.get_map()
         assert 0.05 * ours.sum() < rgrid.sum() <= 1.001 * ours.sum(), (media, rgrid.sum(), ours.sum())
-        m.set_energy_scale(float(rgrid.sum() / ours.sum()))     # match the overall brightness the races left
-        m.build_map()
         u8, _ = m.render(w, h, 0.0, False, bool(media), want_f32=False)
         b = u8[..., :3].astype(np.float64)
         corr = np.corrcoef(a.ravel(), b.ravel())[0, 1]
