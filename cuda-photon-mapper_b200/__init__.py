@@ -73,6 +73,7 @@ def lib():
             "pm_knn_size": (i32, [vp, i32, C.POINTER(i64), C.POINTER(C.c_int32)]),
             "pm_knn_query": (i32, [vp, i32, vp, i64, i32, f32, vp, vp, vp]),
             "pm_knn_radiance": (i32, [vp, i32, vp, i64, i32, f32, vp]),
+            "pm_knn_radiance_cone": (i32, [vp, vp, i64, i32, f32, f32, vp]),
             "pm_render_knn": (i32, [vp, f32, b, i32, i32, i32, i32, i32, f32, f32, f32, vp, vp]),
             "pm_render_knn_rows": (i32, [vp, f32, b, i32, i32, i32, i32, i32, i32, f32, f32, f32, vp, vp]),
             "pm_render_knn_host": (i32, [vp, f32, b, i32, i32, i32, f32, f32, f32, vp, vp]),
@@ -287,6 +288,10 @@ class PhotonMapper:
         """Mode B frame into caller-owned DEVICE buffers: rows y0, y0+y_step, ... < y1."""
         y1 = h if y1 is None else y1
         self._ck(self.L.pm_render_knn_rows(self.h, t, media, w, h, y0, y1, y_step, k, max_r2, w_surface, w_volume, _ptr(rgba), _ptr(rgbf)))
+
+    def knn_radiance_cone(self, queries4, nq, k, sq_radius, exposure, rgb4):
+        """Legacy fixed-radius cone-filter estimate; queries4 = (x, y, z, wall id)."""
+        self._ck(self.L.pm_knn_radiance_cone(self.h, _ptr(queries4), nq, k, sq_radius, exposure, _ptr(rgb4)))
 
     def knn_sorted(self, which, n):
         keys = np.empty(n, np.uint32); perm = np.empty(n, np.uint32)

@@ -638,6 +638,30 @@ int pm_render_knn_host(pm_context *c, float t, bool media, int width, int height
   CK(c, cudaStreamSynchronize(c->stream));
   return PM_OK;
 }
+int pm_knn_radiance_cone(pm_context *c, const float *q4, int64_t nq, int k, float sq_radius, float exposure, float *rgb4) {
+  ARG(c, c && rgb4, "null output");
+  ARG(c, k >= 1 && k <= 128, "k must be in [1, 128]");
+  ARG(c, nq >= 0 && (nq == 0 || q4), "null queries");
+  ARG(c, sq_radius >= 0.0f && exposure != 0.0f, "bad radius / exposure");
+  const KnnMap &m = c->knn[PM_MAP_SURFACE];
+  if (m.n > 0 && (m.src_pos != c->d_rec_pos || !c->d_rec_dir)) { c->err = "the cone filter needs the surface map built from the record buffers (pm_knn_build)"; return PM_ERR_STATE; }
+  CK(c, cudaSetDevice(c->device));
+  // inward wall normals: surfaceNormal(1, id, p, gOrigin) = normalize(e_axis * (0 - offset)), photonMappingKernel - Copy.cu:193
+  float normals[PM_MAX_PLANES][3];
+  memset(normals, 0, sizeof(normals));
+  for (int i = 0; i < PM_MAX_PLANES; i++) {
+    int axis = (int)c->scene.planes[i][0];
+    float off = c->scene.planes[i][1];
+    if (axis >= 0 && axis <= 2 && off != 0.0f) normals[i][axis] = off > 0.0f ? -1.0f : 1.0f;
+  }
+  {
+    SpanGuard g(c, K_KNN_QUERY);
+    CK(c, knn_query(m, (const float4 *)q4, nq, k, sq_radius, nullptr, nullptr, nullptr, 0, (float4 *)rgb4, c->num_sms, c->stream, c->d_rec_pos,
+                    c->d_rec_dir, &normals[0][0], exposure));
+  }
+  if (nq > 0) c->launches++;
+  return PM_OK;
+}
 int pm_knn_sorted_host(pm_context *c, int which, uint32_t *keys, uint32_t *perm, int64_t n) {
   ARG(c, c && (which == PM_MAP_SURFACE || which == PM_MAP_VOLUME), "bad map id");
   const KnnMap &m = c->knn[which];

@@ -459,12 +459,50 @@ __device__ __forceinline__ float4 knn_radiance(const TopK<KL> &top, int k, const
   return make_float4(r * inv, g * inv, b * inv, rk2);
 }
 
+// The only point-based estimator the reference's author wrote: the fixed-radius cone filter of the legacy file
+// (photonMappingKernel - Copy.cu:191-208): over the photons that hit the SAME object within sqRadius,
+//   energy += power * max(0, -dot(N, dir)) * (1 - sqrt(d2)) / exposure.
+// Here it is evaluated over the (at most k) nearest photons within the radius that the search returned.
+struct ConeArgs {
+  const float4 *pos_meta, *dir;   // per ORIGINAL record index
+  float normal[PM_MAX_PLANES][3]; // inward wall normals (surfaceNormal(type 1, id, p, gOrigin))
+  float exposure;
+  int enabled;
+};
+template <int KL>
+__device__ __forceinline__ float4 knn_cone(const TopK<KL> &top, int k, const float4 *__restrict__ power, const ConeArgs &ca, int wall, int lane) {
+  float r = 0.0f, g = 0.0f, b = 0.0f, n = 0.0f;
+  const float nx = ca.normal[wall][0], ny = ca.normal[wall][1], nz = ca.normal[wall][2];
+#pragma unroll
+  for (int i = 0; i < KL; i++) {
+    int pos = i * 32 + lane;
+    if (pos < k && top.s[i] != kMaxKey) {
+      uint32_t o = (uint32_t)(top.s[i] & 0xffffffffu);
+      int seq, kind, type, id;
+      unpack_meta(__float_as_uint(__ldg(&ca.pos_meta[o].w)), seq, kind, type, id);
+      if (type == 1 && id == wall) {
+        float4 d = __ldg(ca.dir + o), pw = __ldg(power + o);
+        float d2 = __uint_as_float((uint32_t)(top.s[i] >> 32));
+        float w = fmaxf(0.0f, -((nx * d.x + ny * d.y) + nz * d.z)) * __fdiv_rn(1.0f - __fsqrt_rn(d2), ca.exposure);
+        r += pw.x * w; g += pw.y * w; b += pw.z * w; n += 1.0f;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    r += __shfl_xor_sync(0xffffffffu, r, o); g += __shfl_xor_sync(0xffffffffu, g, o); b += __shfl_xor_sync(0xffffffffu, b, o);
+    n += __shfl_xor_sync(0xffffffffu, n, o);
+  }
+  return make_float4(r, g, b, n);
+}
+
 // mode 0: write indices / distances / counts.  mode 1: radiance estimate (sum of powers / disc area or ball volume)
 template <int KL>
 __global__ void __launch_bounds__(kQueryThreads) knn_query_kernel(const __grid_constant__ TreeView tv, const float4 *__restrict__ queries,
                                                                   long long nq, int k, float max_r2, int32_t *__restrict__ out_idx,
                                                                   float *__restrict__ out_d2, int32_t *__restrict__ out_cnt,
-                                                                  const float4 *__restrict__ power, int volume, float4 *__restrict__ out_rgb) {
+                                                                  const float4 *__restrict__ power, int volume, float4 *__restrict__ out_rgb,
+                                                                  const __grid_constant__ ConeArgs cone) {
   __shared__ __align__(128) float sbox[kMaxStagedFloats];
   __shared__ __align__(8) unsigned long long bar;
   __shared__ u64 pend_all[kQueryThreads / 32][64];
@@ -477,7 +515,9 @@ __global__ void __launch_bounds__(kQueryThreads) knn_query_kernel(const __grid_c
     TopK<KL> top;
     knn_search<KL>(tv, sbox, pend, qp.x, qp.y, qp.z, k, max_r2, lane, top);
     if (out_rgb) {
-      float4 est = knn_radiance<KL>(top, k, power, volume, lane);
+      int wall = (int)qp.w;
+      float4 est = cone.enabled ? (((unsigned)wall < (unsigned)PM_MAX_PLANES) ? knn_cone<KL>(top, k, power, cone, wall, lane) : make_float4(0.f, 0.f, 0.f, 0.f))
+                                : knn_radiance<KL>(top, k, power, volume, lane);
       if (lane == 0) out_rgb[q] = est;
     } else {
       int cnt = 0;
@@ -656,15 +696,22 @@ static TreeView make_view(const KnnMap &m) {
 }
 
 cudaError_t knn_query(const KnnMap &m, const float4 *queries, long long nq, int k, float max_r2, int32_t *idx, float *d2, int32_t *cnt,
-                      int volume, float4 *rgb, int num_sms, cudaStream_t st) {
+                      int volume, float4 *rgb, int num_sms, cudaStream_t st, const float4 *cone_pos_meta, const float4 *cone_dir,
+                      const float *cone_normals15, float exposure) {
   if (nq <= 0) return cudaSuccess;
   TreeView tv = make_view(m);
   long long want = (nq + kQueryThreads / 32 - 1) / (kQueryThreads / 32), cap = (long long)num_sms * 16;
   unsigned grid = (unsigned)(want < cap ? want : cap);
   const float4 *pw = m.power;
-  if (k <= 32) knn_query_kernel<1><<<grid, kQueryThreads, 0, st>>>(tv, queries, nq, k, max_r2, idx, d2, cnt, pw, volume, rgb);
-  else if (k <= 64) knn_query_kernel<2><<<grid, kQueryThreads, 0, st>>>(tv, queries, nq, k, max_r2, idx, d2, cnt, pw, volume, rgb);
-  else knn_query_kernel<4><<<grid, kQueryThreads, 0, st>>>(tv, queries, nq, k, max_r2, idx, d2, cnt, pw, volume, rgb);
+  ConeArgs ca;
+  memset(&ca, 0, sizeof(ca));
+  if (cone_dir) {
+    ca.pos_meta = cone_pos_meta; ca.dir = cone_dir; ca.exposure = exposure; ca.enabled = 1;
+    memcpy(ca.normal, cone_normals15, sizeof(ca.normal));
+  }
+  if (k <= 32) knn_query_kernel<1><<<grid, kQueryThreads, 0, st>>>(tv, queries, nq, k, max_r2, idx, d2, cnt, pw, volume, rgb, ca);
+  else if (k <= 64) knn_query_kernel<2><<<grid, kQueryThreads, 0, st>>>(tv, queries, nq, k, max_r2, idx, d2, cnt, pw, volume, rgb, ca);
+  else knn_query_kernel<4><<<grid, kQueryThreads, 0, st>>>(tv, queries, nq, k, max_r2, idx, d2, cnt, pw, volume, rgb, ca);
   return cudaGetLastError();
 }
 

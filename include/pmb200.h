@@ -130,6 +130,11 @@ int pm_knn_query(pm_context *ctx, int which, const float *dev_queries4, int64_t 
                  int32_t *dev_idx, float *dev_d2, int32_t *dev_cnt);
 /* radiance estimate per query: dev_rgb4[q] = (sum of the found powers / (pi r_k^2) [surface] or (4/3 pi r_k^3) [volume], r_k^2) */
 int pm_knn_radiance(pm_context *ctx, int which, const float *dev_queries4, int64_t nq, int k, float max_r2, float *dev_rgb4);
+/* the legacy estimator (the only point-based one the reference's author wrote, "photonMappingKernel - Copy.cu":191-208):
+ * fixed squared radius (0.7 there), cone filter, per-object photon lists.  Queries: float4 (x, y, z, wall id 0..4);
+ * dev_rgb4[q] = (sum over the <= k nearest surface photons within sq_radius that hit the same wall of
+ * power * max(0, -N.dir) * (1 - sqrt(d2)) / exposure, number of contributing photons).  Needs pm_knn_build(PM_MAP_SURFACE). */
+int pm_knn_radiance_cone(pm_context *ctx, const float *dev_queries4, int64_t nq, int k, float sq_radius, float exposure, float *dev_rgb4);
 /* stages 3+4+5, Mode B: rows [y0,y1) of a frame whose wall term is a k-NN estimate in the surface map and whose ten
  * ray-march terms are k-NN estimates in the volume map (media only), weighted by w_surface / w_volume and composited
  * like the reference (media: march sum + 0.15 * wall term).  Both maps must have been built with powers. */

@@ -143,3 +143,28 @@ void pmo_knn_estimate(const float *power4, const int32_t *idx, const float *d2, 
     for (int ch = 0; ch < 3; ch++) out_rgb3[3 * q + ch] = den > 0.0 ? (float)(s[ch] / den) : 0.0f;
   }
 }
+
+/* Legacy cone-filter estimate ("photonMappingKernel - Copy.cu":191-208) over a k-NN result restricted to sq_radius:
+ * for the found photons that hit wall `wall[q]` (meta type 1, same id): power * max(0, -N.dir) * (1 - sqrt(d2)) / exposure,
+ * FP32 weights as the reference, accumulated in double.  meta layout: seq[0:4) | kind[4] | (type+1)[5:7) | (id+1)[7:11). */
+void pmo_knn_cone_estimate(const float *pos_meta4, const float *dir4, const float *power4, const int32_t *idx, const float *d2,
+                           const int32_t *cnt, const int32_t *wall, const float *normals15, float exposure, long nq, int k,
+                           float *out_rgbn4) {
+  for (long q = 0; q < nq; q++) {
+    double s[3] = {0, 0, 0};
+    int used = 0;
+    int w = wall[q];
+    for (int j = 0; j < cnt[q] && w >= 0 && w < 5; j++) {
+      long o = idx[q * k + j];
+      uint32_t meta;
+      memcpy(&meta, pos_meta4 + 4 * o + 3, 4);
+      int type = (int)((meta >> 5) & 3u) - 1, id = (int)((meta >> 7) & 15u) - 1;
+      if (type != 1 || id != w) continue;
+      const float *n = normals15 + 3 * w, *d = dir4 + 4 * o, *p = power4 + 4 * o;
+      float weight = fmaxf(0.0f, -((n[0] * d[0] + n[1] * d[1]) + n[2] * d[2])) * ((1.0f - sqrtf(d2[q * k + j])) / exposure);
+      s[0] += (double)(p[0] * weight); s[1] += (double)(p[1] * weight); s[2] += (double)(p[2] * weight);
+      used++;
+    }
+    out_rgbn4[4 * q] = (float)s[0]; out_rgbn4[4 * q + 1] = (float)s[1]; out_rgbn4[4 * q + 2] = (float)s[2]; out_rgbn4[4 * q + 3] = (float)used;
+  }
+}

@@ -60,6 +60,7 @@ class Oracle:
         L.pmo_hilbert30_many.argtypes = [C.c_void_p, C.c_long, C.c_void_p]
         L.pmo_stable_sort_perm.argtypes = [C.c_void_p, C.c_long, C.c_void_p]
         L.pmo_knn_bruteforce.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.pmo_knn_cone_estimate.argtypes = [C.c_void_p] * 8 + [C.c_float, C.c_long, C.c_int, C.c_void_p]
         L.pmo_knn_estimate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_void_p]
 
     # -- scene -----------------------------------------------------------------------------------
@@ -178,4 +179,12 @@ class Oracle:
         out = np.empty((nq, 3), np.float32)
         self.lib.pmo_knn_estimate(_p(power4), _p(np.ascontiguousarray(idx)), _p(np.ascontiguousarray(d2)), _p(np.ascontiguousarray(cnt)),
                                   nq, k, int(volume), _p(out))
+        return out
+
+    def knn_cone_estimate(self, pos_meta4, dir4, power4, idx, d2, cnt, wall, normals, exposure):
+        nq, k = idx.shape
+        out = np.empty((nq, 4), np.float32)
+        a = [np.ascontiguousarray(x, t) for x, t in ((pos_meta4, np.float32), (dir4, np.float32), (power4, np.float32), (idx, np.int32),
+                                                      (d2, np.float32), (cnt, np.int32), (wall, np.int32), (normals, np.float32))]
+        self.lib.pmo_knn_cone_estimate(*[_p(x) for x in a], C.c_float(exposure), nq, k, _p(out))
         return out

@@ -230,3 +230,48 @@ def test_render_knn_vs_oracle(pm, oracle, media):
     expect_u8 = np.clip(np.nan_to_num(got[:, :3].astype(np.float64) * 255.0, nan=0.0), 0, 255).astype(np.uint8)
     assert np.array_equal(u8[:, :3], expect_u8) and np.all(u8[:, 3] == 0)
     m.close()
+
+
+def test_legacy_cone_filter_estimator(pm, oracle):
+    """the fixed-radius cone-filter estimate of the legacy file ("photonMappingKernel - Copy.cu":191-208,
+    sqRadius 0.7, exposure 50) over the k nearest surface photons within the radius; against oracle/knn_oracle.c."""
+    import torch
+    from pmb200 import dist as pd
+    n, k, sq_radius, exposure = 30000, 100, 0.7, 50.0
+    osc = oracle.default_scene()
+    m = pm.PhotonMapper(n_photons=n)
+    m.set_scene(copy_scene(pm.Scene, osc))
+    m.init_random_numbers()
+    m.set_record_capacity(16 * n)
+    m.clear_map()
+    m.trace(0.0, media=False, records=True, no_map=True)
+    m.knn_build(0)
+    pos_p, pow_p, dir_p, cnt = m.record_buffers(0)
+    pos = pd.device_tensor(pos_p, cnt * 4, "<f4").cpu().numpy().reshape(cnt, 4).copy()
+    pw = pd.device_tensor(pow_p, cnt * 4, "<f4").cpu().numpy().reshape(cnt, 4).copy()
+    dr = pd.device_tensor(dir_p, cnt * 4, "<f4").cpu().numpy().reshape(cnt, 4).copy()
+    meta = pos[:, 3].copy().view(np.uint32)
+    typ = ((meta >> 5) & 3).astype(np.int32) - 1
+    wid = ((meta >> 7) & 15).astype(np.int32) - 1
+    opos = pos.copy(); opos[typ != 1, :3] = np.nan
+    rng = np.random.default_rng(12)
+    inside = (typ == 1) & (np.abs(pos[:, 0]) <= 1.6) & (np.abs(pos[:, 1]) <= 1.6) & (pos[:, 2] >= 0) & (pos[:, 2] <= 6.1)
+    pick = rng.choice(np.flatnonzero(inside), 500, replace=False)
+    q = pos[pick].copy()
+    q[:, 3] = wid[pick].astype(np.float32)          # query = a point on that wall + its wall id
+    q[:10, 3] = 7.0                                   # unknown wall id -> zero
+    tq = torch.from_numpy(q).cuda()
+    rgb = torch.empty((500, 4), dtype=torch.float32, device="cuda")
+    m.knn_radiance_cone(tq, 500, k, sq_radius, exposure, rgb)
+    m.sync()
+    idx, d2, c = oracle.knn_bruteforce(opos, q, k, sq_radius)
+    normals = np.zeros((5, 3), np.float32)
+    for i in range(5):
+        normals[i, int(osc.planes[i][0])] = -1.0 if osc.planes[i][1] > 0 else 1.0
+    want = oracle.knn_cone_estimate(pos, dr, pw, idx, d2, c, q[:, 3].astype(np.int32), normals, exposure)
+    got = rgb.cpu().numpy()
+    assert np.array_equal(got[:, 3], want[:, 3])
+    assert np.all(got[:10] == 0)
+    assert np.abs(got[:, :3] - want[:, :3]).max() <= 2e-5 * np.abs(want[:, :3]).max()
+    assert want[10:, 3].mean() > 10
+    m.close()
