@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpmb200.so")
+LIB_PATH = os.environ.get("PMB200_LIB") or os.path.join(_HERE, "libpmb200.so")   # PMB200_LIB: development override
 
 PM_TRACE_MEDIA, PM_TRACE_RECORDS, PM_TRACE_NO_MAP = 1, 2, 4
 GRID_N = 32

@@ -46,6 +46,7 @@ struct pm_context {
   int64_t vrec_cap = 0, vrec_count = 0;
 
   KnnMap knn[2];                   // Mode B maps: surface, volume
+  unsigned long long *d_work = nullptr;   // work counter of the Mode B renderer
   int knn_curve = PM_CURVE_HILBERT;
 
   uchar4 *d_fb_u8 = nullptr;
@@ -213,7 +214,7 @@ int pm_destroy(pm_context *c) {
   cudaFree(c->d_table); cudaFree(c->d_acc); cudaFree(c->d_grid); cudaFree(c->d_vol); cudaFree(c->d_surf);
   cudaFree(c->d_jump); cudaFree(c->d_rec_pos); cudaFree(c->d_rec_pow); cudaFree(c->d_rec_dir); cudaFree(c->d_rec_count);
   cudaFree(c->d_fb_u8); cudaFree(c->d_fb_f32); cudaFree(c->d_vrec_pos); cudaFree(c->d_vrec_pow);
-  knn_free(c->knn[0]); knn_free(c->knn[1]);
+  knn_free(c->knn[0]); knn_free(c->knn[1]); cudaFree(c->d_work);
   for (auto &sp : c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
   delete c;
   return PM_OK;
@@ -615,7 +616,8 @@ int pm_render_knn_rows(pm_context *c, float t, bool media, int width, int height
   c->dsc = make_device_scene(c->scene, t);
   {
     SpanGuard g(c, K_KNN_RENDER);
-    CK(c, knn_render(c->dsc, c->knn[0], c->knn[1], k, max_r2, w_surface, w_volume, width, height, y0, y1, y_step, media, (uchar4 *)dev_rgba,
+    if (!c->d_work) CK(c, cudaMalloc(&c->d_work, sizeof(unsigned long long)));
+    CK(c, knn_render(c->dsc, c->knn[0], c->knn[1], k, max_r2, w_surface, w_volume, width, height, y0, y1, y_step, media, c->d_work, (uchar4 *)dev_rgba,
                      (float4 *)dev_rgbf, c->num_sms, c->stream));
   }
   if (y1 > y0) c->launches++;

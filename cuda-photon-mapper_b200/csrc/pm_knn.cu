@@ -45,14 +45,29 @@ __device__ __forceinline__ uint32_t quant10(float p, float lo, float inv_extent)
   if (f >= 1023.0f) return 1023u;
   return (uint32_t)f;
 }
+// Cell of a position: 10 bits per axis over the map's world box; positions outside it get bit 30 and a coarse 192-unit box
+// (see oracle/knn_oracle.c cell_of: clamping them into the border cells gives the border leaves boxes that reach far
+// outside the scene, and queries near the border then visit thousands of leaves).
+__device__ __forceinline__ bool inside_axis(float p, float lo, float inv_extent) {
+  float f = (p - lo) * inv_extent * 1024.0f;
+  return f >= -0.5f && f <= 1024.5f;
+}
+__device__ __forceinline__ uint32_t cell_of(float x, float y, float z, uint32_t &X0, uint32_t &X1, uint32_t &X2) {
+  if (inside_axis(x, -1.5f, 1.0f / 3.0f) && inside_axis(y, -1.5f, 1.0f / 3.0f) && inside_axis(z, 0.0f, 1.0f / 6.0f)) {
+    X0 = quant10(x, -1.5f, 1.0f / 3.0f); X1 = quant10(y, -1.5f, 1.0f / 3.0f); X2 = quant10(z, 0.0f, 1.0f / 6.0f);
+    return 0u;
+  }
+  X0 = quant10(x, -96.0f, 1.0f / 192.0f); X1 = quant10(y, -96.0f, 1.0f / 192.0f); X2 = quant10(z, -93.0f, 1.0f / 192.0f);
+  return 1u << 30;
+}
 __device__ __forceinline__ uint32_t morton30(float x, float y, float z) {
-  return spread10(quant10(x, -1.5f, 1.0f / 3.0f)) | (spread10(quant10(y, -1.5f, 1.0f / 3.0f)) << 1) |
-         (spread10(quant10(z, 0.0f, 1.0f / 6.0f)) << 2);
+  uint32_t X0, X1, X2, flag = cell_of(x, y, z, X0, X1, X2);
+  return flag | spread10(X0) | (spread10(X1) << 1) | (spread10(X2) << 2);
 }
 
 // the same cell along the 3-D Hilbert curve (Skilling's transpose algorithm); identical integer code in oracle/knn_oracle.c
 __device__ __forceinline__ uint32_t hilbert30(float x, float y, float z) {
-  uint32_t X0 = quant10(x, -1.5f, 1.0f / 3.0f), X1 = quant10(y, -1.5f, 1.0f / 3.0f), X2 = quant10(z, 0.0f, 1.0f / 6.0f);
+  uint32_t X0, X1, X2, flag = cell_of(x, y, z, X0, X1, X2);
 #pragma unroll
   for (uint32_t Q = 1u << 9; Q > 1; Q >>= 1) {
     const uint32_t P = Q - 1;
@@ -65,7 +80,7 @@ __device__ __forceinline__ uint32_t hilbert30(float x, float y, float z) {
 #pragma unroll
   for (uint32_t Q = 1u << 9; Q > 1; Q >>= 1) if (X2 & Q) t ^= Q - 1;
   X0 ^= t; X1 ^= t; X2 ^= t;
-  return (spread10(X0) << 2) | (spread10(X1) << 1) | spread10(X2);
+  return flag | (spread10(X0) << 2) | (spread10(X1) << 1) | spread10(X2);
 }
 
 // filter: 0 = every row is a point; 1 = keep only wall hits (meta type == 1) of a record buffer
@@ -555,7 +570,8 @@ __global__ void __launch_bounds__(kQueryThreads) knn_render_kernel(const __grid_
                                                                    const __grid_constant__ TreeView tvv, const float4 *__restrict__ pow_s,
                                                                    const float4 *__restrict__ pow_v, int k, float max_r2, float w_surf,
                                                                    float w_vol, int width, int height, int y0, int y1, int y_step, int media,
-                                                                   uchar4 *__restrict__ rgba, float4 *__restrict__ rgbf) {
+                                                                   uchar4 *__restrict__ rgba, float4 *__restrict__ rgbf,
+                                                                   unsigned long long *__restrict__ work_counter) {
   extern __shared__ __align__(128) unsigned char dyn[];
   float *sbox_s = (float *)dyn, *sbox_v = sbox_s + kMaxStagedFloats;
   u64 *pend_all = (u64 *)(sbox_v + kMaxStagedFloats);
@@ -564,10 +580,44 @@ __global__ void __launch_bounds__(kQueryThreads) knn_render_kernel(const __grid_
   if (media) stage_top_levels(tvv, sbox_v, bars + 1);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   u64 *pend = pend_all + w * 64;
-  const long long warps = (long long)gridDim.x * (kQueryThreads / 32);
-  const long long nrows = (y1 - y0 + y_step - 1) / y_step, npix = nrows * width;   // rows y0, y0+y_step, ... < y1
-  for (long long j = (long long)blockIdx.x * (kQueryThreads / 32) + w; j < npix; j += warps) {
-    int px = (int)(j % width), py = y0 + (int)(j / width) * y_step;
+  const int nrows = (y1 - y0 + y_step - 1) / y_step;   // rows y0, y0+y_step, ... < y1
+  const float inf = cuda::std::numeric_limits<float>::infinity();
+  // Work decomposition: the frame is cut into units of kRun consecutive pixels of one row; units are numbered so that
+  // eight consecutive ids are vertically adjacent (a tile of 8 rows x kRun columns), and every warp fetches its next unit
+  // from a global counter.  Warps that run at the same time therefore work on neighbouring pixels (shared leaves in
+  // L1/L2), no warp is stuck with a long static list of expensive pixels (the gather cost varies by orders of magnitude
+  // over the image: a static split left the SMs 78 % idle), and
+  // a warp's consecutive pixels are neighbours, so the k-th distance found for one pixel can bound the search of the next
+  // (same wall / same march step): searching within 1.2x the neighbour's radius first skips the phase in which every
+  // candidate passes.  If fewer than k photons lie within the hinted radius the search is repeated without it, so the
+  // result is exact either way.  Hints: lane i holds the hint of march step i, lane 10 the wall hint.
+  constexpr int kRun = 16, kRows = kQueryThreads / 32;
+  const int tiles_x = (width + kRun - 1) / kRun, tiles_y = (nrows + kRows - 1) / kRows;
+  auto search = [&](const TreeView &tv, const float *sbox, float qx, float qy, float qz, float hint_r2, TopK<KL> &top) -> float {
+    float lim = fminf(max_r2, hint_r2 * 1.44f);
+    KSTAT(6, lim < max_r2 ? 1 : 0);
+    u64 kth;
+    for (;;) {
+      knn_search<KL>(tv, sbox, pend, qx, qy, qz, k, lim, lane, top);
+      kth = top.at(k - 1);
+      if (kth != kMaxKey || !(lim < max_r2)) break;
+      KSTAT(5, 1);
+      lim = max_r2;                            // the hint was too tight (or the map holds fewer than k photons): unbounded retry
+    }
+    return kth == kMaxKey ? inf : __uint_as_float((uint32_t)(kth >> 32));
+  };
+  const long long units = (long long)tiles_x * tiles_y * kRows;
+  for (;;) {
+   long long u = 0;
+   if (lane == 0) u = (long long)atomicAdd(work_counter, 1ull);
+   u = __shfl_sync(0xffffffffu, u, 0);
+   if (u >= units) break;
+   const long long tile = u / kRows;
+   const int row = (int)(tile / tiles_x) * kRows + (int)(u % kRows), x0 = (int)(tile % tiles_x) * kRun;
+   if (row >= nrows) continue;
+   float hint = inf;
+   for (int px = x0; px < width && px < x0 + kRun; px++) {
+    const int py = y0 + row * y_step;
     const long long pix = (long long)py * width + px;
     float x = (float)px + sc.cam_ox, y = (float)py + sc.cam_oy;
     v3 rgb = V(0.0f, 0.0f, 0.0f);
@@ -579,28 +629,34 @@ __global__ void __launch_bounds__(kQueryThreads) knn_render_kernel(const __grid_
 #pragma unroll 1
       for (int i = 0; i < 10; i++) {
         prev = add(mul(ray, 0.6f), prev);
-        knn_search<KL>(tvv, sbox_v, pend, prev.x, prev.y, prev.z, k, max_r2, lane, top);
+        float r2 = search(tvv, sbox_v, prev.x, prev.y, prev.z, __shfl_sync(0xffffffffu, hint, i), top);
+        if (lane == i) hint = r2;
         float4 e = knn_radiance<KL>(top, k, pow_v, 1, lane);
         rgb = add(rgb, mul(V(e.x, e.y, e.z), w_vol));
       }
     }
     Hit h; h.hit = 0; h.type = 0; h.idx = 0; h.dist = -1.0f;
     raytrace(sc, ray, origin, h);
+    bool wall = false;
     if (h.hit) {
       v3 P = mul(ray, h.dist);
       if (h.type == 0 && h.idx == 1) follow_specular(sc, ray, origin, h, P, 1);
       else if (h.type == 0 && h.idx == 0) follow_specular(sc, ray, origin, h, P, 0);
       if (h.hit && h.type == 1) {   // warp-uniform: every lane traced the same ray
-        knn_search<KL>(tvs, sbox_s, pend, P.x, P.y, P.z, k, max_r2, lane, top);
+        wall = true;
+        float r2 = search(tvs, sbox_s, P.x, P.y, P.z, __shfl_sync(0xffffffffu, hint, 10), top);
+        if (lane == 10) hint = r2;
         float4 e = knn_radiance<KL>(top, k, pow_s, 0, lane);
         v3 c = mul(V(e.x, e.y, e.z), w_surf);
         rgb = media ? add(rgb, mul(c, 0.15f)) : add(rgb, c);
       }
     }
+    if (!wall && lane == 10) hint = inf;
     if (lane == 0) {
       if (rgbf) rgbf[pix] = make_float4(rgb.x, rgb.y, rgb.z, 1.0f);
       if (rgba) rgba[pix] = make_uchar4(quantise_u8(rgb.x), quantise_u8(rgb.y), quantise_u8(rgb.z), 0);
     }
+   }
   }
 }
 
@@ -716,19 +772,20 @@ cudaError_t knn_query(const KnnMap &m, const float4 *queries, long long nq, int 
 }
 
 cudaError_t knn_render(const DeviceScene &sc, const KnnMap &ms, const KnnMap &mv, int k, float max_r2, float w_surf, float w_vol, int width,
-                       int height, int y0, int y1, int y_step, bool media, uchar4 *rgba, float4 *rgbf, int num_sms, cudaStream_t st) {
+                       int height, int y0, int y1, int y_step, bool media, unsigned long long *work_counter, uchar4 *rgba, float4 *rgbf, int num_sms, cudaStream_t st) {
   if (y_step < 1) y_step = 1;
   long long n = (long long)((y1 - y0 + y_step - 1) / y_step) * width;
   if (n <= 0) return cudaSuccess;
   TreeView tvs = make_view(ms), tvv = make_view(mv);
-  long long want = (n + kQueryThreads / 32 - 1) / (kQueryThreads / 32), cap = (long long)num_sms * 16;
+  long long want = (long long)((width + 15) / 16) * (((y1 - y0 + y_step - 1) / y_step + 7) / 8), cap = (long long)num_sms * 16;   // 8x16-pixel tiles
   unsigned grid = (unsigned)(want < cap ? want : cap);
   size_t smem = sizeof(float) * 2 * kMaxStagedFloats + sizeof(u64) * (kQueryThreads / 32) * 64 + 2 * sizeof(unsigned long long);
+  KCK(cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), st));
 #define LAUNCH_RENDER(KL)                                                                                                  \
   do {                                                                                                                     \
     KCK(cudaFuncSetAttribute(knn_render_kernel<KL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
     knn_render_kernel<KL><<<grid, kQueryThreads, smem, st>>>(sc, tvs, tvv, ms.power, mv.power, k, max_r2, w_surf, w_vol, width, height, y0, \
-                                                              y1, y_step, media ? 1 : 0, rgba, rgbf);                               \
+                                                              y1, y_step, media ? 1 : 0, rgba, rgbf, work_counter);                               \
   } while (0)
   if (k <= 32) LAUNCH_RENDER(1); else if (k <= 64) LAUNCH_RENDER(2); else LAUNCH_RENDER(4);
 #undef LAUNCH_RENDER

@@ -33,16 +33,38 @@ static inline uint32_t quant10(float p, float lo, float inv_extent) {
   if (f >= 1023.0f) return 1023u;
   return (uint32_t)f;
 }
-/* world box of the photon map: x,y in [-1.5,1.5], z in [0,6]; positions outside are clamped to the border cells */
-uint32_t pmo_morton30(const float p[3]) {
-  uint32_t x = quant10(p[0], -1.5f, 1.0f / 3.0f), y = quant10(p[1], -1.5f, 1.0f / 3.0f), z = quant10(p[2], 0.0f, 1.0f / 6.0f);
-  return spread10(x) | (spread10(y) << 1) | (spread10(z) << 2);
+/* Sort keys.  Cell = 10 bits per axis over the photon map's world box (x,y in [-1.5,1.5], z in [0,6], PMK:21-23).
+ * Photons OUTSIDE that box (the reference's shadow photons land on the infinite wall planes far outside it, PMK:1185-1196)
+ * get bit 30 set and are keyed over a coarse 192-unit box instead: if they were clamped into the border cells they would
+ * share leaves with the in-box photons next to the border, and every such leaf would get a box reaching far outside the
+ * scene (measured: a heavy tail of queries visiting thousands of leaves). */
+static inline int inside_axis(float p, float lo, float inv_extent) {
+  float f = (p - lo) * inv_extent * 1024.0f;
+  return f >= -0.5f && f <= 1024.5f;
 }
-/* The same 10-bit cell coordinates along the 3-D Hilbert curve (Skilling's transpose algorithm, AIP Conf. Proc. 707,
- * 2004): the sort key the product uses by default.  Runs of consecutive points of a Z-curve straddle octant boundaries,
- * so the bounding boxes of fixed-size runs (the tree's leaves and nodes) are loose; Hilbert runs are always connected. */
+static inline int inside_box(const float p[3]) {
+  return inside_axis(p[0], -1.5f, 1.0f / 3.0f) && inside_axis(p[1], -1.5f, 1.0f / 3.0f) && inside_axis(p[2], 0.0f, 1.0f / 6.0f);
+}
+static inline void cell_of(const float p[3], uint32_t X[3], uint32_t *flag) {
+  if (inside_box(p)) {
+    X[0] = quant10(p[0], -1.5f, 1.0f / 3.0f); X[1] = quant10(p[1], -1.5f, 1.0f / 3.0f); X[2] = quant10(p[2], 0.0f, 1.0f / 6.0f);
+    *flag = 0u;
+  } else {
+    X[0] = quant10(p[0], -96.0f, 1.0f / 192.0f); X[1] = quant10(p[1], -96.0f, 1.0f / 192.0f); X[2] = quant10(p[2], -93.0f, 1.0f / 192.0f);
+    *flag = 1u << 30;
+  }
+}
+uint32_t pmo_morton30(const float p[3]) {
+  uint32_t X[3], flag;
+  cell_of(p, X, &flag);
+  return flag | spread10(X[0]) | (spread10(X[1]) << 1) | (spread10(X[2]) << 2);
+}
+/* The same cell along the 3-D Hilbert curve (Skilling's transpose algorithm, AIP Conf. Proc. 707, 2004): the sort key the
+ * product uses by default.  Runs of consecutive points of a Z-curve straddle octant boundaries, so the bounding boxes of
+ * fixed-size runs (the tree's leaves and nodes) are loose; Hilbert runs are always connected. */
 uint32_t pmo_hilbert30(const float p[3]) {
-  uint32_t X[3] = {quant10(p[0], -1.5f, 1.0f / 3.0f), quant10(p[1], -1.5f, 1.0f / 3.0f), quant10(p[2], 0.0f, 1.0f / 6.0f)};
+  uint32_t X[3], flag;
+  cell_of(p, X, &flag);
   const uint32_t M = 1u << 9;
   for (uint32_t Q = M; Q > 1; Q >>= 1) {
     uint32_t P = Q - 1;
@@ -55,7 +77,7 @@ uint32_t pmo_hilbert30(const float p[3]) {
   uint32_t t = 0;
   for (uint32_t Q = M; Q > 1; Q >>= 1) if (X[2] & Q) t ^= Q - 1;
   X[0] ^= t; X[1] ^= t; X[2] ^= t;
-  return (spread10(X[0]) << 2) | (spread10(X[1]) << 1) | spread10(X[2]);   /* X[0] holds the most significant bit of each triple */
+  return flag | (spread10(X[0]) << 2) | (spread10(X[1]) << 1) | spread10(X[2]);   /* X[0] holds the most significant bit of each triple */
 }
 void pmo_morton30_many(const float *pos4, long n, uint32_t *keys) {
   for (long i = 0; i < n; i++) keys[i] = pmo_morton30(pos4 + 4 * i);
