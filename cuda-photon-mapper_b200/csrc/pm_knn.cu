@@ -45,9 +45,9 @@ __device__ __forceinline__ uint32_t quant10(float p, float lo, float inv_extent)
   if (f >= 1023.0f) return 1023u;
   return (uint32_t)f;
 }
-// Cell of a position: 10 bits per axis over the map's world box; positions outside it get bit 30 and a coarse 192-unit box
-// (see oracle/knn_oracle.c cell_of: clamping them into the border cells gives the border leaves boxes that reach far
-// outside the scene, and queries near the border then visit thousands of leaves).
+// Cell of a position: 10 bits per axis over one of three concentric boxes, tier number in key bits 30-31 (world box,
+// 4x box, 192-unit box) -- identical to oracle/knn_oracle.c cell_of, which explains why out-of-box photons are neither
+// clamped into the border cells nor all lumped into one coarse tier.
 __device__ __forceinline__ bool inside_axis(float p, float lo, float inv_extent) {
   float f = (p - lo) * inv_extent * 1024.0f;
   return f >= -0.5f && f <= 1024.5f;
@@ -57,8 +57,12 @@ __device__ __forceinline__ uint32_t cell_of(float x, float y, float z, uint32_t 
     X0 = quant10(x, -1.5f, 1.0f / 3.0f); X1 = quant10(y, -1.5f, 1.0f / 3.0f); X2 = quant10(z, 0.0f, 1.0f / 6.0f);
     return 0u;
   }
+  if (inside_axis(x, -6.0f, 1.0f / 12.0f) && inside_axis(y, -6.0f, 1.0f / 12.0f) && inside_axis(z, -9.0f, 1.0f / 24.0f)) {
+    X0 = quant10(x, -6.0f, 1.0f / 12.0f); X1 = quant10(y, -6.0f, 1.0f / 12.0f); X2 = quant10(z, -9.0f, 1.0f / 24.0f);
+    return 1u << 30;
+  }
   X0 = quant10(x, -96.0f, 1.0f / 192.0f); X1 = quant10(y, -96.0f, 1.0f / 192.0f); X2 = quant10(z, -93.0f, 1.0f / 192.0f);
-  return 1u << 30;
+  return 2u << 30;
 }
 __device__ __forceinline__ uint32_t morton30(float x, float y, float z) {
   uint32_t X0, X1, X2, flag = cell_of(x, y, z, X0, X1, X2);
@@ -619,6 +623,9 @@ __global__ void __launch_bounds__(kQueryThreads) knn_render_kernel(const __grid_
    for (int px = x0; px < width && px < x0 + kRun; px++) {
     const int py = y0 + row * y_step;
     const long long pix = (long long)py * width + px;
+#ifdef PM_KNN_STATS
+    long long t_begin = clock64();
+#endif
     float x = (float)px + sc.cam_ox, y = (float)py + sc.cam_oy;
     v3 rgb = V(0.0f, 0.0f, 0.0f);
     const v3 origin = V(0.0f, 0.0f, 0.0f);
@@ -653,7 +660,11 @@ __global__ void __launch_bounds__(kQueryThreads) knn_render_kernel(const __grid_
     }
     if (!wall && lane == 10) hint = inf;
     if (lane == 0) {
+#ifdef PM_KNN_STATS
+      if (rgbf) rgbf[pix] = make_float4(rgb.x, rgb.y, rgb.z, (float)(clock64() - t_begin));   // debug: cycles per pixel
+#else
       if (rgbf) rgbf[pix] = make_float4(rgb.x, rgb.y, rgb.z, 1.0f);
+#endif
       if (rgba) rgba[pix] = make_uchar4(quantise_u8(rgb.x), quantise_u8(rgb.y), quantise_u8(rgb.z), 0);
     }
    }

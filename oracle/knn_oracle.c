@@ -33,25 +33,30 @@ static inline uint32_t quant10(float p, float lo, float inv_extent) {
   if (f >= 1023.0f) return 1023u;
   return (uint32_t)f;
 }
-/* Sort keys.  Cell = 10 bits per axis over the photon map's world box (x,y in [-1.5,1.5], z in [0,6], PMK:21-23).
- * Photons OUTSIDE that box (the reference's shadow photons land on the infinite wall planes far outside it, PMK:1185-1196)
- * get bit 30 set and are keyed over a coarse 192-unit box instead: if they were clamped into the border cells they would
- * share leaves with the in-box photons next to the border, and every such leaf would get a box reaching far outside the
- * scene (measured: a heavy tail of queries visiting thousands of leaves). */
+/* Sort keys.  Cell = 10 bits per axis over a box, in three tiers (tier number in key bits 30-31):
+ *   tier 0  the photon map's world box (x,y in [-1.5,1.5], z in [0,6], PMK:21-23);
+ *   tier 1  photons outside it but inside the 4x larger concentric box (x,y in [-6,6], z in [-9,15]): the reference's
+ *           shadow photons land on the infinite wall planes outside the box (PMK:1185-1196) and its volume photons up to
+ *           three units from the light, i.e. above the ceiling;
+ *   tier 2  everything farther, over a coarse 192-unit box.
+ * Clamping outside photons into the border cells of tier 0 (first version) made them share leaves with the in-box photons
+ * next to the border, giving those leaves boxes that reach far outside the scene; keying ALL of them over the coarse box
+ * (second version) put the millions of volume photons above the ceiling into a handful of cells, i.e. into leaves of
+ * random points whose boxes all overlap: queries there scanned the whole population (58 ms for one query). */
 static inline int inside_axis(float p, float lo, float inv_extent) {
   float f = (p - lo) * inv_extent * 1024.0f;
   return f >= -0.5f && f <= 1024.5f;
 }
-static inline int inside_box(const float p[3]) {
-  return inside_axis(p[0], -1.5f, 1.0f / 3.0f) && inside_axis(p[1], -1.5f, 1.0f / 3.0f) && inside_axis(p[2], 0.0f, 1.0f / 6.0f);
-}
 static inline void cell_of(const float p[3], uint32_t X[3], uint32_t *flag) {
-  if (inside_box(p)) {
+  if (inside_axis(p[0], -1.5f, 1.0f / 3.0f) && inside_axis(p[1], -1.5f, 1.0f / 3.0f) && inside_axis(p[2], 0.0f, 1.0f / 6.0f)) {
     X[0] = quant10(p[0], -1.5f, 1.0f / 3.0f); X[1] = quant10(p[1], -1.5f, 1.0f / 3.0f); X[2] = quant10(p[2], 0.0f, 1.0f / 6.0f);
     *flag = 0u;
+  } else if (inside_axis(p[0], -6.0f, 1.0f / 12.0f) && inside_axis(p[1], -6.0f, 1.0f / 12.0f) && inside_axis(p[2], -9.0f, 1.0f / 24.0f)) {
+    X[0] = quant10(p[0], -6.0f, 1.0f / 12.0f); X[1] = quant10(p[1], -6.0f, 1.0f / 12.0f); X[2] = quant10(p[2], -9.0f, 1.0f / 24.0f);
+    *flag = 1u << 30;
   } else {
     X[0] = quant10(p[0], -96.0f, 1.0f / 192.0f); X[1] = quant10(p[1], -96.0f, 1.0f / 192.0f); X[2] = quant10(p[2], -93.0f, 1.0f / 192.0f);
-    *flag = 1u << 30;
+    *flag = 2u << 30;
   }
 }
 uint32_t pmo_morton30(const float p[3]) {
