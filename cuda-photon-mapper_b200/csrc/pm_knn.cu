@@ -8,7 +8,7 @@
 //   keys[n']        30-bit Morton code of the position clamped to the map's world box (10 bits/axis, x lowest), n' = n
 //                   rounded up to the sort tile; records that are not wall hits and the padding get key 0xFFFFFFFF
 //   radix sort      4 passes x 8-bit digits over (key, index) pairs: per-tile histogram -> exclusive scan of the
-//                   digit-major histogram table -> stable scatter (ranks from warp match_any + per-warp digit counters)
+//                   digit-major histogram table -> stable scatter (ranks from warp ballots + per-warp digit counters, tile staged in shared memory)
 //   spos[n]         float4 (x, y, z, bits(original record index)) in sorted order: a leaf = 32 consecutive rows = one
 //                   coalesced 512-byte load by one warp
 //   tree            implicit and 32-wide: level 0 = leaves, level l+1 groups 32 entities of level l; only axis-aligned
@@ -187,7 +187,9 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(uint32_t *__re
 __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                                                                      uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
                                                                      int shift, uint32_t nb, const uint32_t *__restrict__ gbase) {
-  __shared__ uint32_t wh[kSortThreads / 32][256];   // per-warp digit counters, then per-warp output offsets
+  __shared__ uint32_t wh[kSortThreads / 32][256];   // per-warp digit counters, then per-warp offsets inside the staged tile
+  __shared__ uint2 stage[kSortTile];                // the tile, sorted by digit (stable), before it is written out
+  __shared__ uint32_t gofs[256], scan_sh[32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < (kSortThreads / 32) * 256; i += kSortThreads) (&wh[0][0])[i] = 0;
   __syncthreads();
@@ -199,7 +201,9 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint3
 #pragma unroll
   for (int r = 0; r < kSortRows; r++) {
     uint32_t d = (key[r] >> shift) & 255u;
-    unsigned peers = __match_any_sync(0xffffffffu, d);
+    unsigned peers = 0xffffffffu;   // lanes with the same digit, from eight ballots (MATCH.ANY is far slower than VOTE here)
+#pragma unroll
+    for (int b = 0; b < 8; b++) { unsigned bal = __ballot_sync(0xffffffffu, (d >> b) & 1u); peers &= ((d >> b) & 1u) ? bal : ~bal; }
     int leader = __ffs(peers) - 1;
     uint32_t old = 0;
     if (lane == leader) { old = wh[w][d]; wh[w][d] = old + __popc(peers); }
@@ -208,8 +212,13 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint3
     __syncwarp();
   }
   __syncthreads();
-  {   // thread d: exclusive scan over the warps, starting at this tile's global offset for digit d
-    uint32_t run = gbase[(size_t)threadIdx.x * nb + blockIdx.x];
+  {   // thread d: where digit d starts inside the tile (scan over digits) and inside each warp's share of it (scan over warps)
+    uint32_t tot = 0;
+#pragma unroll
+    for (int i = 0; i < kSortThreads / 32; i++) tot += wh[i][threadIdx.x];
+    uint32_t start = block_exclusive_scan(tot, nullptr, scan_sh);
+    gofs[threadIdx.x] = gbase[(size_t)threadIdx.x * nb + blockIdx.x] - start;   // global position = gofs[d] + position in the staged tile
+    uint32_t run = start;
 #pragma unroll
     for (int i = 0; i < kSortThreads / 32; i++) { uint32_t t = wh[i][threadIdx.x]; wh[i][threadIdx.x] = run; run += t; }
   }
@@ -217,19 +226,40 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint3
 #pragma unroll
   for (int r = 0; r < kSortRows; r++) {
     uint32_t d = (key[r] >> shift) & 255u;
-    uint32_t p = wh[w][d] + rank[r];
-    keys_out[p] = key[r]; vals_out[p] = val[r];
+    stage[wh[w][d] + rank[r]] = make_uint2(key[r], val[r]);
+  }
+  __syncthreads();
+  // write-out: consecutive threads take consecutive staged elements, i.e. consecutive addresses within a digit run, instead
+  // of 32 scattered 4-byte stores per warp instruction (the unstaged version was bound by L2 sector writes)
+#pragma unroll 4
+  for (int i = threadIdx.x; i < kSortTile; i += kSortThreads) {
+    uint2 kv = stage[i];
+    uint32_t p = gofs[(kv.x >> shift) & 255u] + (uint32_t)i;
+    keys_out[p] = kv.x; vals_out[p] = kv.y;
   }
 }
 
-// sorted rows: (x, y, z, bits(original index))
+// sorted rows: (x, y, z, bits(original index)), and -- a warp's 32 rows being exactly one leaf -- the leaf boxes
+// (six arrays of length p_out; leaves >= n_out, the padding, stay empty)
+__device__ __forceinline__ float warp_min(float v);
+__device__ __forceinline__ float warp_max(float v);
 __global__ void __launch_bounds__(256) permute_kernel(const float4 *__restrict__ pos, const uint32_t *__restrict__ vals, long long n,
-                                                      float4 *__restrict__ spos) {
+                                                      float4 *__restrict__ spos, long long n_out, long long p_out, float *__restrict__ boxes) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  uint32_t v = vals[i];
-  float4 p = pos[v];
-  spos[i] = make_float4(p.x, p.y, p.z, __uint_as_float(v));
+  long long e = i >> 5;
+  if (e >= p_out) return;
+  const float inf = cuda::std::numeric_limits<float>::infinity();
+  float lx = inf, ly = inf, lz = inf, hx = -inf, hy = -inf, hz = -inf;
+  if (i < n) {
+    uint32_t v = vals[i];
+    float4 p = pos[v];
+    spos[i] = make_float4(p.x, p.y, p.z, __uint_as_float(v));
+    lx = hx = p.x; ly = hy = p.y; lz = hz = p.z;
+  }
+  lx = warp_min(lx); ly = warp_min(ly); lz = warp_min(lz); hx = warp_max(hx); hy = warp_max(hy); hz = warp_max(hz);
+  if ((threadIdx.x & 31) == 0) {
+    boxes[e] = lx; boxes[p_out + e] = ly; boxes[2 * p_out + e] = lz; boxes[3 * p_out + e] = hx; boxes[4 * p_out + e] = hy; boxes[5 * p_out + e] = hz;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -244,19 +274,6 @@ __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
-}
-// level 0: boxes of the leaves (32 sorted photons each).  out = six arrays of length p_out (entries >= n_out stay empty)
-__global__ void __launch_bounds__(256) leaf_box_kernel(const float4 *__restrict__ spos, long long n, long long n_out, long long p_out,
-                                                       float *__restrict__ out) {
-  long long e = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  if (e >= p_out) return;
-  const float inf = cuda::std::numeric_limits<float>::infinity();
-  float lx = inf, ly = inf, lz = inf, hx = -inf, hy = -inf, hz = -inf;
-  long long i = e * 32 + lane;
-  if (e < n_out && i < n) { float4 p = spos[i]; lx = hx = p.x; ly = hy = p.y; lz = hz = p.z; }
-  lx = warp_min(lx); ly = warp_min(ly); lz = warp_min(lz); hx = warp_max(hx); hy = warp_max(hy); hz = warp_max(hz);
-  if (lane == 0) { out[e] = lx; out[p_out + e] = ly; out[2 * p_out + e] = lz; out[3 * p_out + e] = hx; out[4 * p_out + e] = hy; out[5 * p_out + e] = hz; }
 }
 __global__ void __launch_bounds__(256) node_box_kernel(const float *__restrict__ in, long long n_in, long long p_in, long long n_out,
                                                        long long p_out, float *__restrict__ out) {
@@ -721,8 +738,6 @@ cudaError_t knn_build(KnnMap &m, const float4 *pos, const float4 *power, long lo
   KCK(cudaStreamSynchronize(st));   // the number of kept points sizes the tree
   m.n = (long long)nv; m.n_sorted_pad = n_pad;
   if (m.n == 0) return cudaSuccess;
-  permute_kernel<<<(unsigned)((m.n + 255) / 256), 256, 0, st>>>(pos, m.vals[cur], m.n, m.spos);
-  (*launches)++;
   // level geometry
   long long cnt = (m.n + 31) / 32; int L = 0; size_t total = 0;
   for (;;) {
@@ -733,7 +748,7 @@ cudaError_t knn_build(KnnMap &m, const float4 *pos, const float4 *power, long lo
   }
   m.levels = L;
   KCK(ensure((void **)&m.boxes, &m.cap_boxes, sizeof(float) * total));
-  leaf_box_kernel<<<(unsigned)((m.pad[0] * 32 + 255) / 256), 256, 0, st>>>(m.spos, m.n, m.cnt[0], m.pad[0], m.boxes + m.off[0]);
+  permute_kernel<<<(unsigned)((m.pad[0] * 32 + 255) / 256), 256, 0, st>>>(pos, m.vals[cur], m.n, m.spos, m.cnt[0], m.pad[0], m.boxes + m.off[0]);
   (*launches)++;
   for (int l = 1; l < L; l++) {
     node_box_kernel<<<(unsigned)((m.pad[l] * 32 + 255) / 256), 256, 0, st>>>(m.boxes + m.off[l - 1], m.cnt[l - 1], m.pad[l - 1], m.cnt[l],
