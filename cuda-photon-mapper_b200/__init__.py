@@ -58,7 +58,7 @@ def lib():
             "pm_position_objects": (i32, [C.POINTER(Scene), f32, C.POINTER(Scene)]),
             "pm_set_photon_count": (i32, [vp, i64]), "pm_set_photon_range": (i32, [vp, i64, i64]),
             "pm_set_energy_scale": (i32, [vp, f32]),
-            "pm_init_random_table": (i32, [vp]), "pm_set_random_table_host": (i32, [vp, vp, i64]),
+            "pm_init_random_table": (i32, [vp]), "pm_init_random_table_philox": (i32, [vp, C.c_uint64]), "pm_set_random_table_host": (i32, [vp, vp, i64]),
             "pm_get_random_table_host": (i32, [vp, vp, i64]),
             "pm_set_mwc_state": (i32, [vp, u32, u32]), "pm_get_mwc_state": (i32, [vp, C.POINTER(u32), C.POINTER(u32)]),
             "pm_clear_map": (i32, [vp]), "pm_trace": (i32, [vp, f32, C.c_uint]),
@@ -176,6 +176,10 @@ class PhotonMapper:
     def init_random_numbers(self):
         """initRandomNumbers() (simplePBO.cpp:125) == launch_init_random_numbers_kernel on this context."""
         self._ck(self.L.pm_init_random_table(self.h))
+
+    def init_random_numbers_philox(self, seed=0x5EED):
+        """Counter-based table: row i from Philox4x32-10(counter i, key seed)."""
+        self._ck(self.L.pm_init_random_table_philox(self.h, seed))
 
     def set_random_table(self, xyz):
         xyz = np.ascontiguousarray(xyz, np.float32)

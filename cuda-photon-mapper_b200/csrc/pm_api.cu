@@ -319,6 +319,16 @@ int pm_init_random_table(pm_context *c) {
   c->mwc_w = h_mwc_advance(1, c->mwc_w, draws);
   return PM_OK;
 }
+int pm_init_random_table_philox(pm_context *c, uint64_t seed) {
+  ARG(c, c != nullptr, "null context");
+  CK(c, cudaSetDevice(c->device));
+  {
+    SpanGuard g(c, K_MWC_TABLE);
+    CK(c, launch_philox_table(c->d_table, c->n_photons, seed, c->stream));
+  }
+  c->launches++;
+  return PM_OK;
+}
 int pm_set_random_table_host(pm_context *c, const float *xyz, int64_t n) {
   ARG(c, c && xyz, "null argument");
   ARG(c, n == c->n_photons, "table length must equal the photon count");

@@ -35,6 +35,23 @@ __global__ void __launch_bounds__(256) mwc_table_kernel(float4 *__restrict__ tab
   table[i] = make_float4(x, y, z, 0.0f);
 }
 
+// Philox4x32-10 (Random123) table: row i = the reference's randFloat(1.0) mapping of the first three words of
+// philox(counter = (i,0,0,0), key = seed) -- the counter-based alternative to the MWC stream for throughput runs
+__global__ void __launch_bounds__(256) philox_table_kernel(float4 *__restrict__ table, long long n, uint32_t k0, uint32_t k1) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t c0 = (uint32_t)i, c1 = 0u, c2 = 0u, c3 = 0u;
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0, h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+    c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  auto unit = [](uint32_t u) { float rnd = __fdiv_rn((float)((int)u), 65535.0f); rnd = rnd * 2.0f * 1.0f; return rnd - 1.0f; };
+  table[i] = make_float4(unit(c0), unit(c1), unit(c2), 0.0f);
+}
+
 // ------------------------------------------------------------------------------------------------------
 // record sink
 // ------------------------------------------------------------------------------------------------------
@@ -373,6 +390,12 @@ cudaError_t launch_mwc_table(float4 *table, long long n, uint32_t w0, uint32_t z
   if (n <= 0) return cudaSuccess;
   unsigned blocks = (unsigned)((n + 255) / 256);
   mwc_table_kernel<<<blocks, 256, 0, st>>>(table, n, w0, z0, J);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_philox_table(float4 *table, long long n, unsigned long long seed, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  philox_table_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(table, n, (uint32_t)seed, (uint32_t)(seed >> 32));
   return cudaGetLastError();
 }
 

@@ -81,6 +81,9 @@ int  pm_set_energy_scale(pm_context *ctx, float scale);   /* photon map is multi
 
 /* random-direction table T2 (PMK:80) */
 int pm_init_random_table(pm_context *ctx);       /* MWC stream, == launch_init_random_numbers_kernel */
+/* counter-based alternative: row i = Philox4x32-10(counter i, key seed) mapped like randFloat(1.0); the MWC state (medium
+ * draws) is untouched.  The oracle consumes the same table (oracle/pm_oracle.c pmo_philox_table). */
+int pm_init_random_table_philox(pm_context *ctx, uint64_t seed);
 int pm_set_random_table_host(pm_context *ctx, const float *host_xyz, int64_t n);
 int pm_get_random_table_host(pm_context *ctx, float *host_xyz, int64_t n);
 int pm_set_mwc_state(pm_context *ctx, uint32_t w, uint32_t z);   /* where the medium-scatter draws continue from */

@@ -48,6 +48,7 @@ class Oracle:
         L.pmo_rand_float.restype = C.c_float
         L.pmo_rand_float.argtypes = [C.c_void_p, C.c_void_p, C.c_float]
         L.pmo_mwc_table.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.pmo_philox_table.argtypes = [C.c_uint64, C.c_void_p, C.c_int]
         L.pmo_position_objects.argtypes = [C.POINTER(Scene), C.c_float]
         L.pmo_emit.restype = C.c_long
         L.pmo_emit.argtypes = [C.POINTER(Scene), C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_int,
@@ -90,6 +91,16 @@ class Oracle:
         for i in range(n):
             out[i] = self.lib.pmo_mwc_next(C.c_void_p(st.ctypes.data), C.c_void_p(st.ctypes.data + 4))
         return out, (int(st[0]), int(st[1]))
+
+    def philox(self, ctr, key):
+        c = np.array(ctr, np.uint32); k = np.array(key, np.uint32); o = np.zeros(4, np.uint32)
+        self.lib.pmo_philox4x32_10(_p(c), _p(k), _p(o))
+        return o
+
+    def philox_table(self, n, seed=0x5EED):
+        tab = np.zeros((n, 3), np.float32)
+        self.lib.pmo_philox_table(C.c_uint64(seed), _p(tab), n)
+        return tab
 
     # -- stage 1 -----------------------------------------------------------------------------------
     def emit(self, scene, table, n0, n1, t=0.0, media=False, rng=(6548, 316), grid=None, max_records=0,

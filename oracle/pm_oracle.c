@@ -66,6 +66,34 @@ void pmo_mwc_table(uint32_t *w, uint32_t *z, float *xyz, int n) {
     xyz[3 * i + 2] = pmo_rand_float(w, z, 1.0f);
   }
 }
+/* Philox4x32-10 (Salmon et al., SC'11; Random123) -- the counter-based alternative to the reference's MWC table for
+ * throughput runs: row i of the table = randFloat-style mapping of the first three words of
+ * philox(counter = (i, 0, 0, 0), key = (seed_lo, seed_hi)).  Not part of the reference; defined here, mirrored in
+ * csrc/pm_trace.cu, pinned by the Random123 known-answer vectors in tests/test_oracle_golden.py. */
+void pmo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+  for (int r = 0; r < 10; r++) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+static float unit_from_u32(uint32_t u) {   /* the reference's randFloat(1.0) mapping of a raw draw, PMK:1039-1052 */
+  float rnd = (float)((int32_t)u) / (float)65535;
+  rnd = rnd * 2 * 1.0f;
+  return rnd - 1.0f;
+}
+void pmo_philox_table(uint64_t seed, float *xyz, int n) {
+  uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+  for (int i = 0; i < n; i++) {
+    uint32_t ctr[4] = {(uint32_t)i, 0u, 0u, 0u}, o[4];
+    pmo_philox4x32_10(ctr, key, o);
+    xyz[3 * i] = unit_from_u32(o[0]); xyz[3 * i + 1] = unit_from_u32(o[1]); xyz[3 * i + 2] = unit_from_u32(o[2]);
+  }
+}
+
 /* randomize, PMK:1201-1211: three draws, statement order x,y,z, each scaled by the input component */
 static v3 randomize(uint32_t *w, uint32_t *z, v3 r) {
   v3 m;

@@ -15,6 +15,9 @@ uint32_t pmo_mwc_next(uint32_t *w, uint32_t *z);
 float    pmo_rand_float(uint32_t *w, uint32_t *z, float max);
 void     pmo_mwc_table(uint32_t *w, uint32_t *z, float *xyz, int n);
 
+void     pmo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+void     pmo_philox_table(uint64_t seed, float *xyz, int n);
+
 void pmo_scene_default(pm_scene *sc);
 void pmo_position_objects(pm_scene *sc, float t);
 void pmo_voxel(const float p[3], int v[3]);

@@ -199,6 +199,24 @@ def test_progressive_passes_accumulate(pm, oracle):
     m.close()
 
 
+def test_philox_table_and_trace(pm, oracle):
+    """Counter-based RNG mode: the Philox table is bit-exact with the oracle's, and a trace over it matches the oracle
+    consuming the same table (records bit-exact)."""
+    n = 20000
+    osc = oracle.default_scene()
+    m = _mapper(pm, n, copy_scene(pm.Scene, osc))
+    m.init_random_numbers_philox(0x5EED)
+    table = oracle.philox_table(n, 0x5EED)
+    assert bits_equal(m.get_random_table(), table)
+    assert m.get_mwc_state() == (6548, 316)
+    m.set_record_capacity(16 * n)
+    m.clear_map(); m.trace(0.3, media=True, records=True); m.build_map()
+    ogrid, orec, _ = oracle.emit(osc, table, 0, n, 0.3, True, rng=(6548, 316), max_records=16 * n)
+    assert m.get_records().tobytes() == orec.tobytes()
+    assert np.abs(m.get_map() - ogrid).max() <= MAP_TOL * np.abs(ogrid).max()
+    m.close()
+
+
 def _fold(pm, acc):
     """Accumulators with the grey replicas summed (a CTA picks its replica by block index, so only the sum is
     shard-invariant)."""
