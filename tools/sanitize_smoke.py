@@ -21,6 +21,13 @@ m.knn_build(0); m.knn_build(1)
 rgba = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda"); rgbf = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
 m.render_knn(w, h, 0.3, True, 50, float("inf"), 1e-4, 1e-2, rgba=rgba, rgbf=rgbf)
 m.render_knn(w, h, 0.3, False, 100, 0.01, 1e-4, 1e-2, rgba=rgba, rgbf=rgbf, y0=1, y1=h, y_step=3)
+q = torch.rand((64, 4), device="cuda") * 3 - 1.5
+idx = torch.empty((64, 20), dtype=torch.int32, device="cuda"); d2 = torch.empty((64, 20), device="cuda"); cnt = torch.empty(64, dtype=torch.int32, device="cuda")
+m.knn_query(0, q, 64, 20, float("inf"), idx, d2, cnt)
+rgb = torch.empty((64, 4), device="cuda")
+m.knn_radiance_cone(q, 64, 100, 0.7, 50.0, rgb)
+m.init_random_numbers_philox(7)
+m.clear_map(); m.trace(0.0, media=True); m.build_map()
 m.sync()
 print("sanitize smoke ok: map sum %.4f, frame mean %.5f, knn frame mean %.5f" % (float(m.get_map().sum()), float(f32[..., :3].mean()), float(rgbf[..., :3].mean())))
 m.close()
