@@ -46,6 +46,8 @@ def parse():
                     help="a (default, headline): the reference's voxel-map estimator; b: k-NN photon map (records all-gathered, "
                          "tree built on every rank, row bands) -- for Mode B scaling runs")
     ap.add_argument("--knn", type=int, default=50, help="k of the Mode B estimate")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="Mode A: do not overlap a frame's render + frame gather (side stream) with the next frame's trace")
     ap.add_argument("--passes", type=int, default=1,
                     help="progressive photon mapping (BASELINE config 5): photon passes accumulated per frame, each with a fresh "
                          "direction table from the continuing MWC stream (Mode A)")
@@ -353,6 +355,16 @@ def main():
         if e: e[4].record()
         step_b.keep = (sp, vp)    # the maps reference the gathered arrays
 
+    # Mode A pipelining: the render + frame gather of frame i run on a side stream while the main stream already traces
+    # frame i+1 (the trace only touches the accumulators, the render only the gather tables).  Dependencies: render(i) waits
+    # for build(i); build(i+1) rewrites the tables and waits for render(i).  Every frame is still rendered and gathered in
+    # full, and the last one completes before the closing barrier.
+    overlap = not a.no_overlap
+    side = torch.cuda.Stream() if overlap else None
+    ev_built, ev_rendered = torch.cuda.Event(), torch.cuda.Event()
+    main_stream = torch.cuda.current_stream()
+    state = {"pending": False}
+
     def step_a(e=None):
         if e: e[0].record()
         m.clear_map()
@@ -363,11 +375,25 @@ def main():
         if e: e[1].record()
         pmdist.allreduce_accumulators(acc)        # exact: int64 sum over NVLink (no-op at N=1)
         if e: e[2].record()
+        if overlap and state["pending"]:
+            main_stream.wait_event(ev_rendered)   # the previous frame's render still reads the tables
         m.build_map()
         if e: e[3].record()
-        m.render_device(W, H, 0.0, False, True, rgba=rgba, rgbf=rgbf, y0=y0, y1=y1)
-        pmdist.gather_frame(rgba, y0, y1)
-        pmdist.gather_frame(rgbf, y0, y1)
+        if overlap:
+            ev_built.record(main_stream)
+            side.wait_event(ev_built)
+            m.set_stream(side.cuda_stream)
+            with torch.cuda.stream(side):
+                m.render_device(W, H, 0.0, False, True, rgba=rgba, rgbf=rgbf, y0=y0, y1=y1)
+                ev_rendered.record(side)
+                pmdist.gather_frame(rgba, y0, y1)
+                pmdist.gather_frame(rgbf, y0, y1)
+            m.set_stream(main_stream.cuda_stream)
+            state["pending"] = True
+        else:
+            m.render_device(W, H, 0.0, False, True, rgba=rgba, rgbf=rgbf, y0=y0, y1=y1)
+            pmdist.gather_frame(rgba, y0, y1)
+            pmdist.gather_frame(rgbf, y0, y1)
         if e: e[4].record()
 
     step = step_b if a.mode == "b" else step_a
@@ -414,6 +440,8 @@ def main():
             m.frame(W, H, 0.0, emit=True, interp=False, media=True, out_u8=h_rgba, out_f32=h_rgbf)
         else:
             step()
+            if side is not None:
+                main_stream.wait_stream(side)     # the frame gather runs on the side stream
             if rank == 0:
                 h_rgba.copy_(rgba, non_blocking=True); h_rgbf.copy_(rgbf, non_blocking=True)
             torch.cuda.synchronize()
