@@ -332,15 +332,27 @@ def main():
 
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(a.steps)]
 
+    side_b = torch.cuda.Stream() if (world > 1 and not a.no_overlap) else None
+    ev_traced = torch.cuda.Event()
+    main_stream = torch.cuda.current_stream()
+
     def step_b(e=None):
         if e: e[0].record()
         m.clear_map()
         m.trace(0.0, media=True, records=True, no_map=True)
         if e: e[1].record()
         sp = pmdist.allgather_records(*[m.record_buffers(0)[i] for i in (0, 1, 3)])
-        vp = pmdist.allgather_records(*[m.record_buffers(1)[i] for i in (0, 1, 3)])
         if e: e[2].record()
-        m.knn_build_points(0, sp[0], sp[1], sp[2], records=True)
+        if world > 1 and side_b is not None:      # the volume records travel while the surface tree is being built
+            ev_traced.record(main_stream)
+            side_b.wait_event(ev_traced)
+            with torch.cuda.stream(side_b):
+                vp = pmdist.allgather_records(*[m.record_buffers(1)[i] for i in (0, 1, 3)])
+            m.knn_build_points(0, sp[0], sp[1], sp[2], records=True)
+            main_stream.wait_stream(side_b)
+        else:
+            vp = pmdist.allgather_records(*[m.record_buffers(1)[i] for i in (0, 1, 3)])
+            m.knn_build_points(0, sp[0], sp[1], sp[2], records=True)
         m.knn_build_points(1, vp[0], vp[1], vp[2], records=True)
         if e: e[3].record()
         # the k-NN gather cost varies strongly over the image: rank r renders rows r, r+N, r+2N, ... and the frames are
@@ -492,7 +504,8 @@ def main():
             "photons_per_s": NP / (ms_per_step * 1e-3), "pixels_per_s": W * H / (ms_per_step * 1e-3),
             "stages_ms": ({"clear+trace": float(stages[0]), "allreduce": float(stages[1]), "build_map+tables": float(stages[2]),
                            "render(+gather)": float(stages[3])} if a.mode == "a" else
-                          {"trace_with_records": float(stages[0]), "allgather_records": float(stages[1]), "build_maps": float(stages[2]),
+                          {"trace_with_records": float(stages[0]), "allgather_surface_records": float(stages[1]),
+                           "allgather_volume_records||build_surface, build_volume": float(stages[2]),
                            "knn_render(+gather)": float(stages[3])}),
             "gpu_launches": int(launches),
             "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": C.sizeof(pmb200.Scene),
