@@ -17,7 +17,7 @@ inline uint32_t host_powmod(uint32_t a, unsigned long long e, uint32_t m) {
 }
 
 // pm_trace.cu
-cudaError_t launch_mwc_table(float4 *table, long long n, uint32_t w0, uint32_t z0, const MwcJump *J, cudaStream_t st);
+cudaError_t launch_mwc_table(float4 *table, long long first, long long last, uint32_t w0, uint32_t z0, const MwcJump *J, cudaStream_t st);
 cudaError_t launch_philox_table(float4 *table, long long n, unsigned long long seed, cudaStream_t st);
 // each returns the number of kernels launched; *err receives the CUDA status
 int launch_trace_volume(const DeviceScene &sc, const float4 *table, long long first, long long last, unsigned flags, uint32_t w0,

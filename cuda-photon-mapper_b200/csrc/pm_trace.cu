@@ -23,10 +23,13 @@ namespace pm {
 // ------------------------------------------------------------------------------------------------------
 // random table: thread i owns draws 3i..3i+2 of the stream that starts at (w0,z0); rand3 order x,y,z
 // ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) mwc_table_kernel(float4 *__restrict__ table, long long n, uint32_t w0, uint32_t z0,
+// Rows [first, last) are generated, plus rows 0..2 (every photon's medium walk reads them, PMK:1258): a rank of a
+// multi-GPU job only needs its own photon range.
+__global__ void __launch_bounds__(256) mwc_table_kernel(float4 *__restrict__ table, long long first, long long last, uint32_t w0, uint32_t z0,
                                                         const MwcJump *__restrict__ J) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long i = t < 3 ? t : first + (t - 3);
+  if (i >= last || (t >= 3 && i < 3)) return;
   Mwc s;
   uint32_t steps = (uint32_t)(3 * i);
   s.z = mwc_jump(J, 0, z0, steps);
@@ -386,10 +389,11 @@ __global__ void __launch_bounds__(kSurfaceThreads, 1) surface_kernel(const __gri
 // ------------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------------
-cudaError_t launch_mwc_table(float4 *table, long long n, uint32_t w0, uint32_t z0, const MwcJump *J, cudaStream_t st) {
-  if (n <= 0) return cudaSuccess;
+cudaError_t launch_mwc_table(float4 *table, long long first, long long last, uint32_t w0, uint32_t z0, const MwcJump *J, cudaStream_t st) {
+  long long n = last - first + 3;
+  if (last <= 0) return cudaSuccess;
   unsigned blocks = (unsigned)((n + 255) / 256);
-  mwc_table_kernel<<<blocks, 256, 0, st>>>(table, n, w0, z0, J);
+  mwc_table_kernel<<<blocks, 256, 0, st>>>(table, first, last, w0, z0, J);
   return cudaGetLastError();
 }
 

@@ -80,7 +80,8 @@ int  pm_set_photon_range(pm_context *ctx, int64_t first, int64_t last);        /
 int  pm_set_energy_scale(pm_context *ctx, float scale);   /* photon map is multiplied by this when built (1 = reference) */
 
 /* random-direction table T2 (PMK:80) */
-int pm_init_random_table(pm_context *ctx);       /* MWC stream, == launch_init_random_numbers_kernel */
+int pm_init_random_table(pm_context *ctx);       /* MWC stream, == launch_init_random_numbers_kernel.  Generates the rows of the
+                                                    current photon range (+ rows 0..2); the stream advances by 3*n_photons */
 /* counter-based alternative: row i = Philox4x32-10(counter i, key seed) mapped like randFloat(1.0); the MWC state (medium
  * draws) is untouched.  The oracle consumes the same table (oracle/pm_oracle.c pmo_philox_table). */
 int pm_init_random_table_philox(pm_context *ctx, uint64_t seed);

@@ -217,6 +217,29 @@ def test_philox_table_and_trace(pm, oracle):
     m.close()
 
 
+def test_sharded_table_generation(pm, oracle):
+    """A rank of a multi-GPU job generates only its own rows of the direction table (plus rows 0..2, which every photon's
+    medium walk reads): the rows, the MWC state and the traced records equal the oracle's for that photon range."""
+    n, a, b = 20000, 7001, 13000
+    osc = oracle.default_scene()
+    m = _mapper(pm, n, copy_scene(pm.Scene, osc))
+    m.set_photon_range(a, b)
+    m.init_random_numbers()
+    table, st = oracle.mwc_table(n)
+    got = m.get_random_table()
+    assert bits_equal(got[a:b], table[a:b]) and bits_equal(got[:3], table[:3])
+    assert m.get_mwc_state() == st
+    m.set_record_capacity(16 * (b - a))
+    m.clear_map(); m.trace(0.0, media=True, records=True, no_map=True)
+    _, st_shard = oracle.mwc_draws(9 * a, *st)
+    _, orec, _ = oracle.emit(osc, table, a, b, 0.0, True, rng=st_shard, max_records=16 * (b - a), want_grid=False)
+    assert m.get_records().tobytes() == orec.tobytes()
+    m.set_photon_range(0, n)                       # widening the range after a sharded fill is refused
+    with pytest.raises(pm.PmError, match="photon range"):
+        m.trace(0.0)
+    m.close()
+
+
 def _fold(pm, acc):
     """Accumulators with the grey replicas summed (a CTA picks its replica by block index, so only the sum is
     shard-invariant)."""
