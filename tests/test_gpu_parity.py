@@ -45,13 +45,17 @@ def test_mwc_table_bit_exact(pm, oracle):
 
 @pytest.mark.parametrize("media", [False, True])
 @pytest.mark.parametrize("t", [0.0, 0.7])
-@pytest.mark.parametrize("scene_name", ["default", "cfg1"])
+@pytest.mark.parametrize("scene_name", ["default", "cfg1", "backwall5"])
 def test_trace_records_and_map(pm, oracle, media, t, scene_name):
     """Stage 1: photon records bit-exact (position, direction, power, object ids, order), photon map within MAP_TOL."""
     n = 20000
     osc = oracle.default_scene()
     if scene_name == "cfg1":
         cfg1_scene(osc)
+    elif scene_name == "backwall5":
+        # back wall at z = 5 (as in the legacy variant, "photonMappingKernel - Copy.cu":28): its hits fall in voxel slab 26, not on
+        # the map boundary slab 31 that splatEnergy hard-codes -> exercises the per-photon off-slab fallback of store_photon
+        osc.planes[4][1] = 5.0
     m = _mapper(pm, n, copy_scene(pm.Scene, osc))
     m.init_random_numbers()
     table, st = oracle.mwc_table(n)
