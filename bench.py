@@ -441,29 +441,44 @@ def main():
     ms_per_step = total_ms / a.steps
     stages = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(4)] for e in ev]).mean(0)
 
-    # ---- end to end through the C-ABI with HOST buffers (pinned): frame call + D2H of both framebuffers ----
-    h_rgba = torch.empty((H, W, 4), dtype=torch.uint8).pin_memory()
-    h_rgbf = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
+    # ---- end to end through the C-ABI with HOST buffers (pinned): scene struct in, the reference's uchar4 frame out.
+    #      One GPU: pm_frame_host_async, the copy of frame f runs under the trace of frame f+1 and the host waits for every
+    #      frame (one frame behind).  Multi-GPU / Mode B: step + D2H of the assembled frame on rank 0, synchronous. ----
+    h_rgba2 = [torch.empty((H, W, 4), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    h_rgba = h_rgba2[0]
     e2e_steps = max(3, min(a.steps, 30))
+    pipelined = world == 1 and a.mode == "a" and a.passes == 1
+    pending = []
 
     def e2e_step():
         m.set_scene(scene)                        # the frame's only host input: the scene / parameter block
-        if world == 1 and a.mode == "a":
-            m.frame(W, H, 0.0, emit=True, interp=False, media=True, out_u8=h_rgba, out_f32=h_rgbf)
+        if pipelined:
+            tk = m.frame_async(W, H, h_rgba2[e2e_step.n & 1], t=0.0, emit=True, interp=False, media=True)
+            e2e_step.n += 1
+            if pending:
+                m.frame_wait(pending.pop())       # frame f-1 is complete in host memory before frame f+1 is submitted
+            pending.append(tk)
         else:
             step()
             if side is not None:
                 main_stream.wait_stream(side)     # the frame gather runs on the side stream
             if rank == 0:
-                h_rgba.copy_(rgba, non_blocking=True); h_rgbf.copy_(rgbf, non_blocking=True)
+                h_rgba.copy_(rgba, non_blocking=True)
             torch.cuda.synchronize()
+    e2e_step.n = 0
+
+    def e2e_drain():
+        while pending:
+            m.frame_wait(pending.pop())
 
     for _ in range(3):
         e2e_step()
+    e2e_drain()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         e2e_step()
+    e2e_drain()                                   # the last frame is in host memory too
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
     if world > 1:
@@ -485,7 +500,7 @@ def main():
         dom = max(kern, key=lambda k: kern[k]["avg_ms"] * kern[k]["launches"])
         # algorithmic (compulsory) HBM bytes per launch, DESIGN.md "kernels": one float3 direction per photon for the two
         # trace kernels; one uchar4 + one float4 per pixel for the render kernel
-        alg = {"volume_kernel": 12.0 * n_local, "surface_kernel": 12.0 * n_local, "render_kernel": 20.0 * W * rows}
+        alg = {"volume_kernel": 12.0 * n_local, "trace_kernel": 12.0 * n_local, "render_kernel": 20.0 * W * rows}
         dom_bytes = alg.get(dom, 0.0)
         dom_ms = kern[dom]["avg_ms"]
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
@@ -509,15 +524,17 @@ def main():
                            "knn_render(+gather)": float(stages[3])}),
             "gpu_launches": int(launches),
             "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": C.sizeof(pmb200.Scene),
-                    "d2h_bytes_per_step": W * H * 4 + W * H * 16, "steps": e2e_steps,
-                    "what": "pm_frame_host: scene struct in, emit+render, uchar4 + float4 frames copied to pinned host memory"},
+                    "d2h_bytes_per_step": W * H * 4, "steps": e2e_steps,
+                    "what": ("pm_frame_host_async + pm_frame_wait per frame: scene struct in, emit + render, the reference's uchar4 "
+                             "frame copied to pinned host memory under the next frame's trace" if pipelined else
+                             "step + D2H of the assembled uchar4 frame on rank 0, synchronous")},
             "kernels": kern,
             "roofline": {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_ms,
-                         "note": "Mode A keeps no photon records, so the compulsory HBM traffic of the trace kernels is one 12 B "
-                                 "direction per photon: they are instruction-issue bound (ncu: issue slots ~83% busy), not "
-                                 "HBM bound; see DESIGN.md 'rooflines' and profiles/"},
+                         "note": "Mode A keeps no photon records, so the compulsory HBM traffic of the fused trace kernel is one 12 B "
+                                 "direction per photon: its surface warps are instruction-issue bound and its medium-walk warps "
+                                 "L2-atomic bound (3 REDs per photon), not HBM bound; see DESIGN.md 'rooflines' and profiles/"},
             "clocks": clocks,
         }
         if not a.no_cpu_baseline and world == 1 and a.mode == "a":

@@ -17,7 +17,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PMB200_LIB") or os.path.join(_HERE, "libpmb200.so")   # PMB200_LIB: development override
 
-PM_TRACE_MEDIA, PM_TRACE_RECORDS, PM_TRACE_NO_MAP = 1, 2, 4
+PM_TRACE_MEDIA, PM_TRACE_RECORDS, PM_TRACE_NO_MAP, PM_TRACE_SPLIT = 1, 2, 4, 8
 GRID_N = 32
 ACC_HIT_ENTRIES = 5 * 32 * 32 * 4
 ACC_ENTRIES = ACC_HIT_ENTRIES + 32 * 32 * 32 * 3 + 8 * 32 * 32 * 32
@@ -61,7 +61,7 @@ def lib():
             "pm_init_random_table": (i32, [vp]), "pm_init_random_table_philox": (i32, [vp, C.c_uint64]), "pm_set_random_table_host": (i32, [vp, vp, i64]),
             "pm_get_random_table_host": (i32, [vp, vp, i64]),
             "pm_set_mwc_state": (i32, [vp, u32, u32]), "pm_get_mwc_state": (i32, [vp, C.POINTER(u32), C.POINTER(u32)]),
-            "pm_clear_map": (i32, [vp]), "pm_trace": (i32, [vp, f32, C.c_uint]),
+            "pm_clear_map": (i32, [vp]), "pm_trace": (i32, [vp, f32, C.c_uint]), "pm_set_volume_warps": (i32, [vp, i32]),
             "pm_accumulators": (i32, [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]),
             "pm_get_accumulators_host": (i32, [vp, vp]),
             "pm_build_map": (i32, [vp]), "pm_get_map_host": (i32, [vp, vp]), "pm_set_map_host": (i32, [vp, vp]),
@@ -82,6 +82,8 @@ def lib():
             "pm_render": (i32, [vp, f32, b, b, i32, i32, i32, i32, vp, vp]),
             "pm_render_host": (i32, [vp, f32, b, b, i32, i32, vp, vp]),
             "pm_frame_host": (i32, [vp, f32, b, b, b, i32, i32, vp, vp]),
+            "pm_frame_host_async": (i32, [vp, f32, b, b, b, i32, i32, vp, C.POINTER(C.c_int64)]),
+            "pm_frame_wait": (i32, [vp, C.c_int64]),
             "pm_launch_count": (i64, [vp]),
             "pm_enable_timing": (i32, [vp, b]), "pm_kernel_count": (i32, []), "pm_kernel_name": (C.c_char_p, [i32]),
             "pm_get_timings": (i32, [vp, vp, vp]),
@@ -203,9 +205,13 @@ class PhotonMapper:
     def clear_map(self):
         self._ck(self.L.pm_clear_map(self.h))
 
-    def trace(self, t=0.0, media=False, records=False, no_map=False):
-        flags = (PM_TRACE_MEDIA if media else 0) | (PM_TRACE_RECORDS if records else 0) | (PM_TRACE_NO_MAP if no_map else 0)
+    def trace(self, t=0.0, media=False, records=False, no_map=False, split=False):
+        flags = ((PM_TRACE_MEDIA if media else 0) | (PM_TRACE_RECORDS if records else 0) | (PM_TRACE_NO_MAP if no_map else 0)
+                 | (PM_TRACE_SPLIT if split else 0))
         self._ck(self.L.pm_trace(self.h, t, flags))
+
+    def set_volume_warps(self, warps):
+        self._ck(self.L.pm_set_volume_warps(self.h, warps))
 
     def accumulators(self):
         """(device pointer, number of int64 entries) of the exact accumulators."""
@@ -325,6 +331,15 @@ class PhotonMapper:
     def frame(self, w, h, t=0.0, emit=True, interp=False, media=False, out_u8=None, out_f32=None):
         """One display() frame (callbacksPBO.cpp:47-101) through host buffers."""
         self._ck(self.L.pm_frame_host(self.h, t, emit, interp, media, w, h, _ptr(out_u8), _ptr(out_f32)))
+
+    def frame_async(self, w, h, out_u8, t=0.0, emit=True, interp=False, media=False):
+        """pm_frame_host_async: enqueue a frame whose uchar4 image lands in out_u8 (pinned host memory); returns the ticket."""
+        tk = C.c_int64()
+        self._ck(self.L.pm_frame_host_async(self.h, t, emit, interp, media, w, h, _ptr(out_u8), C.byref(tk)))
+        return tk.value
+
+    def frame_wait(self, ticket):
+        self._ck(self.L.pm_frame_wait(self.h, ticket))
 
     def launch_count(self):
         return self.L.pm_launch_count(self.h)

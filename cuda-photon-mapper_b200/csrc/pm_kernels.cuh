@@ -21,11 +21,13 @@ cudaError_t launch_mwc_table(float4 *table, long long first, long long last, uin
 cudaError_t launch_philox_table(float4 *table, long long n, unsigned long long seed, cudaStream_t st);
 // each returns the number of kernels launched; *err receives the CUDA status
 int launch_trace_volume(const DeviceScene &sc, const float4 *table, long long first, long long last, unsigned flags, uint32_t w0,
-                        uint32_t z0, const MwcJump *J, unsigned long long *acc, float4 *rec_pos, float4 *rec_pow, float4 *rec_dir,
-                        unsigned long long *rec_count, long long rec_cap, int num_sms, cudaStream_t st, cudaError_t *err);
-int launch_trace_surface(const DeviceScene &sc, const float4 *table, long long first, long long last, unsigned flags,
-                         unsigned long long *acc, float4 *rec_pos, float4 *rec_pow, float4 *rec_dir, unsigned long long *rec_count,
-                         long long rec_cap, int num_sms, cudaStream_t st, cudaError_t *err);
+                        uint32_t z0, const MwcJump *J, unsigned long long *acc, uint32_t *vol_cnt, float4 *rec_pos, float4 *rec_pow,
+                        float4 *rec_dir, unsigned long long *rec_count, long long rec_cap, int num_sms, cudaStream_t st,
+                        cudaError_t *err);
+int launch_trace(const DeviceScene &sc, const float4 *table, long long first, long long last, unsigned flags, int vol_warps, uint32_t w0,
+                 uint32_t z0, const MwcJump *J, unsigned long long *acc, uint32_t *vol_cnt, float4 *rec_pos, float4 *rec_pow,
+                 float4 *rec_dir, float4 *vrec_pos, float4 *vrec_pow, long long vrec_cap, unsigned long long *rec_count, long long rec_cap,
+                 int num_sms, cudaStream_t st, cudaError_t *err);
 
 // pm_map.cu
 cudaError_t launch_build_map(const long long *acc, float energy_scale, float *grid, cudaStream_t st);

@@ -21,6 +21,12 @@ constexpr int    kAccVoxEntries = PM_GRID_VOXELS * 3;                          /
 constexpr int    kGreyReplicas  = 8;
 constexpr int    kAccGreyEntries = kGreyReplicas * PM_GRID_VOXELS;             // 262 144
 constexpr int    kAccEntries    = kAccHitEntries + kAccVoxEntries + kAccGreyEntries;   // 380 928 int64 = 3 047 424 B
+// Scratch for the medium walk: its deposits carry one of three energies (9, 8, 7 x 0.00005, a function of the step only),
+// so volume_kernel COUNTS them -- 32-bit REDs, twice the L2 rate of 64-bit ones -- in vol_cnt[replica][step][voxel] and
+// fold_volume_kernel adds count x quantum (exact integers) to acc_grey and clears the counts.  Not part of the accumulator
+// state: always zero between launches.
+constexpr int    kVolCntReplicas = 4;
+constexpr int    kVolCntEntries  = kVolCntReplicas * 3 * PM_GRID_VOXELS;       // 393 216 u32 = 1.5 MB
 constexpr double kHitScale      = 16777216.0;          // 2^24
 constexpr double kVoxScale      = 68719476736.0;       // 2^36
 

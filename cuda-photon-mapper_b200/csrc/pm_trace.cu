@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256) philox_table_kernel(float4 *__restrict__ 
     c0 = n0; c1 = l1; c2 = n2; c3 = l0;
     k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
   }
-  auto unit = [](uint32_t u) { float rnd = __fdiv_rn((float)((int)u), 65535.0f); rnd = rnd * 2.0f * 1.0f; return rnd - 1.0f; };
+  auto unit = [](uint32_t u) { float rnd = div65535((float)((int)u)); rnd = rnd * 2.0f * 1.0f; return rnd - 1.0f; };
   table[i] = make_float4(unit(c0), unit(c1), unit(c2), 0.0f);
 }
 
@@ -60,9 +60,12 @@ __global__ void __launch_bounds__(256) philox_table_kernel(float4 *__restrict__ 
 // ------------------------------------------------------------------------------------------------------
 struct Sink {
   unsigned long long *acc;       // kAccEntries, or nullptr (PM_TRACE_NO_MAP)
-  float4 *rec_pos, *rec_pow, *rec_dir;   // surface records: appended (surface_kernel) / volume records: slot = 3*(index-first)+step
+  float4 *rec_pos, *rec_pow, *rec_dir;   // surface records: appended
+  float4 *vrec_pos, *vrec_pow;           // volume records: slot = 3*(index-first)+step
+  long long vrec_cap;
   unsigned long long *rec_count; // global append cursor (surface records)
   long long rec_cap;
+  uint32_t *vol_cnt;             // kVolCntEntries deposit counters of the medium walk (volume_kernel only)
 };
 
 __device__ __forceinline__ void acc_add(unsigned long long *p, long long v) {
@@ -91,11 +94,10 @@ __device__ __forceinline__ void append_record(const Sink &sk, int seq, int kind,
 // jumps to its first photon once (table look-ups) and then advances by the grid stride with one modular
 // multiplication per lane (cz, cw = a^(9*stride) mod m, computed by the launcher).
 // ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) volume_kernel(const __grid_constant__ DeviceScene sc, const float4 *__restrict__ table,
-                                                     long long first, long long last, unsigned flags, uint32_t w0, uint32_t z0,
-                                                     const MwcJump *__restrict__ J, uint32_t cw, uint32_t cz, Sink sk) {
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  long long gi = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+// One thread's share of the medium walk: photons gi, gi + stride, ... < last.  cw, cz = a^(9*stride) mod m.
+__device__ __forceinline__ void volume_walk(const DeviceScene &sc, const float4 *__restrict__ table, long long first, long long gi,
+                                            long long last, long long stride, unsigned flags, uint32_t w0, uint32_t z0,
+                                            const MwcJump *__restrict__ J, uint32_t cw, uint32_t cz, int replica, const Sink &sk) {
   if (gi >= last) return;
   const bool rec = (flags & PM_TRACE_RECORDS) != 0;
   const v3 light = V(sc.light[0], sc.light[1], sc.light[2]);
@@ -104,9 +106,12 @@ __global__ void __launch_bounds__(256) volume_kernel(const __grid_constant__ Dev
   base.w = mwc_jump(J, 1, w0, 9u * (uint32_t)gi);
   // randomNumbers[i], i = 0..2 (sic, PMK:1258): the same three table rows scale every photon's draws
   const float4 t0 = __ldg(table + 0), t1 = __ldg(table + 1), t2 = __ldg(table + 2);
+  uint32_t *const cnt = sk.vol_cnt + replica * 3 * PM_GRID_VOXELS;
+  float4 td_next = __ldg(table + gi);
   for (; gi < last; gi += stride) {
     const int index = (int)gi;
-    const float4 td = __ldg(table + gi);
+    const float4 td = td_next;
+    if (gi + stride < last) td_next = __ldg(table + gi + stride);   // next row in flight under this photon's walk
     v3 rgb = V(10.0f, 10.0f, 10.0f);
     v3 ray = normalize(V(td.x, td.y, td.z));
     v3 prev = light;
@@ -115,25 +120,16 @@ __global__ void __launch_bounds__(256) volume_kernel(const __grid_constant__ Dev
     for (int i = 0; i < 3; i++) {
       rgb = subs(rgb, 1.0f);
       v3 P = add(mul(ray, 1.0f), prev);
-      v3 e = mul(rgb, 0.00005f);
-      if (sk.acc) {
-        int vx = clampi(voxel_x(P.x)), vy = clampi(voxel_x(P.y)), vz = clampi(voxel_z(P.z));
-        int v = (vx * PM_GRID_N + vy) * PM_GRID_N + vz;
-        if (e.x == e.y && e.y == e.z) {   // always true on this path: one atomic instead of three
-          acc_add(sk.acc + kAccHitEntries + kAccVoxEntries + (blockIdx.x % kGreyReplicas) * PM_GRID_VOXELS + v,
-                  __double2ll_rn((double)e.x * kVoxScale));
-        } else {
-          unsigned long long *p = sk.acc + kAccHitEntries + 3 * v;
-          acc_add(p + 0, __double2ll_rn((double)e.x * kVoxScale));
-          acc_add(p + 1, __double2ll_rn((double)e.y * kVoxScale));
-          acc_add(p + 2, __double2ll_rn((double)e.z * kVoxScale));
-        }
+      if (sk.acc) {   // e is a function of the step only: count the deposit, fold_volume_kernel turns counts into energy
+        int vx = voxel_x_clamped(P.x), vy = voxel_x_clamped(P.y), vz = voxel_z_clamped(P.z);
+        atomicAdd(cnt + i * PM_GRID_VOXELS + (vx * PM_GRID_N + vy) * PM_GRID_N + vz, 1u);
       }
       if (rec) {   // volume records have a fixed slot: deterministic order, coalesced, no atomics
+        v3 e = mul(rgb, 0.00005f);
         long long slot = 3 * (gi - first) + i;
-        if (slot < sk.rec_cap) {
-          sk.rec_pos[slot] = make_float4(P.x, P.y, P.z, __uint_as_float(pack_meta(i, 1, -1, -1)));
-          sk.rec_pow[slot] = make_float4(e.x, e.y, e.z, __int_as_float(index));
+        if (slot < sk.vrec_cap) {
+          sk.vrec_pos[slot] = make_float4(P.x, P.y, P.z, __uint_as_float(pack_meta(i, 1, -1, -1)));
+          sk.vrec_pow[slot] = make_float4(e.x, e.y, e.z, __int_as_float(index));
         }
       }
       const float4 tr = i == 0 ? t0 : (i == 1 ? t1 : t2);
@@ -147,6 +143,37 @@ __global__ void __launch_bounds__(256) volume_kernel(const __grid_constant__ Dev
     base.z = mulmod(base.z, cz, mwc_modulus(0));
     base.w = mulmod(base.w, cw, mwc_modulus(1));
   }
+}
+
+// stand-alone medium walk (PM_TRACE_SPLIT): grid-stride over the whole range
+__global__ void __launch_bounds__(256) volume_kernel(const __grid_constant__ DeviceScene sc, const float4 *__restrict__ table,
+                                                     long long first, long long last, unsigned flags, uint32_t w0, uint32_t z0,
+                                                     const MwcJump *__restrict__ J, uint32_t cw, uint32_t cz, Sink sk) {
+  volume_walk(sc, table, first, first + (long long)blockIdx.x * blockDim.x + threadIdx.x, last, (long long)gridDim.x * blockDim.x, flags,
+              w0, z0, J, cw, cz, blockIdx.x % kVolCntReplicas, sk);
+}
+
+// counts -> energy: acc_grey[0][v] += sum over replicas and steps of count * quantum(step); the counts are cleared.
+// The quanta are computed with the same FP32 operations as the walk (rgb = 10 - 1 - ..., e = rgb * 0.00005f).
+__global__ void __launch_bounds__(256) fold_volume_kernel(uint32_t *__restrict__ cnt, unsigned long long *__restrict__ acc) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= PM_GRID_VOXELS) return;
+  long long sum = 0;
+  float rgb = 10.0f;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    rgb = rgb - 1.0f;
+    const long long q = __double2ll_rn((double)(rgb * 0.00005f) * kVoxScale);
+    unsigned long long n = 0;
+#pragma unroll
+    for (int r = 0; r < kVolCntReplicas; r++) {
+      uint32_t *p = cnt + (r * 3 + i) * PM_GRID_VOXELS + v;
+      n += *p;
+      *p = 0u;
+    }
+    sum += (long long)n * q;
+  }
+  if (sum) acc[kAccHitEntries + kAccVoxEntries + v] += (unsigned long long)sum;   // one thread per voxel, stream-ordered
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -167,7 +194,7 @@ struct SmemAcc {
 // storePhoton + splatEnergy + storeNeighborPhoton, PMK:1059-1144, :1164-1183 (type 0 = sphere: nothing is stored)
 __device__ __forceinline__ void store_photon(const Sink &sk, SmemAcc &sa, int type, int id, v3 loc, v3 e) {
   if (!sk.acc || type == 0) return;
-  int vx = clampi(voxel_x(loc.x)), vy = clampi(voxel_x(loc.y)), vz = clampi(voxel_z(loc.z));
+  int vx = voxel_x_clamped(loc.x), vy = voxel_x_clamped(loc.y), vz = voxel_z_clamped(loc.z);
   // wall id -> slab axis / slab index / in-plane coordinates, as splatEnergy hard-codes them (selects, no branches)
   const int ax = (id == 0 || id == 2) ? 0 : ((id == 1 || id == 3) ? 1 : 2);
   const int slab = (id == 0 || id == 3 || id == 4) ? PM_GRID_N - 1 : 0;
@@ -230,9 +257,13 @@ constexpr int kSurfaceThreads = 1024;
 constexpr int kRefillLanes = 8;
 constexpr size_t kSurfaceSmem = sizeof(uint32_t) * 2 * kAccHitEntries;   // 122 880 B
 
-__global__ void __launch_bounds__(kSurfaceThreads, 1) surface_kernel(const __grid_constant__ DeviceScene sc,
-                                                                     const float4 *__restrict__ table, long long first, long long last,
-                                                                     unsigned flags, Sink sk) {
+// Warp-specialised: warps [0, vol_warps) of every CTA run the medium walk of the CTA's photon range (L2-atomic bound,
+// nearly no issue slots), the other warps run the surface walk (issue bound, no L2 traffic) -- the two halves of
+// emitPhotons overlap on the same SM instead of running back to back.  vol_warps = 0: surface walk only.
+__global__ void __launch_bounds__(kSurfaceThreads, 1) trace_kernel(const __grid_constant__ DeviceScene sc,
+                                                                   const float4 *__restrict__ table, long long first, long long last,
+                                                                   unsigned flags, int vol_warps, uint32_t w0, uint32_t z0,
+                                                                   const MwcJump *__restrict__ J, uint32_t cw, uint32_t cz, Sink sk) {
   extern __shared__ uint32_t smem_u32[];
   SmemAcc sa;
   sa.lo = smem_u32; sa.hi = smem_u32 + kAccHitEntries;
@@ -243,12 +274,20 @@ __global__ void __launch_bounds__(kSurfaceThreads, 1) surface_kernel(const __gri
   const bool rec = (flags & PM_TRACE_RECORDS) != 0;
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
-  // each warp owns a contiguous slice of the photon range; lanes are refilled from it
-  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
-  const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long long per = (last - first + warps - 1) / warps;
-  long long cur = first + gw * per;
-  long long end = cur + per < last ? cur + per : last;
+  // the CTA owns a contiguous part of the photon range
+  const long long per_cta = (last - first + gridDim.x - 1) / gridDim.x;
+  const long long cta_first = first + (long long)blockIdx.x * per_cta < last ? first + (long long)blockIdx.x * per_cta : last;
+  const long long cta_last = cta_first + per_cta < last ? cta_first + per_cta : last;
+  const int warp = threadIdx.x >> 5;
+  if (warp < vol_warps)
+    volume_walk(sc, table, first, cta_first + threadIdx.x, cta_last, (long long)vol_warps * 32, flags, w0, z0, J, cw, cz,
+                blockIdx.x % kVolCntReplicas, sk);
+  // each surface warp owns a contiguous slice of the CTA's range; lanes are refilled from it
+  const int surf_warps = (blockDim.x >> 5) - vol_warps;
+  const long long per = (cta_last - cta_first + surf_warps - 1) / surf_warps;
+  long long cur = cta_first + (long long)(warp - vol_warps) * per;
+  long long end = cur + per < cta_last ? cur + per : cta_last;
+  if (warp < vol_warps) { cur = 0; end = 0; }
   if (cur > end) cur = end;
 
   const v3 light = V(sc.light[0], sc.light[1], sc.light[2]);
@@ -406,42 +445,68 @@ cudaError_t launch_philox_table(float4 *table, long long n, unsigned long long s
 static Sink make_sink(unsigned flags, unsigned long long *acc, float4 *rec_pos, float4 *rec_pow, float4 *rec_dir,
                       unsigned long long *rec_count, long long rec_cap) {
   Sink sk;
+  sk.vol_cnt = nullptr; sk.vrec_pos = sk.vrec_pow = nullptr; sk.vrec_cap = 0;
   sk.acc = (flags & PM_TRACE_NO_MAP) ? nullptr : acc;
   sk.rec_pos = rec_pos; sk.rec_pow = rec_pow; sk.rec_dir = rec_dir; sk.rec_count = rec_count; sk.rec_cap = rec_cap;
   return sk;
 }
 
+static unsigned volume_blocks(long long n, int num_sms) {
+  long long want = (n + 255) / 256, cap = (long long)num_sms * 8;
+  return (unsigned)(want < cap ? want : cap);
+}
+
+static cudaError_t launch_fold(uint32_t *vol_cnt, unsigned long long *acc, cudaStream_t st) {
+  fold_volume_kernel<<<PM_GRID_VOXELS / 256, 256, 0, st>>>(vol_cnt, acc);
+  return cudaGetLastError();
+}
+
+// PM_TRACE_SPLIT: the medium walk as its own launch (+ the count fold)
 int launch_trace_volume(const DeviceScene &sc, const float4 *table, long long first, long long last, unsigned flags, uint32_t w0,
-                        uint32_t z0, const MwcJump *J, unsigned long long *acc, float4 *rec_pos, float4 *rec_pow, float4 *rec_dir,
-                        unsigned long long *rec_count, long long rec_cap, int num_sms, cudaStream_t st, cudaError_t *err) {
+                        uint32_t z0, const MwcJump *J, unsigned long long *acc, uint32_t *vol_cnt, float4 *rec_pos, float4 *rec_pow,
+                        float4 *rec_dir, unsigned long long *rec_count, long long rec_cap, int num_sms, cudaStream_t st,
+                        cudaError_t *err) {
   *err = cudaSuccess;
   long long n = last - first;
   if (n <= 0) return 0;
-  Sink sk = make_sink(flags, acc, rec_pos, rec_pow, rec_dir, rec_count, rec_cap);
-  long long want = (n + 255) / 256, cap = (long long)num_sms * 8;
-  unsigned blocks = (unsigned)(want < cap ? want : cap);
+  Sink sk = make_sink(flags, acc, nullptr, nullptr, nullptr, rec_count, 0);
+  sk.vol_cnt = vol_cnt; sk.vrec_pos = rec_pos; sk.vrec_pow = rec_pow; sk.vrec_cap = rec_cap;
+  unsigned blocks = volume_blocks(n, num_sms);
   unsigned long long steps = 9ull * blocks * 256ull;
   volume_kernel<<<blocks, 256, 0, st>>>(sc, table, first, last, flags, w0, z0, J, host_powmod(18000u, steps, mwc_modulus(1)),
                                         host_powmod(36969u, steps, mwc_modulus(0)), sk);
   *err = cudaGetLastError();
-  return 1;
+  if (*err != cudaSuccess || !sk.acc) return 1;
+  *err = launch_fold(vol_cnt, sk.acc, st);
+  return 2;
 }
 
-int launch_trace_surface(const DeviceScene &sc, const float4 *table, long long first, long long last, unsigned flags,
-                         unsigned long long *acc, float4 *rec_pos, float4 *rec_pow, float4 *rec_dir, unsigned long long *rec_count,
-                         long long rec_cap, int num_sms, cudaStream_t st, cudaError_t *err) {
+// The trace launch.  vol_warps > 0: fused medium + surface walk (the volume records go to vrec_*); 0: surface walk only.
+int launch_trace(const DeviceScene &sc, const float4 *table, long long first, long long last, unsigned flags, int vol_warps, uint32_t w0,
+                 uint32_t z0, const MwcJump *J, unsigned long long *acc, uint32_t *vol_cnt, float4 *rec_pos, float4 *rec_pow,
+                 float4 *rec_dir, float4 *vrec_pos, float4 *vrec_pow, long long vrec_cap, unsigned long long *rec_count, long long rec_cap,
+                 int num_sms, cudaStream_t st, cudaError_t *err) {
   *err = cudaSuccess;
   long long n = last - first;
   if (n <= 0) return 0;
   Sink sk = make_sink(flags, acc, rec_pos, rec_pow, rec_dir, rec_count, rec_cap);
-  *err = cudaFuncSetAttribute(surface_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSurfaceSmem);
+  sk.vol_cnt = vol_cnt; sk.vrec_pos = vrec_pos; sk.vrec_pow = vrec_pow; sk.vrec_cap = vrec_cap;
+  *err = cudaFuncSetAttribute(trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSurfaceSmem);
   if (*err != cudaSuccess) return 0;
+  const int cta_warps = kSurfaceThreads / 32;
+  if (vol_warps < 0) vol_warps = 0;
+  if (vol_warps > cta_warps / 2) vol_warps = cta_warps / 2;
   long long warps_needed = (n + 31) / 32;
-  long long ctas = (warps_needed + (kSurfaceThreads / 32) - 1) / (kSurfaceThreads / 32);
+  long long ctas = (warps_needed + (cta_warps - vol_warps) - 1) / (cta_warps - vol_warps);
   unsigned grid = (unsigned)(ctas < num_sms ? ctas : num_sms);
-  surface_kernel<<<grid, kSurfaceThreads, kSurfaceSmem, st>>>(sc, table, first, last, flags, sk);
+  unsigned long long steps = 9ull * 32ull * (unsigned)vol_warps;
+  trace_kernel<<<grid, kSurfaceThreads, kSurfaceSmem, st>>>(sc, table, first, last, flags, vol_warps, w0, z0, J,
+                                                            host_powmod(18000u, steps, mwc_modulus(1)),
+                                                            host_powmod(36969u, steps, mwc_modulus(0)), sk);
   *err = cudaGetLastError();
-  return 1;
+  if (*err != cudaSuccess || !vol_warps || !sk.acc) return 1;
+  *err = launch_fold(vol_cnt, sk.acc, st);
+  return 2;
 }
 
 }  // namespace pm

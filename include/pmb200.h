@@ -94,8 +94,12 @@ int pm_get_mwc_state(const pm_context *ctx, uint32_t *w, uint32_t *z);
 #define PM_TRACE_MEDIA    1u   /* participatingMediaFlag */
 #define PM_TRACE_RECORDS  2u   /* also append photon records to the SoA buffers (Mode B input) */
 #define PM_TRACE_NO_MAP   4u   /* skip the voxel-map accumulation (records only) */
+#define PM_TRACE_SPLIT    8u   /* run the medium walk and the surface walk as two launches instead of the fused,
+                                  warp-specialised one (same results; kept for measurement and as a cross-check) */
 int pm_clear_map(pm_context *ctx);                                 /* init_photons_kernel, PMK:1503-1521 */
 int pm_trace(pm_context *ctx, float animTime, unsigned flags);
+/* tuning: how many of a CTA's 32 warps run the medium walk in the fused trace kernel (default 6; 1..16) */
+int pm_set_volume_warps(pm_context *ctx, int warps);
 /* the exact (int64 fixed-point) accumulators the trace adds into; sum them across GPUs (e.g. NCCL
  * all-reduce, ncclInt64/ncclSum) between pm_trace and pm_build_map for multi-GPU runs */
 int pm_accumulators(pm_context *ctx, void **dev_ptr, size_t *n_int64);
@@ -168,6 +172,14 @@ int pm_render_host(pm_context *ctx, float animTime, bool interpolateFlag, bool p
  * (callbacksPBO.cpp:47-101) minus OpenGL */
 int pm_frame_host(pm_context *ctx, float animTime, bool emitFlag, bool interpolateFlag, bool participatingMediaFlag,
                   int width, int height, pm_uchar4 *host_rgba, float *host_rgbf);
+/* the same frame, pipelined: everything is enqueued and the call returns at once with a ticket.  The uchar4 frame (the
+ * reference's out_data) is copied to host_rgba -- pinned memory, or the copy is not asynchronous -- on the context's
+ * copy stream from one of two device frame buffers, so the copy of frame f runs under the trace of frame f+1.
+ * pm_frame_wait blocks until the frame of that ticket is in host memory; only the two most recent tickets are valid,
+ * so wait for ticket f-1 (at the latest) before submitting frame f+1. */
+int pm_frame_host_async(pm_context *ctx, float animTime, bool emitFlag, bool interpolateFlag, bool participatingMediaFlag,
+                        int width, int height, pm_uchar4 *host_rgba, int64_t *ticket);
+int pm_frame_wait(pm_context *ctx, int64_t ticket);
 
 /* instrumentation: number of kernels this context has launched so far, and optional per-kernel CUDA-event timing
  * (event pairs recorded on the context's stream around each launch; pm_get_timings synchronises, fills

@@ -271,3 +271,62 @@ def test_legacy_abi_frame(pm, oracle):
         d = np.abs(got.astype(np.int32) - ou8.astype(np.int32))
         assert d.max() <= 1 and (d > 0).mean() <= 2e-3, (t, d.max(), (d > 0).mean())
         assert np.all(got[..., 3] == 0)
+
+
+@pytest.mark.parametrize("warps", [1, 3, 6, 16])
+def test_fused_trace_equals_split_trace(pm, oracle, warps):
+    """The warp-specialised trace kernel (medium walk on `warps` warps of every CTA, surface walk on the rest) and the two
+    separate launches (PM_TRACE_SPLIT) produce identical accumulators, identical volume records and the same MWC state."""
+    n = 50000
+    m = _mapper(pm, n)
+    m.init_random_numbers()
+    st = m.get_mwc_state()
+    m.clear_map(); m.trace(0.3, media=True, split=True)
+    split = _fold(pm, m.get_accumulators())
+    st_split = m.get_mwc_state()
+    m.set_mwc_state(*st)
+    m.set_volume_warps(warps)
+    m.clear_map(); m.trace(0.3, media=True)
+    assert np.array_equal(split, _fold(pm, m.get_accumulators()))
+    assert m.get_mwc_state() == st_split
+    # a partial range that does not divide by anything
+    m.set_mwc_state(*st); m.set_photon_range(777, 31001)
+    m.clear_map(); m.trace(0.3, media=True, split=True)
+    split = _fold(pm, m.get_accumulators())
+    m.set_mwc_state(*st)
+    m.clear_map(); m.trace(0.3, media=True)
+    assert np.array_equal(split, _fold(pm, m.get_accumulators()))
+    m.close()
+
+
+def test_pipelined_frames_equal_synchronous_frames(pm, oracle):
+    """pm_frame_host_async / pm_frame_wait: five animated frames submitted back to back (copy of frame f under the trace of
+    frame f+1, two device frame buffers) are byte-identical to the same frames through the synchronous pm_frame_host."""
+    import torch
+    w, h, n = 640, 360, 40000
+    times = [0.0, 0.2, 0.4, 0.6, 0.8]
+    ref = _mapper(pm, n)
+    ref.init_random_numbers()
+    want = []
+    for t in times:
+        u8 = np.empty((h, w, 4), np.uint8)
+        ref.frame(w, h, t, emit=True, interp=True, media=True, out_u8=u8, out_f32=None)
+        want.append(u8)
+    ref.close()
+    m = _mapper(pm, n)
+    m.init_random_numbers()
+    bufs = [torch.empty((h, w, 4), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    got, prev = [], None
+    for f, t in enumerate(times):
+        tk = m.frame_async(w, h, bufs[f & 1], t=t, emit=True, interp=True, media=True)
+        if prev is not None:
+            m.frame_wait(prev[0])
+            got.append(bufs[prev[1]].numpy().copy())
+        prev = (tk, f & 1)
+    m.frame_wait(prev[0])
+    got.append(bufs[prev[1]].numpy().copy())
+    for f in range(len(times)):
+        assert np.array_equal(got[f], want[f]), f
+    with pytest.raises(pm.PmError):
+        m.frame_wait(0)          # only the two most recent tickets can be waited for
+    m.close()

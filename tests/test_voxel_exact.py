@@ -53,3 +53,54 @@ def test_voxel_identity():
     p = p[np.abs(p) < 3e4]          # the kernels fall back to the literal form beyond |32t/3| >= 2^20
     assert np.array_equal(ref_x(p), fast_x(p))
     assert np.array_equal(ref_z(p), fast_z(p))
+
+
+def clamped_x(p):
+    """voxel_x_clamped (csrc/pm_math.cuh): FP32 + integer arithmetic only"""
+    u = np.float32(32.0) * p                      # exact
+    u = (u.astype(np.float64) + 2.0 ** -48).astype(np.float32)   # fma(32, p, 2^-48): one rounding (the f64 sum of two f32 is exact
+    #                                                              unless their exponents are > 29 apart, where RN is u either way)
+    u = np.clip(u, np.float32(-48.0), np.float32(48.0))
+    k = ((np.floor(u).astype(np.int64) + 48) * 43691) >> 17
+    return np.minimum(k, 31)
+
+
+def clamped_z(p):
+    u = np.clip(np.float32(16.0) * p, np.float32(0.0), np.float32(96.0))
+    k = (np.floor(u).astype(np.int64) * 43691) >> 17
+    return np.minimum(k, 31)
+
+
+def rng_exponents():
+    return np.arange(20, 149, dtype=np.float64)
+
+
+def test_clamped_voxel_matches_literal_form():
+    p = _samples()
+    big = np.float32([1e9, -1e9, 3e38, -3e38, 1e-40, -1e-40, 0.0, -0.0, -2.0 ** -53, -2.0 ** -52, -2.0 ** -54, 2.0 ** -53,
+                      -1.5, np.nextafter(np.float32(-1.5), np.float32(0)), np.nextafter(np.float32(-1.5), np.float32(-2))])
+    tiny = (-(2.0 ** -rng_exponents())).astype(np.float32)
+    big = np.concatenate([big, tiny, -tiny])
+    p = np.concatenate([p, big])
+    assert p.dtype == np.float32
+
+    def sat(f, p):   # the literal double form with the device's saturating double -> int conversion (cvt.rzi.s32.f64)
+        return np.clip(np.trunc(f(p)), -2.0 ** 31, 2.0 ** 31 - 1).astype(np.int64)
+    lit_x = lambda p: ((p.astype(np.float64) + 1.5) / 3.0) * 32
+    lit_z = lambda p: (p.astype(np.float64) / 6.0) * 32
+    assert np.array_equal(np.clip(sat(lit_x, p), 0, 31), clamped_x(p))
+    assert np.array_equal(np.clip(sat(lit_z, p), 0, 31), clamped_z(p))
+    # every float in the two voxel ranges' neighbourhood that is a multiple of 2^-12: all boundaries, both sides
+    q = (np.arange(-3 * 4096, 8 * 4096, dtype=np.int64) / 4096.0).astype(np.float32)
+    assert np.array_equal(np.clip(ref_x(q), 0, 31), clamped_x(q))
+    assert np.array_equal(np.clip(ref_z(q), 0, 31), clamped_z(q))
+
+
+def test_div65535_constant_reciprocal_is_correctly_rounded():
+    """strided subset of oracle/check_div65535.c (the exhaustive run, stride 1, reports 0 mismatches of 2^32)"""
+    import os, subprocess
+    exe = os.path.join(os.path.dirname(__file__), "..", "oracle", "check_div65535")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.dirname(exe), "check_div65535"])
+    out = subprocess.run([exe, "61"], capture_output=True, text=True, check=True).stdout.split()
+    assert int(out[0]) == 0 and int(out[1]) > 70_000_000

@@ -18,7 +18,11 @@ def t(fn, reps=10):
     return a.elapsed_time(b) / reps
 print("surface only, map      %.3f ms" % t(lambda: m.trace(0.0, media=False)))
 print("surface only, no map   %.3f ms" % t(lambda: m.trace(0.0, media=False, no_map=True)))
-print("media, map             %.3f ms" % t(lambda: m.trace(0.0, media=True)))
+print("media, map, split      %.3f ms" % t(lambda: m.trace(0.0, media=True, split=True)))
+for w in (2, 3, 4, 6, 8):
+    m.set_volume_warps(w)
+    print("media, map, fused w=%d  %.3f ms" % (w, t(lambda: m.trace(0.0, media=True))))
+m.set_volume_warps(4)
 print("media, no map          %.3f ms" % t(lambda: m.trace(0.0, media=True, no_map=True)))
 print("clear                  %.3f ms" % t(lambda: m.clear_map()))
 print("build                  %.3f ms" % t(lambda: m.build_map()))
