@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(256) fold_volume_kernel(uint32_t *__restrict__
 // CTA-private accumulator for on-slab wall hits: kAccHitEntries x (lo, hi) 32-bit halves in shared memory.
 struct SmemAcc {
   uint32_t *lo, *hi;
+  uint32_t *shadow;   // per wall texel: number of shadow photons (each deposits exactly -0.25 grey), folded in at the flush
   __device__ __forceinline__ void add(int e, long long v) {
     if (v == 0) return;
     uint32_t vlo = (uint32_t)v, vhi = (uint32_t)((unsigned long long)v >> 32);
@@ -191,27 +192,9 @@ struct SmemAcc {
   }
 };
 
-// storePhoton + splatEnergy + storeNeighborPhoton, PMK:1059-1144, :1164-1183 (type 0 = sphere: nothing is stored)
-__device__ __forceinline__ void store_photon(const Sink &sk, SmemAcc &sa, int type, int id, v3 loc, v3 e) {
-  if (!sk.acc || type == 0) return;
-  int vx = voxel_x_clamped(loc.x), vy = voxel_x_clamped(loc.y), vz = voxel_z_clamped(loc.z);
-  // wall id -> slab axis / slab index / in-plane coordinates, as splatEnergy hard-codes them (selects, no branches)
-  const int ax = (id == 0 || id == 2) ? 0 : ((id == 1 || id == 3) ? 1 : 2);
-  const int slab = (id == 0 || id == 3 || id == 4) ? PM_GRID_N - 1 : 0;
-  const int vfix = ax == 0 ? vx : (ax == 1 ? vy : vz);
-  const int a = ax == 0 ? vy : vx, b = ax == 2 ? vy : vz;
-  const int on_slab = (unsigned)id > 4u ? -1 : (vfix == slab ? 1 : 0);
-  if (on_slab == 1) {   // the common case: keyed energy sum, the 6x6 stencil is applied once per voxel in pm_map.cu
-    int en = ((id * PM_GRID_N + a) * PM_GRID_N + b) * 4;
-    if (e.x == e.y && e.y == e.z) sa.add(en + 3, __float2ll_rn(e.x * (float)kHitScale));
-    else {
-      sa.add(en + 0, __float2ll_rn(e.x * (float)kHitScale));
-      sa.add(en + 1, __float2ll_rn(e.y * (float)kHitScale));
-      sa.add(en + 2, __float2ll_rn(e.z * (float)kHitScale));
-    }
-    return;
-  }
-  // rare: the clamped voxel is off the wall's slab (a wall that is not on the map boundary): expand per photon
+// The clamped voxel is off the wall's slab (a wall that is not on the map boundary): expand the splat per photon.  Rare.
+// (Measured: making this and the mirror/glass direction updates real calls costs 17% -- the call ABI spills the walk's state.)
+static __device__ __forceinline__ void splat_offslab(const Sink &sk, int id, int on_slab, int vx, int vy, int vz, v3 e) {
   unsigned long long *vox = sk.acc + kAccHitEntries;
   {
     unsigned long long *p = vox + ((vx * PM_GRID_N + vy) * PM_GRID_N + vz) * 3;
@@ -242,6 +225,30 @@ __device__ __forceinline__ void store_photon(const Sink &sk, SmemAcc &sa, int ty
       }
 }
 
+// storePhoton + splatEnergy + storeNeighborPhoton, PMK:1059-1144, :1164-1183 (type 0 = sphere: nothing is stored)
+__device__ __forceinline__ void store_photon(const Sink &sk, SmemAcc &sa, int type, int id, v3 loc, v3 e, bool shadow) {
+  if (!sk.acc || type == 0) return;
+  int vx = voxel_x_clamped(loc.x), vy = voxel_x_clamped(loc.y), vz = voxel_z_clamped(loc.z);
+  // wall id -> slab axis / slab index / in-plane coordinates, as splatEnergy hard-codes them (selects, no branches)
+  const int ax = (id == 0 || id == 2) ? 0 : ((id == 1 || id == 3) ? 1 : 2);
+  const int slab = (id == 0 || id == 3 || id == 4) ? PM_GRID_N - 1 : 0;
+  const int vfix = ax == 0 ? vx : (ax == 1 ? vy : vz);
+  const int a = ax == 0 ? vy : vx, b = ax == 2 ? vy : vz;
+  const int on_slab = (unsigned)id > 4u ? -1 : (vfix == slab ? 1 : 0);
+  if (on_slab == 1) {   // the common case: keyed energy sum, the 6x6 stencil is applied once per voxel in pm_map.cu
+    int en = ((id * PM_GRID_N + a) * PM_GRID_N + b) * 4;
+    if (shadow) atomicAdd(sa.shadow + (en >> 2), 1u);   // half of all deposits: one 32-bit count instead of a 64-bit add with carry
+    else if (e.x == e.y && e.y == e.z) sa.add(en + 3, __float2ll_rn(e.x * (float)kHitScale));
+    else {
+      sa.add(en + 0, __float2ll_rn(e.x * (float)kHitScale));
+      sa.add(en + 1, __float2ll_rn(e.y * (float)kHitScale));
+      sa.add(en + 2, __float2ll_rn(e.z * (float)kHitScale));
+    }
+    return;
+  }
+  splat_offslab(sk, id, on_slab, vx, vy, vz, e);   // rare: the clamped voxel is off the wall's slab
+}
+
 // getColor / filterColor, PMK:605-617
 __device__ __forceinline__ v3 get_color(v3 in, int type, int idx) {
   v3 m = V(1.0f, 1.0f, 1.0f);
@@ -254,24 +261,27 @@ __device__ __forceinline__ v3 get_color(v3 in, int type, int idx) {
 enum : int { ST_IDLE = 0, ST_PRIMARY, ST_SHADOW, ST_CHAIN_R, ST_CHAIN_F1, ST_CHAIN_F2 };
 
 constexpr int kSurfaceThreads = 1024;
-constexpr int kRefillLanes = 8;
-constexpr size_t kSurfaceSmem = sizeof(uint32_t) * 2 * kAccHitEntries;   // 122 880 B
+constexpr int kRefillLanes = 8;   // measured: 4 is 13% slower, 12 and 16 are the same as 8; taking chunks off a CTA-wide cursor
+                                  // instead of static per-warp slices is 20% slower; prefetching the table rows changes nothing
+constexpr int kShadowEntries = kAccHitEntries / 4;                                      // one per wall texel
+constexpr size_t kSurfaceSmem = sizeof(uint32_t) * (2 * kAccHitEntries + kShadowEntries);   // 184 320 B
 
 // Warp-specialised: warps [0, vol_warps) of every CTA run the medium walk of the CTA's photon range (L2-atomic bound,
 // nearly no issue slots), the other warps run the surface walk (issue bound, no L2 traffic) -- the two halves of
 // emitPhotons overlap on the same SM instead of running back to back.  vol_warps = 0: surface walk only.
+template <bool kRec>   // kRec: the launch appends photon records (PM_TRACE_RECORDS); Mode A compiles that path out
 __global__ void __launch_bounds__(kSurfaceThreads, 1) trace_kernel(const __grid_constant__ DeviceScene sc,
                                                                    const float4 *__restrict__ table, long long first, long long last,
                                                                    unsigned flags, int vol_warps, uint32_t w0, uint32_t z0,
                                                                    const MwcJump *__restrict__ J, uint32_t cw, uint32_t cz, Sink sk) {
   extern __shared__ uint32_t smem_u32[];
   SmemAcc sa;
-  sa.lo = smem_u32; sa.hi = smem_u32 + kAccHitEntries;
-  for (int i = threadIdx.x; i < 2 * kAccHitEntries; i += blockDim.x) smem_u32[i] = 0u;
+  sa.lo = smem_u32; sa.hi = smem_u32 + kAccHitEntries; sa.shadow = smem_u32 + 2 * kAccHitEntries;
+  for (int i = threadIdx.x; i < 2 * kAccHitEntries + kShadowEntries; i += blockDim.x) smem_u32[i] = 0u;
   __syncthreads();
 
   const bool media = flags & PM_TRACE_MEDIA;
-  const bool rec = (flags & PM_TRACE_RECORDS) != 0;
+  const bool rec = kRec;
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
   // the CTA owns a contiguous part of the photon range
@@ -280,8 +290,8 @@ __global__ void __launch_bounds__(kSurfaceThreads, 1) trace_kernel(const __grid_
   const long long cta_last = cta_first + per_cta < last ? cta_first + per_cta : last;
   const int warp = threadIdx.x >> 5;
   if (warp < vol_warps)
-    volume_walk(sc, table, first, cta_first + threadIdx.x, cta_last, (long long)vol_warps * 32, flags, w0, z0, J, cw, cz,
-                blockIdx.x % kVolCntReplicas, sk);
+    volume_walk(sc, table, first, cta_first + threadIdx.x, cta_last, (long long)vol_warps * 32, kRec ? flags : (flags & ~PM_TRACE_RECORDS),
+                w0, z0, J, cw, cz, blockIdx.x % kVolCntReplicas, sk);
   // each surface warp owns a contiguous slice of the CTA's range; lanes are refilled from it
   const int surf_warps = (blockDim.x >> 5) - vol_warps;
   const long long per = (cta_last - cta_first + surf_warps - 1) / surf_warps;
@@ -371,13 +381,13 @@ __global__ void __launch_bounds__(kSurfaceThreads, 1) trace_kernel(const __grid_
       if (!(h.hit && bounces <= 5)) { state = ST_IDLE; continue; }
       if (new_point) P = add(mul(ray, h.dist), prev);
       if (caustics) rgb = mul(V(1.0f, 1.0f, 1.0f), 10.0f);
-      else rgb = mul(divs(mul(get_color(rgb, h.type, h.idx), 1.0f), __fsqrt_rn((float)bounces)), 5.0f);
+      else rgb = mul(mul(mul(get_color(rgb, h.type, h.idx), 1.0f), sc.inv_sqrt_bounce[bounces & 7]), 5.0f);   // 1 <= bounces <= 5 here
       loc = P; e = rgb;
     } else {                     // shadowPhoton, PMK:1185-1196: -0.25 at the next hit along the same ray
       loc = add(mul(ray, h.dist), org);
       e = V(-0.25f, -0.25f, -0.25f);
     }
-    store_photon(sk, sa, h.type, h.idx, loc, e);
+    store_photon(sk, sa, h.type, h.idx, loc, e, state == ST_SHADOW);
     if (rec) append_record(sk, seq, 0, h.type, h.idx, index, loc, ray, e);
     seq++;
     if (state == ST_PRIMARY && !caustics) {
@@ -420,6 +430,7 @@ __global__ void __launch_bounds__(kSurfaceThreads, 1) trace_kernel(const __grid_
   if (sk.acc) {
     for (int e = threadIdx.x; e < kAccHitEntries; e += blockDim.x) {
       unsigned long long v = (unsigned long long)sa.lo[e] | ((unsigned long long)sa.hi[e] << 32);
+      if ((e & 3) == 3) v += (unsigned long long)((long long)sa.shadow[e >> 2] * __float2ll_rn(-0.25f * (float)kHitScale));
       if (v) atomicAdd(sk.acc + e, v);
     }
   }
@@ -491,7 +502,9 @@ int launch_trace(const DeviceScene &sc, const float4 *table, long long first, lo
   if (n <= 0) return 0;
   Sink sk = make_sink(flags, acc, rec_pos, rec_pow, rec_dir, rec_count, rec_cap);
   sk.vol_cnt = vol_cnt; sk.vrec_pos = vrec_pos; sk.vrec_pow = vrec_pow; sk.vrec_cap = vrec_cap;
-  *err = cudaFuncSetAttribute(trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSurfaceSmem);
+  const bool rec = (flags & PM_TRACE_RECORDS) != 0;
+  auto kernel = rec ? trace_kernel<true> : trace_kernel<false>;
+  *err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSurfaceSmem);
   if (*err != cudaSuccess) return 0;
   const int cta_warps = kSurfaceThreads / 32;
   if (vol_warps < 0) vol_warps = 0;
@@ -500,7 +513,7 @@ int launch_trace(const DeviceScene &sc, const float4 *table, long long first, lo
   long long ctas = (warps_needed + (cta_warps - vol_warps) - 1) / (cta_warps - vol_warps);
   unsigned grid = (unsigned)(ctas < num_sms ? ctas : num_sms);
   unsigned long long steps = 9ull * 32ull * (unsigned)vol_warps;
-  trace_kernel<<<grid, kSurfaceThreads, kSurfaceSmem, st>>>(sc, table, first, last, flags, vol_warps, w0, z0, J,
+  kernel<<<grid, kSurfaceThreads, kSurfaceSmem, st>>>(sc, table, first, last, flags, vol_warps, w0, z0, J,
                                                             host_powmod(18000u, steps, mwc_modulus(1)),
                                                             host_powmod(36969u, steps, mwc_modulus(0)), sk);
   *err = cudaGetLastError();

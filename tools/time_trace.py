@@ -19,7 +19,7 @@ def t(fn, reps=10):
 print("surface only, map      %.3f ms" % t(lambda: m.trace(0.0, media=False)))
 print("surface only, no map   %.3f ms" % t(lambda: m.trace(0.0, media=False, no_map=True)))
 print("media, map, split      %.3f ms" % t(lambda: m.trace(0.0, media=True, split=True)))
-for w in (2, 3, 4, 6, 8):
+for w in (4, 5, 6, 7, 8):
     m.set_volume_warps(w)
     print("media, map, fused w=%d  %.3f ms" % (w, t(lambda: m.trace(0.0, media=True))))
 m.set_volume_warps(4)
