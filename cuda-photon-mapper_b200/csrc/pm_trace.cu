@@ -94,54 +94,108 @@ __device__ __forceinline__ void append_record(const Sink &sk, int seq, int kind,
 // jumps to its first photon once (table look-ups) and then advances by the grid stride with one modular
 // multiplication per lane (cz, cw = a^(9*stride) mod m, computed by the launcher).
 // ------------------------------------------------------------------------------------------------------
-// One thread's share of the medium walk: photons gi, gi + stride, ... < last.  cw, cz = a^(9*stride) mod m.
+// One photon of the medium walk: three unit steps from the light, a deposit at each, nine MWC draws (state s by value).
+struct VolumeCtx {
+  float4 t0, t1, t2;   // randomNumbers[i], i = 0..2 (sic, PMK:1258): the same three table rows scale every photon's draws
+  uint32_t *cnt;       // this CTA's replica of the deposit counters
+  v3 light;
+  long long first;     // first photon of the launch (record slots are relative to it)
+  bool rec;
+};
+__device__ __forceinline__ VolumeCtx volume_ctx(const DeviceScene &sc, const float4 *__restrict__ table, long long first, unsigned flags,
+                                                int replica, const Sink &sk) {
+  VolumeCtx c;
+  c.t0 = __ldg(table + 0); c.t1 = __ldg(table + 1); c.t2 = __ldg(table + 2);
+  c.cnt = sk.vol_cnt + replica * 3 * PM_GRID_VOXELS;
+  c.light = V(sc.light[0], sc.light[1], sc.light[2]);
+  c.first = first;
+  c.rec = (flags & PM_TRACE_RECORDS) != 0;
+  return c;
+}
+__device__ __forceinline__ void volume_photon(const VolumeCtx &c, const Sink &sk, float4 td, long long gi, Mwc s) {
+  v3 rgb = V(10.0f, 10.0f, 10.0f);
+  v3 ray = normalize(V(td.x, td.y, td.z));
+  v3 prev = c.light;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    rgb = subs(rgb, 1.0f);
+    v3 P = add(mul(ray, 1.0f), prev);
+    if (sk.acc) {   // e is a function of the step only: count the deposit, fold_volume_kernel turns counts into energy
+      int vx = voxel_x_clamped(P.x), vy = voxel_x_clamped(P.y), vz = voxel_z_clamped(P.z);
+      atomicAdd(c.cnt + i * PM_GRID_VOXELS + (vx * PM_GRID_N + vy) * PM_GRID_N + vz, 1u);
+    }
+    if (c.rec) {   // volume records have a fixed slot: deterministic order, coalesced, no atomics
+      v3 e = mul(rgb, 0.00005f);
+      long long slot = 3 * (gi - c.first) + i;
+      if (slot < sk.vrec_cap) {
+        sk.vrec_pos[slot] = make_float4(P.x, P.y, P.z, __uint_as_float(pack_meta(i, 1, -1, -1)));
+        sk.vrec_pow[slot] = make_float4(e.x, e.y, e.z, __int_as_float((int)gi));
+      }
+    }
+    const float4 tr = i == 0 ? c.t0 : (i == 1 ? c.t1 : c.t2);
+    v3 r;
+    r.x = rand_float(s, tr.x);
+    r.y = rand_float(s, tr.y);
+    r.z = rand_float(s, tr.z);
+    ray = normalize(r);
+    prev = P;
+  }
+}
+
+// One thread's share of the medium walk, strided: photons gi, gi + stride, ... < last.  cw, cz = a^(9*stride) mod m.
 __device__ __forceinline__ void volume_walk(const DeviceScene &sc, const float4 *__restrict__ table, long long first, long long gi,
                                             long long last, long long stride, unsigned flags, uint32_t w0, uint32_t z0,
                                             const MwcJump *__restrict__ J, uint32_t cw, uint32_t cz, int replica, const Sink &sk) {
   if (gi >= last) return;
-  const bool rec = (flags & PM_TRACE_RECORDS) != 0;
-  const v3 light = V(sc.light[0], sc.light[1], sc.light[2]);
+  const VolumeCtx c = volume_ctx(sc, table, first, flags, replica, sk);
   Mwc base;
   base.z = mwc_jump(J, 0, z0, 9u * (uint32_t)gi);
   base.w = mwc_jump(J, 1, w0, 9u * (uint32_t)gi);
-  // randomNumbers[i], i = 0..2 (sic, PMK:1258): the same three table rows scale every photon's draws
-  const float4 t0 = __ldg(table + 0), t1 = __ldg(table + 1), t2 = __ldg(table + 2);
-  uint32_t *const cnt = sk.vol_cnt + replica * 3 * PM_GRID_VOXELS;
   float4 td_next = __ldg(table + gi);
   for (; gi < last; gi += stride) {
-    const int index = (int)gi;
     const float4 td = td_next;
     if (gi + stride < last) td_next = __ldg(table + gi + stride);   // next row in flight under this photon's walk
-    v3 rgb = V(10.0f, 10.0f, 10.0f);
-    v3 ray = normalize(V(td.x, td.y, td.z));
-    v3 prev = light;
-    Mwc s = base;
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-      rgb = subs(rgb, 1.0f);
-      v3 P = add(mul(ray, 1.0f), prev);
-      if (sk.acc) {   // e is a function of the step only: count the deposit, fold_volume_kernel turns counts into energy
-        int vx = voxel_x_clamped(P.x), vy = voxel_x_clamped(P.y), vz = voxel_z_clamped(P.z);
-        atomicAdd(cnt + i * PM_GRID_VOXELS + (vx * PM_GRID_N + vy) * PM_GRID_N + vz, 1u);
-      }
-      if (rec) {   // volume records have a fixed slot: deterministic order, coalesced, no atomics
-        v3 e = mul(rgb, 0.00005f);
-        long long slot = 3 * (gi - first) + i;
-        if (slot < sk.vrec_cap) {
-          sk.vrec_pos[slot] = make_float4(P.x, P.y, P.z, __uint_as_float(pack_meta(i, 1, -1, -1)));
-          sk.vrec_pow[slot] = make_float4(e.x, e.y, e.z, __int_as_float(index));
-        }
-      }
-      const float4 tr = i == 0 ? t0 : (i == 1 ? t1 : t2);
-      v3 r;
-      r.x = rand_float(s, tr.x);
-      r.y = rand_float(s, tr.y);
-      r.z = rand_float(s, tr.z);
-      ray = normalize(r);
-      prev = P;
-    }
+    volume_photon(c, sk, td, gi, base);
     base.z = mulmod(base.z, cz, mwc_modulus(0));
     base.w = mulmod(base.w, cw, mwc_modulus(1));
+  }
+}
+
+// The medium walk inside the fused kernel.  The CTA's range is cut into S slices of `per` photons, one per surface warp; the V
+// medium-walk warps visit 32-photon blocks in the order (block 0 of slices 0..S-1, block 1 of slices 0..S-1, ...), i.e. they
+// sweep every slice at the same rate as its surface warp does, so the table rows are fetched from DRAM once and found in L2 by
+// the other walk (a plain strided sweep of the CTA range read the whole table twice).  A lane's consecutive photons lie
+// V slices apart, or V - S slices + one block when the slice index wraps: two jump multipliers per MWC lane, from the host.
+struct SliceJump { uint32_t fz, fw, wz, ww; };   // forward (V*per photons) and wrap ((V-S)*per + 32 photons), z and w lanes
+__device__ __forceinline__ void volume_walk_sliced(const DeviceScene &sc, const float4 *__restrict__ table, long long first,
+                                                   long long cta_first, long long cta_last, long long per, int S, int V, unsigned flags,
+                                                   uint32_t w0, uint32_t z0, const MwcJump *__restrict__ J, SliceJump jump, int replica,
+                                                   const Sink &sk) {
+  const int lane = threadIdx.x & 31;
+  int s = threadIdx.x >> 5;            // V <= S: the warp's first block is block 0 of slice `warp`
+  long long b = 0;                     // block (32 photons) inside the slice
+  long long gi = cta_first + s * per + lane;
+  if (cta_first >= cta_last || per <= 0) return;
+  const VolumeCtx c = volume_ctx(sc, table, first, flags, replica, sk);
+  Mwc base;
+  base.z = mwc_jump(J, 0, z0, 9u * (uint32_t)gi);
+  base.w = mwc_jump(J, 1, w0, 9u * (uint32_t)gi);
+  bool valid = lane < per && gi < cta_last;
+  float4 td_next = valid ? __ldg(table + gi) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  while (b * 32 < per) {
+    const float4 td = td_next;
+    const long long gi_now = gi;
+    const bool valid_now = valid;
+    // the lane's next block
+    s += V;
+    const bool wrap = s >= S;
+    if (wrap) { s -= S; b += 1; }
+    gi = cta_first + s * per + b * 32 + lane;
+    valid = b * 32 + lane < per && gi < cta_last;
+    if (valid) td_next = __ldg(table + gi);   // in flight under this photon's walk
+    if (valid_now) volume_photon(c, sk, td, gi_now, base);
+    base.z = mulmod(base.z, wrap ? jump.wz : jump.fz, mwc_modulus(0));
+    base.w = mulmod(base.w, wrap ? jump.ww : jump.fw, mwc_modulus(1));
   }
 }
 
@@ -273,7 +327,7 @@ template <bool kRec>   // kRec: the launch appends photon records (PM_TRACE_RECO
 __global__ void __launch_bounds__(kSurfaceThreads, 1) trace_kernel(const __grid_constant__ DeviceScene sc,
                                                                    const float4 *__restrict__ table, long long first, long long last,
                                                                    unsigned flags, int vol_warps, uint32_t w0, uint32_t z0,
-                                                                   const MwcJump *__restrict__ J, uint32_t cw, uint32_t cz, Sink sk) {
+                                                                   const MwcJump *__restrict__ J, SliceJump jump, Sink sk) {
   extern __shared__ uint32_t smem_u32[];
   SmemAcc sa;
   sa.lo = smem_u32; sa.hi = smem_u32 + kAccHitEntries; sa.shadow = smem_u32 + 2 * kAccHitEntries;
@@ -289,12 +343,13 @@ __global__ void __launch_bounds__(kSurfaceThreads, 1) trace_kernel(const __grid_
   const long long cta_first = first + (long long)blockIdx.x * per_cta < last ? first + (long long)blockIdx.x * per_cta : last;
   const long long cta_last = cta_first + per_cta < last ? cta_first + per_cta : last;
   const int warp = threadIdx.x >> 5;
-  if (warp < vol_warps)
-    volume_walk(sc, table, first, cta_first + threadIdx.x, cta_last, (long long)vol_warps * 32, kRec ? flags : (flags & ~PM_TRACE_RECORDS),
-                w0, z0, J, cw, cz, blockIdx.x % kVolCntReplicas, sk);
-  // each surface warp owns a contiguous slice of the CTA's range; lanes are refilled from it
+  // each surface warp owns a contiguous slice of `per` photons of the CTA's range (the same `per` in every CTA, so that
+  // the host can precompute the medium walk's jump multipliers); lanes are refilled from it
   const int surf_warps = (blockDim.x >> 5) - vol_warps;
-  const long long per = (cta_last - cta_first + surf_warps - 1) / surf_warps;
+  const long long per = (per_cta + surf_warps - 1) / surf_warps;
+  if (warp < vol_warps)
+    volume_walk_sliced(sc, table, first, cta_first, cta_last, per, surf_warps, vol_warps, kRec ? flags : (flags & ~PM_TRACE_RECORDS), w0,
+                       z0, J, jump, blockIdx.x % kVolCntReplicas, sk);
   long long cur = cta_first + (long long)(warp - vol_warps) * per;
   long long end = cur + per < cta_last ? cur + per : cta_last;
   if (warp < vol_warps) { cur = 0; end = 0; }
@@ -512,10 +567,16 @@ int launch_trace(const DeviceScene &sc, const float4 *table, long long first, lo
   long long warps_needed = (n + 31) / 32;
   long long ctas = (warps_needed + (cta_warps - vol_warps) - 1) / (cta_warps - vol_warps);
   unsigned grid = (unsigned)(ctas < num_sms ? ctas : num_sms);
-  unsigned long long steps = 9ull * 32ull * (unsigned)vol_warps;
-  kernel<<<grid, kSurfaceThreads, kSurfaceSmem, st>>>(sc, table, first, last, flags, vol_warps, w0, z0, J,
-                                                            host_powmod(18000u, steps, mwc_modulus(1)),
-                                                            host_powmod(36969u, steps, mwc_modulus(0)), sk);
+  // jump multipliers of the sliced medium walk (volume_walk_sliced): one MWC step forward is x * a, backward x * 2^16 (mod m)
+  const long long S = cta_warps - vol_warps, per_cta = (n + grid - 1) / grid, per = (per_cta + S - 1) / S;
+  const long long fwd = (long long)vol_warps * per, wrp = ((long long)vol_warps - S) * per + 32;
+  auto mult = [](uint32_t a, long long photons, uint32_t m) {
+    return photons >= 0 ? host_powmod(a, 9ull * (unsigned long long)photons, m) : host_powmod(65536u, 9ull * (unsigned long long)(-photons), m);
+  };
+  SliceJump jump;
+  jump.fz = mult(36969u, fwd, mwc_modulus(0)); jump.fw = mult(18000u, fwd, mwc_modulus(1));
+  jump.wz = mult(36969u, wrp, mwc_modulus(0)); jump.ww = mult(18000u, wrp, mwc_modulus(1));
+  kernel<<<grid, kSurfaceThreads, kSurfaceSmem, st>>>(sc, table, first, last, flags, vol_warps, w0, z0, J, jump, sk);
   *err = cudaGetLastError();
   if (*err != cudaSuccess || !vol_warps || !sk.acc) return 1;
   *err = launch_fold(vol_cnt, sk.acc, st);

@@ -5,7 +5,7 @@
 Writes profiles/<tag>_launches.md (per-kernel share of a step), profiles/<tag>_kernels.md (ncu --set full key metrics
 per kernel) and profiles/ncu_traffic.json (DRAM bytes per launch, read by bench.py for roofline.traffic).
 """
-import collections, csv, io, json, os, subprocess, sys
+import collections, csv, io, json, os, re, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
@@ -24,12 +24,12 @@ for r in rows[1:]:
     except ValueError:
         continue
     v = v / 1e3 if r[ui] == "ns" else (v * 1e3 if r[ui] == "ms" else v)   # -> us
-    name = r[ki].split("(")[0].replace("pm::", "")
+    name = re.sub(r"<.*", "", r[ki].split("(")[0].replace("pm::", "").replace("void ", ""))
     d.setdefault(name, []).append(v)
-mine = {k: v for k, v in d.items() if k in ("volume_kernel", "surface_kernel", "build_map_kernel", "build_tables_kernel", "render_kernel")}
+mine = {k: v for k, v in d.items() if k in ("trace_kernel", "fold_volume_kernel", "build_map_kernel", "build_tables_kernel", "render_kernel")}
 tot = sum(sum(v) / len(v) for v in mine.values())
 with open(os.path.join(prof, tag + "_launches.md"), "w") as f:
-    f.write("# %s: ncu launch list (gpu__time_duration.sum, --clock-control none), `python bench.py --steps 10 --warmup 5`\n\n" % tag)
+    f.write("# %s: ncu launch list (gpu__time_duration.sum, --clock-control none), `python bench.py --steps 10 --warmup 5 --no-overlap`\n\n" % tag)
     f.write("Per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes.\n\n")
     f.write("| kernel | launches captured | avg us | share of a step (our kernels) |\n|---|---|---|---|\n")
     for k, v in d.items():
@@ -57,7 +57,7 @@ idx = {n: h.index(n) for n, _ in want if n in h}
 ni = h.index("Kernel Name")
 seen, traffic = {}, {}
 for r in rows[2:]:
-    k = r[ni].split("(")[0].replace("pm::", "")
+    k = re.sub(r"<.*", "", r[ni].split("(")[0].replace("pm::", "").replace("void ", ""))
     if k in seen:
         continue
     seen[k] = r
