@@ -28,6 +28,12 @@ rgb = torch.empty((64, 4), device="cuda")
 m.knn_radiance_cone(q, 64, 100, 0.7, 50.0, rgb)
 m.init_random_numbers_philox(7)
 m.clear_map(); m.trace(0.0, media=True); m.build_map()
+m.trace(0.0, media=True, split=True)                      # the two-launch form of the trace
+m.set_volume_warps(3); m.trace(0.0, media=True)           # fused, another warp split
+pin = [torch.empty((h, w, 4), dtype=torch.uint8).pin_memory() for _ in range(2)]
+tk = [m.frame_async(w, h, pin[i & 1], t=0.1 * i, emit=True, interp=True, media=True) for i in range(2)]   # pipelined frames
+for t_ in tk:
+    m.frame_wait(t_)
 m.sync()
 print("sanitize smoke ok: map sum %.4f, frame mean %.5f, knn frame mean %.5f" % (float(m.get_map().sum()), float(f32[..., :3].mean()), float(rgbf[..., :3].mean())))
 m.close()
