@@ -82,6 +82,8 @@ def lib():
             "pm_render": (i32, [vp, f32, b, b, i32, i32, i32, i32, vp, vp]),
             "pm_render_host": (i32, [vp, f32, b, b, i32, i32, vp, vp]),
             "pm_frame_host": (i32, [vp, f32, b, b, b, i32, i32, vp, vp]),
+            "launch_render_kernel": (None, [vp, C.c_uint, C.c_uint, f32, vp]),
+            "launch_kernel": (None, [vp, C.c_uint, C.c_uint, f32, vp, vp]),
             "pm_frame_host_async": (i32, [vp, f32, b, b, b, i32, i32, vp, C.POINTER(C.c_int64)]),
             "pm_frame_wait": (i32, [vp, C.c_int64]),
             "pm_launch_count": (i64, [vp]),
@@ -366,3 +368,12 @@ def launch_emit_photons_kernel(pos, image_width, image_height, animTime, interpo
 
 def launch_photon_mapping_kernel(pos, image_width, image_height, animTime, interpolateFlag, participatingMediaFlag):
     lib().launch_photon_mapping_kernel(_ptr(pos), image_width, image_height, animTime, interpolateFlag, participatingMediaFlag)
+
+
+# -- the older variant's two launchers (kernelPBO.cu:295, :317), declared but never called by simplePBO.cpp ------------
+def launch_render_kernel(pos, image_width, image_height, time, pixelData):
+    lib().launch_render_kernel(_ptr(pos), image_width, image_height, time, _ptr(pixelData))
+
+
+def launch_kernel(pos, image_width, image_height, time, numPhotons=None, photons=None):
+    lib().launch_kernel(_ptr(pos), image_width, image_height, time, _ptr(numPhotons), _ptr(photons))

@@ -37,6 +37,8 @@ cudaError_t launch_build_tables(const float *grid, float4 *vol_table, float4 *su
 cudaError_t launch_render(const DeviceScene &sc, const float4 *vol_table, const float4 *surf_table, int width, int height,
                           int y0, int y1, bool interp, bool media, uchar4 *rgba, float4 *rgbf, cudaStream_t st);
 
+cudaError_t launch_present_float3(const float *rgb, long long pixels, uchar4 *pos, cudaStream_t st);
+
 // pm_knn.cu -- Mode B photon map: sorted points + implicit 32-wide LBVH (see the file header)
 struct KnnMap {
   long long n = 0;                 // points in the map (after filtering)

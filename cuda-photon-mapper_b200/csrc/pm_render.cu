@@ -113,4 +113,22 @@ cudaError_t launch_render(const DeviceScene &sc, const float4 *vol_table, const 
   return cudaGetLastError();
 }
 
+// render_kernel of the older variant (kernelPBO.cu:268-291): float3 pixels -> uchar4, unscaled, device conversion semantics
+__global__ void __launch_bounds__(256) present_float3_kernel(const float *__restrict__ rgb, long long pixels, uchar4 *__restrict__ pos) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pixels) return;
+  uchar4 o;
+  o.x = (unsigned char)__float2uint_rz(rgb[3 * i + 0]);
+  o.y = (unsigned char)__float2uint_rz(rgb[3 * i + 1]);
+  o.z = (unsigned char)__float2uint_rz(rgb[3 * i + 2]);
+  o.w = 0;
+  pos[i] = o;
+}
+
+cudaError_t launch_present_float3(const float *rgb, long long pixels, uchar4 *pos, cudaStream_t st) {
+  if (pixels <= 0) return cudaSuccess;
+  present_float3_kernel<<<(unsigned)((pixels + 255) / 256), 256, 0, st>>>(rgb, pixels, pos);
+  return cudaGetLastError();
+}
+
 }  // namespace pm

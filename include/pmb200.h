@@ -49,6 +49,18 @@ void launch_emit_photons_kernel(pm_uchar4 *pos, unsigned int image_width, unsign
 void launch_photon_mapping_kernel(pm_uchar4 *pos, unsigned int image_width, unsigned int image_height,
                                   float animTime, bool interpolateFlag, bool participatingMediaFlag);
 
+/* The two launchers of the older variant (kernelPBO.cu), still declared by the caller (simplePBO.cpp:21-24) although
+ * every call site is commented out (simplePBO.cpp:118, :158, :176).  Provided so that the caller's declarations resolve.
+ * launch_render_kernel (kernelPBO.cu:295-313 + render_kernel :268-291): uploads a HOST array of image_width*image_height
+ * float3 pixels and writes pos[i] = {(unsigned char)r, (unsigned char)g, (unsigned char)b, 0} into the DEVICE buffer pos --
+ * no scaling, conversion as nvcc compiles it (cvt.rzi.u32.f32, low byte: negatives and NaN give 0, 300.0f gives 44).
+ * launch_kernel (kernelPBO.cu:317-359): its body is commented out in the reference; what remains -- synchronise, check
+ * for errors, leave pos untouched -- is what this does.  numPhotons / photons are never read. */
+void launch_render_kernel(pm_uchar4 *pos, unsigned int image_width, unsigned int image_height, float time,
+                          const float *pixelData /* float3[image_width * image_height], host */);
+void launch_kernel(pm_uchar4 *pos, unsigned int image_width, unsigned int image_height, float time,
+                   void *numPhotons /* int [][5] */, void *photons /* float *[2][5][5000][3] */);
+
 /* ------------------------------------------------------------------------------------------------
  * (2) Extended API
  * ---------------------------------------------------------------------------------------------- */

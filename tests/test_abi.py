@@ -26,7 +26,8 @@ def test_library_exports_every_declared_symbol(pm):
     lib = ctypes.CDLL(pm.LIB_PATH)
     names = declared_functions()
     assert {"launch_init_random_numbers_kernel", "launch_emit_photons_kernel", "launch_photon_mapping_kernel",
-            "pm_create", "pm_trace", "pm_render", "pm_frame_host"} <= set(names)
+            "launch_render_kernel", "launch_kernel", "pm_create", "pm_trace", "pm_render", "pm_frame_host", "pm_frame_host_async",
+            "pm_frame_wait"} <= set(names)
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
 

@@ -330,3 +330,25 @@ def test_pipelined_frames_equal_synchronous_frames(pm, oracle):
     with pytest.raises(pm.PmError):
         m.frame_wait(0)          # only the two most recent tickets can be waited for
     m.close()
+
+
+def test_older_variant_launchers(pm):
+    """launch_render_kernel (kernelPBO.cu:295 + render_kernel :268): host float3 pixels -> device uchar4, unscaled, with the
+    device's float -> unsigned char conversion (cvt.rzi.u32.f32, low byte); launch_kernel (kernelPBO.cu:317, body commented
+    out in the reference) leaves the buffer untouched."""
+    import torch
+    w, h = 37, 11
+    rng = np.random.default_rng(3)
+    px = rng.uniform(-50, 400, (h * w, 3)).astype(np.float32)
+    px[:8] = [[0, 255, 256], [-1, -0.5, 0.999], [np.nan, np.inf, -np.inf], [300, 511.9, 512], [1e10, 4294967296.0, 4294967040.0],
+              [254.999, 255.5, 1.5], [65535.7, 65536, 1e-30], [-1e-30, 2.0, 3.0]]
+    pos = torch.full((h, w, 4), 77, dtype=torch.uint8, device="cuda")
+    pm.launch_render_kernel(pos, w, h, 0.0, px)
+    got = pos.cpu().numpy().reshape(-1, 4)
+    with np.errstate(invalid="ignore"):
+        u = np.where(np.isnan(px), 0.0, np.clip(np.trunc(px.astype(np.float64)), 0.0, 4294967295.0)).astype(np.uint64)
+    assert np.array_equal(got[:, :3], (u & 0xFF).astype(np.uint8))
+    assert np.all(got[:, 3] == 0)
+    before = pos.clone()
+    pm.launch_kernel(pos, w, h, 0.0)
+    assert torch.equal(pos, before)
