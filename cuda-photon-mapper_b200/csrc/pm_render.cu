@@ -10,7 +10,7 @@
 namespace pm {
 
 __device__ __forceinline__ v3 vol_lookup(const float4 *__restrict__ vol_table, v3 p) {
-  int wx = voxel_x(p.x) - kVolLo, wy = voxel_x(p.y) - kVolLo, wz = voxel_z(p.z) - kVolLo;
+  int wx = voxel_x_wide(p.x) - kVolLo, wy = voxel_x_wide(p.y) - kVolLo, wz = voxel_z_wide(p.z) - kVolLo;   // exact in -2..34
   if ((unsigned)wx >= (unsigned)kVolN || (unsigned)wy >= (unsigned)kVolN || (unsigned)wz >= (unsigned)kVolN) return V(0.0f, 0.0f, 0.0f);
   float4 t = __ldg(vol_table + (wx * kVolN + wy) * kVolN + wz);
   return V(t.x, t.y, t.z);
@@ -19,7 +19,7 @@ __device__ __forceinline__ v3 vol_lookup(const float4 *__restrict__ vol_table, v
 // integrate() for the point p on wall `id` (PMK:314-389); spheres and unknown ids gather nothing
 __device__ __forceinline__ v3 surf_lookup(const float4 *__restrict__ surf_table, v3 p, int type, int id) {
   if (type != 1 || (unsigned)id >= (unsigned)PM_MAX_PLANES) return V(0.0f, 0.0f, 0.0f);
-  int wx = voxel_x(p.x), wy = voxel_x(p.y), wz = voxel_z(p.z);
+  int wx = voxel_x_wide(p.x), wy = voxel_x_wide(p.y), wz = voxel_z_wide(p.z);
   // an empty window on the wall's own axis cannot happen (the slab index is forced), only in-plane coords matter
   int a = (id == 0 || id == 2) ? wy : wx;
   int b = (id == 4) ? wy : wz;

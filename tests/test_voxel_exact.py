@@ -104,3 +104,43 @@ def test_div65535_constant_reciprocal_is_correctly_rounded():
         subprocess.check_call(["make", "-C", os.path.dirname(exe), "check_div65535"])
     out = subprocess.run([exe, "61"], capture_output=True, text=True, check=True).stdout.split()
     assert int(out[0]) == 0 and int(out[1]) > 70_000_000
+
+
+def _div3_trunc(n):
+    return np.where(n >= 0, (n * 43691) >> 17, -((-n * 43691) >> 17))
+
+
+def wide_x(p):
+    """voxel_x_wide (csrc/pm_math.cuh): clamp(voxel, -3, 36) in FP32 + integer arithmetic, NaN -> 0"""
+    with np.errstate(invalid="ignore"):
+        u = np.float32(32.0) * p
+        u = (u.astype(np.float64) + 2.0 ** -48).astype(np.float32)
+        u = np.where(np.isnan(u), np.float32(-48.0), np.clip(u, np.float32(-57.0), np.float32(60.0)))
+        n = np.where(u >= -48.0, np.floor(u), np.ceil(u)).astype(np.int64) + 48
+    return _div3_trunc(n)
+
+
+def wide_z(p):
+    with np.errstate(invalid="ignore"):
+        u = np.float32(16.0) * p
+        u = np.where(np.isnan(u), np.float32(0.0), np.clip(u, np.float32(-9.0), np.float32(108.0)))
+        n = np.where(u >= 0.0, np.floor(u), np.ceil(u)).astype(np.int64)
+    return _div3_trunc(n)
+
+
+def test_wide_voxel_matches_literal_form():
+    p = _samples()
+    tiny = (-(2.0 ** -rng_exponents())).astype(np.float32)
+    extra = np.float32([1e9, -1e9, 3e38, -3e38, np.inf, -np.inf, np.nan, 0.0, -0.0, -1.5, -1.59375, -1.78125, 2.0, 1.875, 1.96875,
+                        -0.5625, -1.6875, 6.75, 6.5625])
+    q = (np.arange(-4 * 4096, 9 * 4096, dtype=np.int64) / 4096.0).astype(np.float32)
+    p = np.concatenate([p, tiny, -tiny, extra, q])
+
+    def sat(v):   # cvt.rzi.s32.f64: saturating, NaN -> 0
+        with np.errstate(invalid="ignore"):
+            return np.where(np.isnan(v), 0.0, np.clip(np.trunc(v), -2.0 ** 31, 2.0 ** 31 - 1)).astype(np.int64)
+    with np.errstate(invalid="ignore", over="ignore"):
+        lit_x = sat(((p.astype(np.float64) + 1.5) / 3.0) * 32)
+        lit_z = sat((p.astype(np.float64) / 6.0) * 32)
+    assert np.array_equal(np.clip(lit_x, -3, 36), wide_x(p))
+    assert np.array_equal(np.clip(lit_z, -3, 36), wide_z(p))
