@@ -20,7 +20,7 @@ LIB_PATH = os.environ.get("PMB200_LIB") or os.path.join(_HERE, "libpmb200.so")  
 PM_TRACE_MEDIA, PM_TRACE_RECORDS, PM_TRACE_NO_MAP, PM_TRACE_SPLIT = 1, 2, 4, 8
 GRID_N = 32
 ACC_HIT_ENTRIES = 5 * 32 * 32 * 4
-ACC_ENTRIES = ACC_HIT_ENTRIES + 32 * 32 * 32 * 3 + 8 * 32 * 32 * 32
+ACC_ENTRIES = ACC_HIT_ENTRIES + 32 * 32 * 32 * 3 + 32 * 32 * 32   # pm_layout.h: hit + vox rgb + grey
 
 RECORD_DTYPE = np.dtype([("type", "<i4"), ("id", "<i4"), ("index", "<i4"), ("kind", "<i4"),
                          ("loc", "<f4", 3), ("dir", "<f4", 3), ("energy", "<f4", 3)])

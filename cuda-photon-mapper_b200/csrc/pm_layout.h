@@ -13,14 +13,15 @@ namespace pm {
 //                                      r == g == b goes to the grey slot (one atomic instead of three)
 // acc_vox[x][y][z][rgb]              : everything that is deposited straight into a voxel with unequal channels,
 //                                      and the fully expanded splat of the rare off-slab hit (scale 2^36)
-// acc_grey[replica][x][y][z]         : straight deposits with r == g == b -- every volume photon of the reference's
-//                                      medium walk (scale 2^36).  Replicated kGreyReplicas times (a CTA picks a replica
-//                                      by its index) because 50M L2 atomics onto a few thousand hot lines serialise.
+// acc_grey[x][y][z]                 : straight deposits with r == g == b -- every volume photon of the reference's
+//                                      medium walk (scale 2^36).  Written by fold_volume_kernel only (one thread per voxel):
+//                                      the walk itself counts into the replicated 32-bit vol_cnt below, so the exchanged
+//                                      state stays 1.2 MB (it was 3 MB while the 64-bit atomics needed 8 replicas here).
 constexpr int    kAccHitEntries = PM_MAX_PLANES * PM_GRID_N * PM_GRID_N * 4;   // 20 480
 constexpr int    kAccVoxEntries = PM_GRID_VOXELS * 3;                          // 98 304
-constexpr int    kGreyReplicas  = 8;
-constexpr int    kAccGreyEntries = kGreyReplicas * PM_GRID_VOXELS;             // 262 144
-constexpr int    kAccEntries    = kAccHitEntries + kAccVoxEntries + kAccGreyEntries;   // 380 928 int64 = 3 047 424 B
+constexpr int    kGreyReplicas  = 1;
+constexpr int    kAccGreyEntries = kGreyReplicas * PM_GRID_VOXELS;             // 32 768
+constexpr int    kAccEntries    = kAccHitEntries + kAccVoxEntries + kAccGreyEntries;   // 151 552 int64 = 1 212 416 B
 // Scratch for the medium walk: its deposits carry one of three energies (9, 8, 7 x 0.00005, a function of the step only),
 // so volume_kernel COUNTS them -- 32-bit REDs, twice the L2 rate of 64-bit ones -- in vol_cnt[replica][step][voxel] and
 // fold_volume_kernel adds count x quantum (exact integers) to acc_grey and clears the counts.  Not part of the accumulator
