@@ -504,11 +504,12 @@ def main():
         dom_bytes = alg.get(dom, 0.0)
         dom_ms = kern[dom]["avg_ms"]
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
-        traffic = None
-        try:   # DRAM bytes per launch from the committed ncu --set full capture of the same configuration
+        traffic, issue_pct = None, None
+        try:   # DRAM bytes per launch / issue-slot utilisation from the committed ncu --set full capture of the same configuration
             prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
             if prof.get("photons") == NP and world == 1:
                 traffic = prof["dram_bytes_per_launch"].get(dom)
+                issue_pct = prof.get("issue_slots_busy_pct", {}).get(dom)
         except Exception:
             pass
         line = {
@@ -532,6 +533,7 @@ def main():
             "roofline": {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_ms,
+                         "issue_slots_busy_pct_ncu": issue_pct,   # the resource the kernel is actually bound by (profiles/, not live)
                          "note": "Mode A keeps no photon records, so the compulsory HBM traffic of the fused trace kernel is one 12 B "
                                  "direction per photon: its surface warps are instruction-issue bound and its medium-walk warps "
                                  "L2-atomic bound (3 REDs per photon), not HBM bound; see DESIGN.md 'rooflines' and profiles/"},

@@ -77,5 +77,12 @@ def to_bytes(v, u):
 for k, r in seen.items():
     a, b = h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
     traffic[k] = to_bytes(r[a], units[a]) + to_bytes(r[b], units[b])
-json.dump({"photons": photons, "source": tag + "_full.ncu-rep", "dram_bytes_per_launch": traffic}, open(os.path.join(prof, "ncu_traffic.json"), "w"), indent=1)
+issue = {}
+for k, r in seen.items():
+    try:
+        issue[k] = float(r[idx["smsp__issue_active.avg.pct_of_peak_sustained_active"]])
+    except (KeyError, ValueError):
+        pass
+json.dump({"photons": photons, "source": tag + "_full.ncu-rep", "dram_bytes_per_launch": traffic, "issue_slots_busy_pct": issue},
+          open(os.path.join(prof, "ncu_traffic.json"), "w"), indent=1)
 print(open(os.path.join(prof, tag + "_kernels.md")).read())
