@@ -29,12 +29,12 @@ for r in rows[1:]:
 mine = {k: v for k, v in d.items() if k in ("trace_kernel", "fold_volume_kernel", "build_map_kernel", "build_tables_kernel", "render_kernel")}
 tot = sum(sum(v) / len(v) for v in mine.values())
 with open(os.path.join(prof, tag + "_launches.md"), "w") as f:
-    f.write("# %s: ncu launch list (gpu__time_duration.sum, --clock-control none), `python bench.py --steps 10 --warmup 5 --no-overlap`\n\n" % tag)
+    f.write("# %s: ncu launch list (gpu__time_duration.sum, --clock-control none), `python bench.py --steps 10 --warmup 5 --no-ref-cuda --no-cpu-baseline --no-mode-b` (tools/profile_r1.sh)\n\n" % tag)
     f.write("Per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes.\n\n")
     f.write("| kernel | launches captured | avg us | share of a step (our kernels) |\n|---|---|---|---|\n")
     for k, v in d.items():
         a = sum(v) / len(v)
-        f.write("| %s | %d | %.1f | %s |\n" % (k[:70], len(v), a, ("%.1f%%" % (100 * a / tot)) if k in mine else "(torch / memset)"))
+        f.write("| %s | %d | %.1f | %s |\n" % (k[:70], len(v), a, ("%.1f%%" % (100 * a / tot)) if k in mine else ("(one-off table fill, outside the step)" if k == "mwc_table_kernel" else "(torch / memset)")))
 print(open(os.path.join(prof, tag + "_launches.md")).read())
 
 # ---- full capture -----------------------------------------------------------------------------------------
