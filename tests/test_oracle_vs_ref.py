@@ -8,9 +8,13 @@ import pytest
 from tests.util import bits_equal, cfg1_scene
 
 CFG1_PLANES = np.array([[0, 1e9], [1, -1.5], [0, -1e9], [1, 1e9], [2, 1e9]], np.float32)
+# back wall at z = 5 as in the legacy variant ("photonMappingKernel - Copy.cu":28): hits in voxel slab 26, off the slab 31 that
+# splatEnergy hard-codes for plane 4 -- the case the CUDA path expands per photon (store_photon's off-slab branch)
+BACKWALL5_PLANES = np.array([[0, 1.5], [1, -1.5], [0, -1.5], [1, 1.5], [2, 5.0]], np.float32)
 
 
-@pytest.mark.parametrize("scene_name,t,media", [("default", 0.0, False), ("default", 2.3, True), ("cfg1", 1.1, True)])
+@pytest.mark.parametrize("scene_name,t,media", [("default", 0.0, False), ("default", 2.3, True), ("cfg1", 1.1, True),
+                                                 ("backwall5", 0.7, True)])
 def test_frame_bit_exact(oracle, refhost, scene_name, t, media):
     n, w, h = 30000, 96, 96
     table, st = oracle.mwc_table(n)
@@ -19,6 +23,9 @@ def test_frame_bit_exact(oracle, refhost, scene_name, t, media):
     if scene_name == "cfg1":
         cfg1_scene(sc)
         refhost.set_scene(nr_objects=(1, 5), planes=CFG1_PLANES, sz_img=w)
+    elif scene_name == "backwall5":
+        sc.planes[4][1] = 5.0
+        refhost.set_scene(planes=BACKWALL5_PLANES, sz_img=w)
     else:
         refhost.set_scene(sz_img=w)
     refhost.set_table(table); refhost.set_rng(*st); refhost.clear_grid()
