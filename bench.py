@@ -132,6 +132,10 @@ def cpu_reference_frame_ms(a, photon_div=16, row_div=8):
     table, st = orc.mwc_table(n_s)
     if refhost.available():
         r = refhost.RefHost()
+        try:   # all the host cores this process may run on, whatever OMP_NUM_THREADS a launcher (torchrun: 1) exported
+            r.omp_set_threads(len(os.sched_getaffinity(0)))
+        except AttributeError:
+            r.omp_set_threads(os.cpu_count() or 1)
         cores = r.omp_threads()
         r.set_scene(sz_img=a.height)
         r.set_table(table); r.set_rng(*st); r.clear_grid()

@@ -59,6 +59,11 @@ class RefHost:
     def omp_threads(self):
         return self.lib.ref_omp_threads()
 
+    def omp_set_threads(self, n):
+        """Use n OpenMP threads from now on (a launcher may have exported OMP_NUM_THREADS=1)."""
+        if hasattr(self.lib, "ref_omp_set_threads"):
+            self.lib.ref_omp_set_threads(int(n))
+
     def set_scene(self, nr_objects=(2, 5), planes=None, spheres=None, light=None, sz_img=512):
         n = np.array(nr_objects, dtype=np.int32)
         p = np.ascontiguousarray(DEFAULT_PLANES if planes is None else planes, dtype=np.float32)
