@@ -39,6 +39,8 @@ def main():
     ap.add_argument("rep"); ap.add_argument("lib"); ap.add_argument("kernel")
     ap.add_argument("--top", type=int, default=40)
     ap.add_argument("--sass", action="store_true", help="also list the hottest individual SASS instructions")
+    ap.add_argument("--sym", default=None, help="substring of the MANGLED symbol whose SASS the capture maps to (default: the kernel name); "
+                                                 "needed when several instantiations share the name, e.g. trace_kernelILb0")
     a = ap.parse_args()
     out = subprocess.run(["ncu", "-i", a.rep, "--page", "source", "--csv", "-k", "regex:" + a.kernel], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
@@ -46,7 +48,7 @@ def main():
     body = [r for r in rows if len(r) == len(hdr) and r[0] != "Address"]
     ia, isamp, iex, ithr = hdr.index("Address"), hdr.index("# Samples"), hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed")
     stall_cols = [i for i, h in enumerate(hdr) if h.startswith("stall_")]
-    tab = line_table(a.lib, a.kernel)
+    tab = line_table(a.lib, a.sym or a.kernel)
     base = min(int(r[ia], 16) for r in body)
     agg = collections.defaultdict(lambda: [0.0, 0.0, 0.0, collections.Counter()])
     sass = []
