@@ -48,6 +48,9 @@ def parse():
     ap.add_argument("--knn", type=int, default=50, help="k of the Mode B estimate")
     ap.add_argument("--no-overlap", action="store_true",
                     help="Mode A: do not overlap a frame's render + frame gather (side stream) with the next frame's trace")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="Mode A, N > 1: how the accumulators are summed -- peer (default): our kernel pulls them over NVLink peer "
+                         "memory inside pm_build_map (CUDA IPC between the ranks); nccl: dist.all_reduce (round 1's path)")
     ap.add_argument("--passes", type=int, default=1,
                     help="progressive photon mapping (BASELINE config 5): photon passes accumulated per frame, each with a fresh "
                          "direction table from the continuing MWC stream (Mode A)")
@@ -119,9 +122,14 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------
 # CPU baseline / reference arm: the reference's own routines on the host cores (oracle/_ref), bounded sample
 # ------------------------------------------------------------------------------------------------------
-def cpu_reference_frame_ms(a, photon_div=16, row_div=8):
-    """Returns (estimated ms/frame, descriptor dict).  Sample: photons/photon_div traced + height/row_div rows
-    rendered, each scaled back to the whole frame."""
+_TABLE_CACHE = {}
+
+
+def cpu_reference_frame_ms(a, photon_div=1, row_div=1):
+    """Returns (ms/frame, descriptor dict) of the reference's own routines on the host cores.  photon_div = row_div = 1:
+    the whole frame of the bench configuration, nothing extrapolated.  Larger divisors (only used when the reference
+    library is absent and the sequential port has to stand in): photons/photon_div traced + height/row_div rows rendered,
+    each scaled back to the whole frame."""
     from oracle import oraclelib, refhost
     if not oraclelib.available():
         import subprocess
@@ -129,7 +137,10 @@ def cpu_reference_frame_ms(a, photon_div=16, row_div=8):
     orc = oraclelib.Oracle()
     n_s = max(a.photons // photon_div, 1000)
     rows = max(a.height // row_div, 1)
-    table, st = orc.mwc_table(n_s)
+    if n_s not in _TABLE_CACHE:                   # the direction table is an input of the frame, generated once (display(): first frame only)
+        _TABLE_CACHE.clear()
+        _TABLE_CACHE[n_s] = orc.mwc_table(n_s)
+    table, st = _TABLE_CACHE[n_s]
     if refhost.available():
         r = refhost.RefHost()
         try:   # all the host cores this process may run on, whatever OMP_NUM_THREADS a launcher (torchrun: 1) exported
@@ -159,32 +170,39 @@ def cpu_reference_frame_ms(a, photon_div=16, row_div=8):
         kind = "port"
     emit_ms = (t1 - t0) * 1e3 * (a.photons / n_s)
     render_ms = (t2 - t1) * 1e3 * (a.height / rows)
-    return emit_ms + render_ms, {
-        "kind": kind, "cores": cores,
-        "sample": "%d of %d photons traced (x%.0f) + %d of %d rows rendered (x%.0f), media on; %s" % (
-            n_s, a.photons, a.photons / n_s, rows, a.height, a.height / rows,
-            "reference routines (photonMappingKernel.cu:1-1521) as host C++ with OpenMP" if kind == "reference"
-            else "sequential oracle port (oracle/_ref absent)"),
-        "emit_ms_scaled": emit_ms, "render_ms_scaled": render_ms}
+    what = ("reference routines (photonMappingKernel.cu:1-1521) as host C++ with OpenMP" if kind == "reference"
+            else "sequential oracle port (oracle/_ref absent)")
+    if n_s == a.photons and rows == a.height:
+        sample = "the whole frame: %d photons traced + %d rows rendered, media on; %s" % (n_s, rows, what)
+    else:
+        sample = "%d of %d photons traced (x%.0f) + %d of %d rows rendered (x%.0f), media on; %s" % (
+            n_s, a.photons, a.photons / n_s, rows, a.height, a.height / rows, what)
+    return emit_ms + render_ms, {"kind": kind, "cores": cores, "sample": sample, "emit_ms": emit_ms, "render_ms": render_ms,
+                                 "whole_frame": n_s == a.photons and rows == a.height}
 
 
 def run_reference_arm(a):
+    """bench.py --impl reference: the reference's own CPU implementation of the path, every host thread, on the SAME
+    configuration (every step traces all the photons and renders all the rows: nothing is sampled or extrapolated)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from oracle import refhost
+    div = (1, 1) if refhost.available() else (64, 16)     # the single-threaded port cannot run 16M photons per step in minutes
     vals, walls = [], []
     desc = None
     for i in range(a.warmup + a.steps):
         t0 = time.perf_counter()
-        v, desc = cpu_reference_frame_ms(a, photon_div=64, row_div=16)
+        v, desc = cpu_reference_frame_ms(a, *div)
         if i >= a.warmup:
             vals.append(v); walls.append((time.perf_counter() - t0) * 1e3)
     v = float(np.mean(vals))
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "ms", "n_gpus": a.gpus, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": float(np.mean(walls)), "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+            "warmup": a.warmup, "ms_per_step": v, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(a),
-            "note": "value = ms/frame estimated from the bounded sample each step runs (see cpu_baseline.sample); ms_per_step = wall "
-                    "time of one such sample step, table generation included",
+            "note": "value = emit + render of one whole frame of the configuration (inputs resident in host memory, table generated "
+                    "once); step wall time incl. clearing the grid: %.1f ms" % float(np.mean(walls)),
+            "same_config": bool(desc["whole_frame"]),
             "cpu_baseline": {"value": v, "unit": "ms", "cores": desc["cores"], "kind": desc["kind"], "sample": desc["sample"]},
             "e2e": {"value": v, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -329,8 +347,28 @@ def main():
     y0, y1 = pmdist.row_band(H, rank, world)
     rows = y1 - y0
 
-    rgba = torch.zeros((H, W, 4), dtype=torch.uint8, device="cuda")
-    rgbf = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
+    # Mode A, N > 1: the ranks' exchange blocks are mapped into each other (CUDA IPC) and the frame lives on rank 0, every
+    # rank rendering its row band straight into it over NVLink
+    peers = False
+    if world > 1 and a.mode == "a" and a.exchange == "peer":
+        ok = torch.ones(1, device="cuda")
+        try:
+            pmdist.connect_peers(m)
+        except pmb200.PmError as ex:
+            print("rank %d: peer connect failed (%s), falling back to NCCL" % (rank, ex), file=sys.stderr)
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        peers = bool(ok.item() > 0)
+        if not peers:
+            m.peer_disconnect()
+    if peers:
+        rgba_ptr, rgba_opened = pmdist.shared_frame(m, W * H * 4)
+        rgbf_ptr, rgbf_opened = pmdist.shared_frame(m, W * H * 16)
+        rgba = pmdist.device_tensor(rgba_ptr, W * H * 4, "|u1").view(H, W, 4) if rank == 0 else rgba_ptr
+        rgbf = pmdist.device_tensor(rgbf_ptr, W * H * 4, "<f4").view(H, W, 4) if rank == 0 else rgbf_ptr
+    else:
+        rgba = torch.zeros((H, W, 4), dtype=torch.uint8, device="cuda")
+        rgbf = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
     acc_ptr, acc_n = m.accumulators()
     acc = pmdist.device_tensor(acc_ptr, acc_n, "<i8")
 
@@ -389,27 +427,32 @@ def main():
             m.init_random_numbers()
             m.trace(0.0, media=True)
         if e: e[1].record()
-        pmdist.allreduce_accumulators(acc)        # exact: int64 sum over NVLink (no-op at N=1)
+        if not peers:
+            pmdist.allreduce_accumulators(pmdist.device_tensor(m.accumulators()[0], acc_n, "<i8"))   # NCCL (no-op at N=1)
         if e: e[2].record()
         if overlap and state["pending"]:
             main_stream.wait_event(ev_rendered)   # the previous frame's render still reads the tables
-        m.build_map()
+        m.build_map()                             # peers: the exchange happens in here (peer_reduce_kernel)
         if e: e[3].record()
+
+        def render_and_assemble():
+            m.render_device(W, H, 0.0, False, True, rgba=rgba, rgbf=rgbf, y0=y0, y1=y1)
+            if peers:
+                m.peer_barrier()                  # every rank's band has landed in rank 0's frame buffers
+            else:
+                pmdist.gather_frame(rgba, y0, y1)
+                pmdist.gather_frame(rgbf, y0, y1)
         if overlap:
             ev_built.record(main_stream)
             side.wait_event(ev_built)
             m.set_stream(side.cuda_stream)
             with torch.cuda.stream(side):
-                m.render_device(W, H, 0.0, False, True, rgba=rgba, rgbf=rgbf, y0=y0, y1=y1)
+                render_and_assemble()
                 ev_rendered.record(side)
-                pmdist.gather_frame(rgba, y0, y1)
-                pmdist.gather_frame(rgbf, y0, y1)
             m.set_stream(main_stream.cuda_stream)
             state["pending"] = True
         else:
-            m.render_device(W, H, 0.0, False, True, rgba=rgba, rgbf=rgbf, y0=y0, y1=y1)
-            pmdist.gather_frame(rgba, y0, y1)
-            pmdist.gather_frame(rgbf, y0, y1)
+            render_and_assemble()
         if e: e[4].record()
 
     step = step_b if a.mode == "b" else step_a
@@ -432,6 +475,8 @@ def main():
     t_beg.record()
     for i in range(a.steps):
         step(ev[i])
+    if side is not None:
+        main_stream.wait_stream(side)             # the last frame's render (+ assembly) is inside the timed span
     t_end.record()
     barrier()
     launches = m.launch_count() - launches0

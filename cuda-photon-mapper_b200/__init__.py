@@ -85,10 +85,24 @@ def lib():
             "launch_render_kernel": (None, [vp, C.c_uint, C.c_uint, f32, vp]),
             "launch_kernel": (None, [vp, C.c_uint, C.c_uint, f32, vp, vp]),
             "pm_frame_host_async": (i32, [vp, f32, b, b, b, i32, i32, vp, C.POINTER(C.c_int64)]),
-            "pm_frame_wait": (i32, [vp, C.c_int64]),
+            "pm_frame_wait": (i32, [vp, C.c_int64]), "pm_reserve_frame": (i32, [vp, i32, i32]),
             "pm_launch_count": (i64, [vp]),
             "pm_enable_timing": (i32, [vp, b]), "pm_kernel_count": (i32, []), "pm_kernel_name": (C.c_char_p, [i32]),
             "pm_get_timings": (i32, [vp, vp, vp]),
+            "pm_peer_export": (i32, [vp, vp]), "pm_peer_connect": (i32, [vp, i32, i32, vp]),
+            "pm_peer_connect_local": (i32, [vp, i32, i32, C.POINTER(vp)]), "pm_peer_disconnect": (i32, [vp]),
+            "pm_peer_info": (i32, [vp, C.POINTER(i32), C.POINTER(i32)]), "pm_peer_barrier": (i32, [vp]), "pm_peer_status": (i32, [vp]),
+            "pm_peer_set_timeout": (i32, [vp, C.c_double]),
+            "pm_shared_alloc": (i32, [vp, C.c_size_t, C.POINTER(vp), vp]), "pm_shared_open": (i32, [vp, vp, C.POINTER(vp)]),
+            "pm_shared_close": (i32, [vp, vp, b]), "pm_set_row_band": (i32, [vp, i32, i32]),
+            "pm_group_create": (i32, [C.POINTER(vp), C.POINTER(i32), i32]), "pm_group_destroy": (i32, [vp]), "pm_group_size": (i32, [vp]),
+            "pm_group_context": (vp, [vp, i32]), "pm_group_last_error": (C.c_char_p, [vp]),
+            "pm_group_set_scene": (i32, [vp, C.POINTER(Scene)]), "pm_group_set_photon_count": (i32, [vp, i64]),
+            "pm_group_set_energy_scale": (i32, [vp, f32]), "pm_group_init_random_table": (i32, [vp]),
+            "pm_group_frame_host": (i32, [vp, f32, b, b, b, i32, i32, vp, vp]),
+            "pm_group_frame_host_async": (i32, [vp, f32, b, b, b, i32, i32, vp, C.POINTER(C.c_int64)]),
+            "pm_group_frame_wait": (i32, [vp, C.c_int64]),
+            "pm_trace_profile": (i32, [vp, b]), "pm_get_trace_profile_host": (i32, [vp, vp, i64, C.POINTER(i64)]),
             "launch_init_random_numbers_kernel": (None, []),
             "launch_emit_photons_kernel": (None, [vp, C.c_uint, C.c_uint, f32, b, b]),
             "launch_photon_mapping_kernel": (None, [vp, C.c_uint, C.c_uint, f32, b, b]),
@@ -124,8 +138,12 @@ def _ptr(a):
 class PhotonMapper:
     """One pm_context: a photon mapper bound to one GPU and one stream."""
 
-    def __init__(self, device=-1, n_photons=10000, scene=None):
+    def __init__(self, device=-1, n_photons=10000, scene=None, _borrowed=None):
         self.L = lib()
+        if _borrowed is not None:       # a rank of a PhotonGroup: the group owns the context
+            self.h, self.n_photons, self._owned = C.c_void_p(_borrowed), n_photons, False
+            return
+        self._owned = True
         h = C.c_void_p()
         rc = self.L.pm_create(C.byref(h), device)
         if rc != 0:
@@ -138,7 +156,8 @@ class PhotonMapper:
 
     def close(self):
         if getattr(self, "h", None):
-            self.L.pm_destroy(self.h)
+            if self._owned:
+                self.L.pm_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -355,6 +374,119 @@ class PhotonMapper:
         ms = np.zeros(n, np.float64); cnt = np.zeros(n, np.int64)
         self._ck(self.L.pm_get_timings(self.h, _ptr(ms), _ptr(cnt)))
         return {self.L.pm_kernel_name(k).decode(): (float(ms[k]), int(cnt[k])) for k in range(n)}
+
+
+    # -- multi-GPU: peers (pm_peer_*) ---------------------------------------------------------
+    def peer_export(self):
+        """64-byte CUDA IPC handle of this context's exchange block (accumulators + flags), as bytes."""
+        buf = C.create_string_buffer(64)
+        self._ck(self.L.pm_peer_export(self.h, buf))
+        return buf.raw
+
+    def peer_connect(self, rank, world, handles):
+        """handles: list of `world` 64-byte handles (entry [rank] is ignored).  pm_build_map then sums the accumulators of all
+        ranks over peer memory; every rank must step through the frames in lockstep."""
+        blob = b"".join(h if h is not None else b"\0" * 64 for h in handles)
+        assert len(blob) == 64 * world
+        self._ck(self.L.pm_peer_connect(self.h, rank, world, blob))
+
+    def peer_disconnect(self):
+        self._ck(self.L.pm_peer_disconnect(self.h))
+
+    def peer_barrier(self):
+        self._ck(self.L.pm_peer_barrier(self.h))
+
+    def peer_status(self):
+        self._ck(self.L.pm_peer_status(self.h))
+
+    def peer_set_timeout(self, seconds):
+        self._ck(self.L.pm_peer_set_timeout(self.h, seconds))
+
+    def shared_alloc(self, nbytes):
+        """(device pointer, 64-byte handle) of device memory other ranks can map with shared_open."""
+        p, buf = C.c_void_p(), C.create_string_buffer(64)
+        self._ck(self.L.pm_shared_alloc(self.h, nbytes, C.byref(p), buf))
+        return p.value, buf.raw
+
+    def shared_open(self, handle):
+        p = C.c_void_p()
+        self._ck(self.L.pm_shared_open(self.h, handle, C.byref(p)))
+        return p.value
+
+    def shared_close(self, ptr, opened):
+        self._ck(self.L.pm_shared_close(self.h, C.c_void_p(ptr), opened))
+
+    def set_row_band(self, y0=-1, y1=-1):
+        self._ck(self.L.pm_set_row_band(self.h, y0, y1))
+
+    def trace_profile(self, on=True):
+        self._ck(self.L.pm_trace_profile(self.h, on))
+
+    def get_trace_profile(self):
+        """[CTAs, 48] uint64 %globaltimer stamps of the last trace launch (see pmb200.h)."""
+        out = np.zeros(48 * 1024, np.uint64)
+        n = C.c_int64()
+        self._ck(self.L.pm_get_trace_profile_host(self.h, _ptr(out), out.size, C.byref(n)))
+        return out[:n.value].reshape(-1, 48)
+
+
+class PhotonGroup:
+    """pm_group: n GPUs behind one object, for a single-process host program (one worker thread per GPU inside the library)."""
+
+    def __init__(self, devices, n_photons=10000, scene=None):
+        self.L = lib()
+        g = C.c_void_p()
+        arr = (C.c_int * len(devices))(*devices)
+        rc = self.L.pm_group_create(C.byref(g), arr, len(devices))
+        if rc != 0:
+            raise PmError({-4: "no CUDA device: pmb200 has no CPU fallback"}.get(rc, f"pm_group_create failed ({rc})"))
+        self.g, self.n = g, len(devices)
+        self.set_photon_count(n_photons)
+        if scene is not None:
+            self.set_scene(scene)
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise PmError(f"pmb200 group error {rc}: {self.L.pm_group_last_error(self.g).decode()}")
+
+    def close(self):
+        if getattr(self, "g", None):
+            self.L.pm_group_destroy(self.g)
+            self.g = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def rank(self, r):
+        """The context of rank r as a (borrowed) PhotonMapper, for inspection."""
+        return PhotonMapper(_borrowed=self.L.pm_group_context(self.g, r), n_photons=self.n_photons)
+
+    def set_scene(self, scene):
+        self._ck(self.L.pm_group_set_scene(self.g, C.byref(scene)))
+
+    def set_photon_count(self, n):
+        self._ck(self.L.pm_group_set_photon_count(self.g, n))
+        self.n_photons = n
+
+    def set_energy_scale(self, s):
+        self._ck(self.L.pm_group_set_energy_scale(self.g, s))
+
+    def init_random_numbers(self):
+        self._ck(self.L.pm_group_init_random_table(self.g))
+
+    def frame(self, w, h, t=0.0, emit=True, interp=False, media=False, out_u8=None, out_f32=None):
+        self._ck(self.L.pm_group_frame_host(self.g, t, emit, interp, media, w, h, _ptr(out_u8), _ptr(out_f32)))
+
+    def frame_async(self, w, h, out_u8, t=0.0, emit=True, interp=False, media=False):
+        tk = C.c_int64()
+        self._ck(self.L.pm_group_frame_host_async(self.g, t, emit, interp, media, w, h, _ptr(out_u8), C.byref(tk)))
+        return tk.value
+
+    def frame_wait(self, ticket):
+        self._ck(self.L.pm_group_frame_wait(self.g, ticket))
 
 
 # -- the reference's three launchers, verbatim names (process-global default context) --------------------

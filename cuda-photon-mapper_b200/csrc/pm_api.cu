@@ -12,98 +12,7 @@
 #include <string>
 #include <vector>
 
-#include "pm_kernels.cuh"
-
-using namespace pm;
-
-struct pm_context {
-  int device = 0;
-  int num_sms = 148;
-  cudaStream_t stream = nullptr;
-  std::string err;
-
-  pm_scene scene;
-  DeviceScene dsc;                 // as of the last launch (after positionObjects)
-  int64_t n_photons = 0;           // nrPhotons == table length
-  int64_t first = 0, last = 0;     // photon range traced by this context
-  float energy_scale = 1.0f;
-
-  float4 *d_table = nullptr;       // one row per photon: (x, y, z, 0)
-  int64_t table_first = 0, table_last = 0;   // rows generated by the last pm_init_random_table (a sharded rank fills only its range)
-  int64_t table_cap = 0;
-  uint32_t mwc_w = PM_MWC_SEED_W, mwc_z = PM_MWC_SEED_Z;
-  MwcJump *d_jump = nullptr;
-
-  long long *d_acc = nullptr;      // kAccEntries int64
-  uint32_t *d_vol_cnt = nullptr;   // kVolCntEntries, zero between launches (pm_layout.h)
-  int vol_warps = 6;               // warps per CTA that run the medium walk in the fused trace kernel
-  float *d_grid = nullptr;         // PM_GRID_FLOATS
-  float4 *d_vol = nullptr, *d_surf = nullptr;
-  bool tables_valid = false;
-
-  // photon records: [0] surface set (appended, cursor d_rec_count), [1] volume set (fixed slots)
-  float4 *d_rec_pos = nullptr, *d_rec_pow = nullptr, *d_rec_dir = nullptr;
-  unsigned long long *d_rec_count = nullptr;
-  int64_t rec_cap = 0;
-  float4 *d_vrec_pos = nullptr, *d_vrec_pow = nullptr;
-  int64_t vrec_cap = 0, vrec_count = 0;
-
-  KnnMap knn[2];                   // Mode B maps: surface, volume
-  unsigned long long *d_work = nullptr;   // work counter of the Mode B renderer
-  int knn_curve = PM_CURVE_HILBERT;
-
-  uchar4 *d_fb_u8 = nullptr;
-  float4 *d_fb_f32 = nullptr;
-  int64_t fb_pixels = 0;
-  // pipelined frames (pm_frame_host_async): two device frame buffers, a copy stream, per-buffer events
-  cudaStream_t copy_stream = nullptr;
-  uchar4 *d_fb_async[2] = {nullptr, nullptr};
-  cudaEvent_t ev_rendered[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
-  int64_t async_pixels = 0, next_ticket = 0;
-
-  int64_t launches = 0;
-
-  // optional per-kernel CUDA-event timing (pm_enable_timing): pairs recorded on the context's stream
-  bool timing = false;
-  struct Span { cudaEvent_t a, b; int kind; };
-  std::vector<Span> spans;
-  size_t spans_used = 0;
-};
-
-enum { K_MWC_TABLE = 0, K_VOLUME, K_SURFACE, K_BUILD_MAP, K_BUILD_TABLES, K_RENDER, K_KNN_BUILD, K_KNN_QUERY, K_KNN_RENDER, K_COUNT };
-static const char *const kKernelNames[K_COUNT] = {"mwc_table_kernel", "volume_kernel", "trace_kernel", "build_map_kernel",
-                                                   "build_tables_kernel", "render_kernel", "knn_build (all kernels)",
-                                                   "knn_query_kernel", "knn_render_kernel"};
-
-// RAII span: records an event pair around one kernel launch when timing is on
-struct SpanGuard {
-  pm_context *c; int idx = -1;
-  SpanGuard(pm_context *ctx, int kind) : c(ctx) {
-    if (!c->timing) return;
-    if (c->spans_used == c->spans.size()) {
-      pm_context::Span s; s.kind = kind;
-      if (cudaEventCreate(&s.a) != cudaSuccess || cudaEventCreate(&s.b) != cudaSuccess) return;
-      c->spans.push_back(s);
-    }
-    idx = (int)c->spans_used++;
-    c->spans[idx].kind = kind;
-    cudaEventRecord(c->spans[idx].a, c->stream);
-  }
-  ~SpanGuard() { if (idx >= 0) cudaEventRecord(c->spans[idx].b, c->stream); }
-};
-
-#define CK(ctx, call)                                                                          \
-  do {                                                                                         \
-    cudaError_t e__ = (call);                                                                  \
-    if (e__ != cudaSuccess) {                                                                  \
-      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                        \
-      return PM_ERR_CUDA;                                                                      \
-    }                                                                                          \
-  } while (0)
-#define ARG(ctx, cond, msg)                                                                    \
-  do {                                                                                         \
-    if (!(cond)) { if (ctx) (ctx)->err = (msg); return PM_ERR_ARG; }                          \
-  } while (0)
+#include "pm_context.h"
 
 // ---- host-side MWC arithmetic (see pm_math.cuh MwcJump) ------------------------------------------------
 static uint32_t h_mulmod(uint32_t a, uint32_t b, uint32_t m) { return host_mulmod(a, b, m); }
@@ -161,6 +70,8 @@ static DeviceScene make_device_scene(const pm_scene &in, float t) {
 
 extern "C" {
 
+int pm_peer_disconnect(pm_context *c);
+
 const char *pm_version(void) { return "pmb200 0.1 (sm_100a)"; }
 
 void pm_scene_default(pm_scene *sc) {
@@ -193,17 +104,21 @@ int pm_create(pm_context **out, int device) {
   c->device = device;
   pm_scene_default(&c->scene);
   c->dsc = make_device_scene(c->scene, 0.0f);
-  auto fail = [&](cudaError_t e) { fprintf(stderr, "pmb200: pm_create: %s\n", cudaGetErrorString(e)); delete c; return PM_ERR_CUDA; };
+  auto fail = [&](cudaError_t e) { fprintf(stderr, "pmb200: pm_create: %s\n", cudaGetErrorString(e)); pm_destroy(c); return PM_ERR_CUDA; };
   cudaError_t e;
   if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(e);
   if ((e = cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return fail(e);
-  if ((e = cudaMalloc(&c->d_acc, sizeof(long long) * kAccEntries)) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&c->d_xchg, kExchangeBytes)) != cudaSuccess) return fail(e);
+  if ((e = cudaMemset(c->d_xchg, 0, kExchangeBytes)) != cudaSuccess) return fail(e);
+  c->d_acc = (long long *)((ExchangeHeader *)c->d_xchg + 1);
+  memset(&c->pv, 0, sizeof(c->pv));
+  c->pv.world = 1; c->pv.rank = 0; c->pv.hdr[0] = (ExchangeHeader *)c->d_xchg; c->pv.acc[0] = c->d_acc;
+  c->pv.timeout_ns = 5000000000ull;
   if ((e = cudaMalloc(&c->d_grid, sizeof(float) * PM_GRID_FLOATS)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&c->d_vol, sizeof(float4) * kVolTableEntries)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&c->d_surf, sizeof(float4) * kSurfTableEntries)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&c->d_jump, sizeof(MwcJump))) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&c->d_rec_count, sizeof(unsigned long long))) != cudaSuccess) return fail(e);
-  if ((e = cudaMemset(c->d_acc, 0, sizeof(long long) * kAccEntries)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&c->d_vol_cnt, sizeof(uint32_t) * kVolCntEntries)) != cudaSuccess) return fail(e);
   if ((e = cudaMemset(c->d_vol_cnt, 0, sizeof(uint32_t) * kVolCntEntries)) != cudaSuccess) return fail(e);
   if ((e = cudaMemset(c->d_grid, 0, sizeof(float) * PM_GRID_FLOATS)) != cudaSuccess) return fail(e);
@@ -222,9 +137,10 @@ int pm_create(pm_context **out, int device) {
 int pm_destroy(pm_context *c) {
   if (!c) return PM_ERR_ARG;
   cudaSetDevice(c->device);
-  cudaFree(c->d_table); cudaFree(c->d_acc); cudaFree(c->d_vol_cnt); cudaFree(c->d_grid); cudaFree(c->d_vol); cudaFree(c->d_surf);
+  pm_peer_disconnect(c);
+  cudaFree(c->d_table); cudaFree(c->d_xchg); cudaFree(c->d_acc_sum); cudaFree(c->d_vol_cnt); cudaFree(c->d_grid); cudaFree(c->d_vol); cudaFree(c->d_surf);
   cudaFree(c->d_jump); cudaFree(c->d_rec_pos); cudaFree(c->d_rec_pow); cudaFree(c->d_rec_dir); cudaFree(c->d_rec_count);
-  cudaFree(c->d_fb_u8); cudaFree(c->d_fb_f32); cudaFree(c->d_vrec_pos); cudaFree(c->d_vrec_pow);
+  cudaFree(c->d_fb_u8); cudaFree(c->d_fb_f32); cudaFree(c->d_vrec_pos); cudaFree(c->d_vrec_pow); cudaFree(c->d_trace_dbg);
   for (int k = 0; k < 2; k++) {
     cudaFree(c->d_fb_async[k]);
     if (c->ev_rendered[k]) cudaEventDestroy(c->ev_rendered[k]);
@@ -330,7 +246,7 @@ int pm_init_random_table(pm_context *c) {
   {
     SpanGuard g(c, K_MWC_TABLE);
     // only the rows this context traces (its photon range) and rows 0..2 are generated; the stream still advances by 3*n
-    CK(c, launch_mwc_table(c->d_table, c->first, c->last, c->mwc_w, c->mwc_z, c->d_jump, c->stream));
+    CK(c, launch_mwc_table(c->d_table, c->first, c->last, c->n_photons, c->mwc_w, c->mwc_z, c->d_jump, c->stream));
     c->table_first = c->first; c->table_last = c->last;
   }
   c->launches++;
@@ -375,7 +291,12 @@ int pm_get_random_table_host(pm_context *c, float *xyz, int64_t n) {
 int pm_clear_map(pm_context *c) {
   ARG(c, c != nullptr, "null context");
   CK(c, cudaSetDevice(c->device));
-  CK(c, cudaMemsetAsync(c->d_acc, 0, sizeof(long long) * kAccEntries, c->stream));
+  if (c->world > 1) {   // frames alternate between the two accumulator buffers (pm_peer.cu): peers may still be reading the other one
+    c->cur ^= 1;
+    c->d_acc = (long long *)((ExchangeHeader *)c->d_xchg + 1) + (size_t)c->cur * kAccStride;
+  }
+  c->acc_summed = false;
+  CK(c, cudaMemsetAsync(c->d_acc, 0, sizeof(long long) * kAccStride, c->stream));   // the buffer and its flag words
   if (c->d_rec_count) CK(c, cudaMemsetAsync(c->d_rec_count, 0, sizeof(unsigned long long), c->stream));
   c->vrec_count = 0;
   c->tables_valid = false;
@@ -439,7 +360,8 @@ int pm_trace(pm_context *c, float t, unsigned flags) {
     const int vol_warps = ((flags & PM_TRACE_MEDIA) && !(flags & PM_TRACE_SPLIT)) ? c->vol_warps : 0;
     c->launches += launch_trace(c->dsc, c->d_table, c->first, c->last, flags, vol_warps, c->mwc_w, c->mwc_z, c->d_jump,
                                 (unsigned long long *)c->d_acc, c->d_vol_cnt, c->d_rec_pos, c->d_rec_pow, c->d_rec_dir, c->d_vrec_pos,
-                                c->d_vrec_pow, c->vrec_cap, c->d_rec_count, c->rec_cap, c->num_sms, c->stream, &terr);
+                                c->d_vrec_pow, c->vrec_cap, c->d_rec_count, c->rec_cap, c->num_sms, c->stream, &terr, c->d_trace_dbg,
+                                (uint32_t *)(c->d_acc + kAccEntries));
   }
   CK(c, terr);
   if (flags & PM_TRACE_MEDIA) {   // the medium scattering consumed 9 draws per photon of the WHOLE job
@@ -448,6 +370,28 @@ int pm_trace(pm_context *c, float t, unsigned flags) {
     c->mwc_w = h_mwc_advance(1, c->mwc_w, draws);
   }
   c->tables_valid = false;
+  return PM_OK;
+}
+
+int pm_trace_profile(pm_context *c, bool on) {
+  ARG(c, c != nullptr, "null context");
+  CK(c, cudaSetDevice(c->device));
+  CK(c, cudaStreamSynchronize(c->stream));
+  cudaFree(c->d_trace_dbg); c->d_trace_dbg = nullptr;
+  if (on) {
+    CK(c, cudaMalloc(&c->d_trace_dbg, sizeof(unsigned long long) * kTraceDbgWords * (size_t)c->num_sms));
+    CK(c, cudaMemset(c->d_trace_dbg, 0, sizeof(unsigned long long) * kTraceDbgWords * (size_t)c->num_sms));
+  }
+  return PM_OK;
+}
+int pm_get_trace_profile_host(pm_context *c, uint64_t *out, int64_t max_words, int64_t *words) {
+  ARG(c, c && out && words, "null argument");
+  if (!c->d_trace_dbg) { c->err = "pm_trace_profile is off"; return PM_ERR_STATE; }
+  *words = (int64_t)kTraceDbgWords * c->num_sms;
+  ARG(c, max_words >= *words, "host buffer too small");
+  CK(c, cudaSetDevice(c->device));
+  CK(c, cudaStreamSynchronize(c->stream));
+  CK(c, cudaMemcpy(out, c->d_trace_dbg, sizeof(unsigned long long) * (size_t)*words, cudaMemcpyDeviceToHost));
   return PM_OK;
 }
 
@@ -460,7 +404,7 @@ int pm_accumulators(pm_context *c, void **dev_ptr, size_t *n) {
 int pm_get_accumulators_host(pm_context *c, int64_t *out) {
   ARG(c, c && out, "null argument");
   CK(c, cudaSetDevice(c->device));
-  CK(c, cudaMemcpyAsync(out, c->d_acc, sizeof(long long) * kAccEntries, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaMemcpyAsync(out, c->acc_summed ? c->d_acc_sum : c->d_acc, sizeof(long long) * kAccEntries, cudaMemcpyDeviceToHost, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));
   return PM_OK;
 }
@@ -468,9 +412,20 @@ int pm_get_accumulators_host(pm_context *c, int64_t *out) {
 int pm_build_map(pm_context *c) {
   ARG(c, c != nullptr, "null context");
   CK(c, cudaSetDevice(c->device));
+  const long long *src = c->d_acc;
+  if (c->world > 1) {   // the path's one exchange: pull and sum every rank's accumulators over peer memory (pm_peer.cu)
+    SpanGuard g(c, K_PEER_REDUCE);
+    c->pv.hdr[c->rank] = (ExchangeHeader *)c->d_xchg;
+    // ranks that share a device (tests) must leave SMs for each other's trace while they spin
+    const int blocks = c->peer_on_same_device ? 16 : c->num_sms;
+    CK(c, launch_peer_reduce(c->pv, c->cur, ++c->seq[0], c->d_acc_sum, blocks, c->stream));
+    c->launches++;
+    c->acc_summed = true;
+    src = c->d_acc_sum;
+  }
   {
     SpanGuard g(c, K_BUILD_MAP);
-    CK(c, launch_build_map(c->d_acc, c->energy_scale, c->d_grid, c->stream));
+    CK(c, launch_build_map(src, c->energy_scale, c->d_grid, c->stream));
   }
   {
     SpanGuard g(c, K_BUILD_TABLES);
@@ -760,6 +715,43 @@ static int ensure_framebuffers(pm_context *c, int64_t pixels) {
   return PM_OK;
 }
 
+// the rows the *_host frame calls cover: the whole frame, or this rank's band (pm_set_row_band)
+static void frame_rows(const pm_context *c, int height, int *y0, int *y1) {
+  *y0 = 0; *y1 = height;
+  if (c->band_y0 >= 0) { *y0 = std::min(c->band_y0, height); *y1 = std::min(c->band_y1, height); }
+}
+
+static int ensure_async_buffers(pm_context *c, int64_t pixels) {
+  if (!c->copy_stream) {
+    CK(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++) {
+      CK(c, cudaEventCreateWithFlags(&c->ev_rendered[k], cudaEventDisableTiming));
+      CK(c, cudaEventCreateWithFlags(&c->ev_copied[k], cudaEventDisableTiming));
+    }
+  }
+  if (pixels > c->async_pixels) {
+    CK(c, cudaStreamSynchronize(c->stream));
+    CK(c, cudaStreamSynchronize(c->copy_stream));
+    for (int k = 0; k < 2; k++) {
+      cudaFree(c->d_fb_async[k]); c->d_fb_async[k] = nullptr;
+    }
+    c->async_pixels = 0;
+    for (int k = 0; k < 2; k++) CK(c, cudaMalloc(&c->d_fb_async[k], sizeof(uchar4) * (size_t)pixels));
+    c->async_pixels = pixels;
+  }
+  return PM_OK;
+}
+
+// Allocate the context-owned frame buffers of the *_host calls now.  Allocation synchronises with the device, so ranks that
+// share a device must not do it between a peer's exchange kernel and their own (pm_group_* reserves before the first frame).
+int pm_reserve_frame(pm_context *c, int width, int height) {
+  ARG(c, c != nullptr && width > 0 && height > 0, "bad frame geometry");
+  CK(c, cudaSetDevice(c->device));
+  int rc = ensure_framebuffers(c, (int64_t)width * height);
+  if (rc != PM_OK) return rc;
+  return ensure_async_buffers(c, (int64_t)width * height);
+}
+
 int pm_render_host(pm_context *c, float t, bool interp, bool media, int width, int height, pm_uchar4 *host_rgba, float *host_rgbf) {
   ARG(c, c != nullptr, "null context");
   ARG(c, width > 0 && height > 0, "bad frame geometry");
@@ -767,10 +759,17 @@ int pm_render_host(pm_context *c, float t, bool interp, bool media, int width, i
   int64_t pixels = (int64_t)width * height;
   int rc = ensure_framebuffers(c, pixels);
   if (rc != PM_OK) return rc;
-  rc = pm_render(c, t, interp, media, width, height, 0, height, host_rgba ? (pm_uchar4 *)c->d_fb_u8 : nullptr, host_rgbf ? (float *)c->d_fb_f32 : nullptr);
+  int y0, y1;
+  frame_rows(c, height, &y0, &y1);
+  rc = pm_render(c, t, interp, media, width, height, y0, y1, host_rgba ? (pm_uchar4 *)c->d_fb_u8 : nullptr, host_rgbf ? (float *)c->d_fb_f32 : nullptr);
   if (rc != PM_OK) return rc;
-  if (host_rgba) CK(c, cudaMemcpyAsync(host_rgba, c->d_fb_u8, sizeof(uchar4) * (size_t)pixels, cudaMemcpyDeviceToHost, c->stream));
-  if (host_rgbf) CK(c, cudaMemcpyAsync(host_rgbf, c->d_fb_f32, sizeof(float4) * (size_t)pixels, cudaMemcpyDeviceToHost, c->stream));
+  // Wait for the frame BEFORE handing the copies to the runtime: a copy into pageable host memory blocks inside the driver until
+  // the stream reaches it, and while it does other host threads cannot launch -- ranks sharing this process would then never
+  // reach the exchange this stream may be waiting in (cudaStreamSynchronize has no such side effect).
+  CK(c, cudaStreamSynchronize(c->stream));
+  const size_t off = (size_t)y0 * width, cnt = (size_t)(y1 - y0) * width;
+  if (host_rgba && cnt) CK(c, cudaMemcpyAsync(host_rgba + off, c->d_fb_u8 + off, sizeof(uchar4) * cnt, cudaMemcpyDeviceToHost, c->stream));
+  if (host_rgbf && cnt) CK(c, cudaMemcpyAsync(host_rgbf + 4 * off, c->d_fb_f32 + off, sizeof(float4) * cnt, cudaMemcpyDeviceToHost, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));
   return PM_OK;
 }
@@ -792,22 +791,9 @@ int pm_frame_host_async(pm_context *c, float t, bool emit, bool interp, bool med
   ARG(c, width > 0 && height > 0, "bad frame geometry");
   CK(c, cudaSetDevice(c->device));
   const int64_t pixels = (int64_t)width * height;
-  if (!c->copy_stream) {
-    CK(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    for (int k = 0; k < 2; k++) {
-      CK(c, cudaEventCreateWithFlags(&c->ev_rendered[k], cudaEventDisableTiming));
-      CK(c, cudaEventCreateWithFlags(&c->ev_copied[k], cudaEventDisableTiming));
-    }
-  }
-  if (pixels > c->async_pixels) {
-    CK(c, cudaStreamSynchronize(c->stream));
-    CK(c, cudaStreamSynchronize(c->copy_stream));
-    for (int k = 0; k < 2; k++) {
-      cudaFree(c->d_fb_async[k]); c->d_fb_async[k] = nullptr;
-    }
-    c->async_pixels = 0;
-    for (int k = 0; k < 2; k++) CK(c, cudaMalloc(&c->d_fb_async[k], sizeof(uchar4) * (size_t)pixels));
-    c->async_pixels = pixels;
+  {
+    int rc0 = ensure_async_buffers(c, pixels);
+    if (rc0 != PM_OK) return rc0;
   }
   const int64_t tk = c->next_ticket;
   const int k = (int)(tk & 1);
@@ -818,10 +804,13 @@ int pm_frame_host_async(pm_context *c, float t, bool emit, bool interp, bool med
     if ((rc = pm_trace(c, t, media ? PM_TRACE_MEDIA : 0u)) != PM_OK) return rc;
     if ((rc = pm_build_map(c)) != PM_OK) return rc;
   }
-  if ((rc = pm_render(c, t, interp, media, width, height, 0, height, (pm_uchar4 *)c->d_fb_async[k], nullptr)) != PM_OK) return rc;
+  int y0, y1;
+  frame_rows(c, height, &y0, &y1);
+  if ((rc = pm_render(c, t, interp, media, width, height, y0, y1, (pm_uchar4 *)c->d_fb_async[k], nullptr)) != PM_OK) return rc;
   CK(c, cudaEventRecord(c->ev_rendered[k], c->stream));
   CK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_rendered[k], 0));
-  CK(c, cudaMemcpyAsync(host_rgba, c->d_fb_async[k], sizeof(uchar4) * (size_t)pixels, cudaMemcpyDeviceToHost, c->copy_stream));
+  const size_t off = (size_t)y0 * width, cnt = (size_t)(y1 - y0) * width;
+  if (cnt) CK(c, cudaMemcpyAsync(host_rgba + off, c->d_fb_async[k] + off, sizeof(uchar4) * cnt, cudaMemcpyDeviceToHost, c->copy_stream));
   CK(c, cudaEventRecord(c->ev_copied[k], c->copy_stream));
   c->next_ticket = tk + 1;
   *ticket = tk;
@@ -833,6 +822,197 @@ int pm_frame_wait(pm_context *c, int64_t ticket) {
   ARG(c, ticket >= 0 && ticket < c->next_ticket && ticket + 2 >= c->next_ticket, "ticket is not one of the two most recent frames");
   CK(c, cudaSetDevice(c->device));
   CK(c, cudaEventSynchronize(c->ev_copied[ticket & 1]));
+  return PM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// multi-GPU: peers.  Every rank's exchange block is mapped into every other rank -- directly when the
+// ranks are contexts of one process (peer access), through CUDA IPC handles when they are processes -- and pm_build_map
+// then sums the accumulators with pm_peer.cu's kernel instead of a library collective.
+// ---------------------------------------------------------------------------------------------------
+static int peer_prepare(pm_context *c, int rank, int world) {
+  ARG(c, c != nullptr, "null context");
+  ARG(c, world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, "rank / world out of range (at most 16 ranks)");
+  CK(c, cudaSetDevice(c->device));
+  CK(c, cudaStreamSynchronize(c->stream));
+  int rc = pm_peer_disconnect(c);
+  if (rc != PM_OK) return rc;
+  if (!c->d_acc_sum) CK(c, cudaMalloc(&c->d_acc_sum, sizeof(long long) * kAccEntries));
+  // Everything a frame launches is launched once NOW, while this context is still alone (world == 1).  With CUDA's lazy module
+  // loading the first launch of a kernel (ours, and the runtime's memset kernels) loads its code, which waits for work already
+  // running on the device -- and a peer that shares the device may by then be spinning inside peer_reduce_kernel, waiting for
+  // exactly this rank (measured: the same-device group timed out on its first frame).
+  {
+    CK(c, preload_trace_kernels()); CK(c, preload_map_kernels()); CK(c, preload_render_kernels()); CK(c, preload_peer_kernels());
+    const int64_t first = c->first, last = c->last;
+    const uint32_t w = c->mwc_w, z = c->mwc_z;
+    c->first = std::min<int64_t>(first, c->n_photons); c->last = std::min<int64_t>(c->first + 64, c->n_photons);
+    uchar4 *tmp = nullptr;
+    CK(c, cudaMalloc(&tmp, sizeof(uchar4) * 64));
+    const int64_t launches = c->launches;
+    const bool timing = c->timing; c->timing = false;
+    rc = pm_clear_map(c);
+    if (rc == PM_OK) rc = pm_trace(c, 0.0f, 0u);
+    if (rc == PM_OK) rc = pm_trace(c, 0.0f, PM_TRACE_MEDIA);
+    if (rc == PM_OK) rc = pm_build_map(c);
+    if (rc == PM_OK) rc = pm_render(c, 0.0f, false, true, 16, 4, 0, 4, (pm_uchar4 *)tmp, nullptr);
+    if (rc == PM_OK && launch_peer_reduce(c->pv, 0, 0u, c->d_acc_sum, 1, c->stream) != cudaSuccess) rc = PM_ERR_CUDA;
+    if (rc == PM_OK && launch_peer_barrier(c->pv, 0u, c->stream) != cudaSuccess) rc = PM_ERR_CUDA;
+    if (rc == PM_OK) rc = pm_clear_map(c);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(tmp);
+    c->first = first; c->last = last; c->mwc_w = w; c->mwc_z = z; c->launches = launches; c->timing = timing;
+    if (rc != PM_OK) return rc;
+  }
+  CK(c, cudaMemsetAsync(c->d_xchg, 0, kExchangeBytes, c->stream));   // sequence numbers restart at 0 on every rank
+  CK(c, cudaStreamSynchronize(c->stream));
+  c->seq[0] = c->seq[1] = 0;
+  return PM_OK;
+}
+static void peer_finish(pm_context *c, int rank, int world) {
+  c->rank = rank; c->world = world;
+  c->pv.world = world; c->pv.rank = rank;
+  c->pv.hdr[rank] = (ExchangeHeader *)c->d_xchg;
+  for (int p = 0; p < world; p++) c->pv.acc[p] = (const long long *)(c->pv.hdr[p] + 1);
+  c->cur = 0; c->d_acc = (long long *)((ExchangeHeader *)c->d_xchg + 1);
+  c->acc_summed = false;
+}
+
+int pm_peer_export(pm_context *c, void *handle) {
+  ARG(c, c && handle, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == PM_PEER_HANDLE_BYTES, "handle size");
+  CK(c, cudaSetDevice(c->device));
+  cudaIpcMemHandle_t h;
+  CK(c, cudaIpcGetMemHandle(&h, c->d_xchg));
+  memcpy(handle, &h, sizeof(h));
+  return PM_OK;
+}
+
+int pm_peer_connect(pm_context *c, int rank, int world, const void *handles) {
+  int rc = peer_prepare(c, rank, world);
+  if (rc != PM_OK) return rc;
+  ARG(c, handles != nullptr || world == 1, "null handles");
+  for (int p = 0; p < world; p++) {
+    if (p == rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char *)handles + (size_t)p * PM_PEER_HANDLE_BYTES, sizeof(h));
+    void *ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      c->err = std::string("cudaIpcOpenMemHandle (rank ") + std::to_string(p) + "): " + cudaGetErrorString(e);
+      cudaGetLastError();
+      pm_peer_disconnect(c);
+      return PM_ERR_CUDA;
+    }
+    c->ipc_opened[p] = ptr;
+    c->pv.hdr[p] = (ExchangeHeader *)ptr;
+  }
+  peer_finish(c, rank, world);
+  return PM_OK;
+}
+
+int pm_peer_connect_local(pm_context *c, int rank, int world, pm_context *const *members) {
+  int rc = peer_prepare(c, rank, world);
+  if (rc != PM_OK) return rc;
+  ARG(c, members != nullptr && members[rank] == c, "members[rank] must be this context");
+  c->peer_on_same_device = false;
+  for (int p = 0; p < world; p++) {
+    if (p == rank) continue;
+    ARG(c, members[p] != nullptr && members[p] != c, "bad member list");
+    if (members[p]->device != c->device) {
+      int can = 0;
+      CK(c, cudaDeviceCanAccessPeer(&can, c->device, members[p]->device));
+      if (!can) { c->err = "device " + std::to_string(c->device) + " cannot access device " + std::to_string(members[p]->device) + " (no P2P path)"; return PM_ERR_STATE; }
+      cudaError_t e = cudaDeviceEnablePeerAccess(members[p]->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { c->err = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e); return PM_ERR_CUDA; }
+      cudaGetLastError();
+    } else {
+      c->peer_on_same_device = true;
+    }
+    c->pv.hdr[p] = (ExchangeHeader *)members[p]->d_xchg;
+  }
+  peer_finish(c, rank, world);
+  return PM_OK;
+}
+
+int pm_peer_disconnect(pm_context *c) {
+  if (!c) return PM_ERR_ARG;
+  for (int p = 0; p < kMaxPeers; p++) {
+    if (c->ipc_opened[p]) { cudaIpcCloseMemHandle(c->ipc_opened[p]); c->ipc_opened[p] = nullptr; }
+    c->pv.hdr[p] = nullptr; c->pv.acc[p] = nullptr;
+  }
+  c->world = 1; c->rank = 0; c->peer_on_same_device = false;
+  c->pv.world = 1; c->pv.rank = 0; c->pv.hdr[0] = (ExchangeHeader *)c->d_xchg;
+  c->cur = 0;
+  if (c->d_xchg) { c->d_acc = (long long *)((ExchangeHeader *)c->d_xchg + 1); c->pv.acc[0] = c->d_acc; }
+  c->acc_summed = false;
+  return PM_OK;
+}
+
+int pm_peer_info(const pm_context *c, int *rank, int *world) {
+  if (!c) return PM_ERR_ARG;
+  if (rank) *rank = c->rank;
+  if (world) *world = c->world;
+  return PM_OK;
+}
+
+int pm_peer_barrier(pm_context *c) {
+  ARG(c, c != nullptr, "null context");
+  if (c->world == 1) return PM_OK;
+  CK(c, cudaSetDevice(c->device));
+  CK(c, launch_peer_barrier(c->pv, ++c->seq[1], c->stream));
+  c->launches++;
+  return PM_OK;
+}
+
+int pm_peer_status(pm_context *c) {
+  ARG(c, c != nullptr, "null context");
+  CK(c, cudaSetDevice(c->device));
+  CK(c, cudaStreamSynchronize(c->stream));
+  uint32_t e = 0;
+  CK(c, cudaMemcpy(&e, &((ExchangeHeader *)c->d_xchg)->error, sizeof(e), cudaMemcpyDeviceToHost));
+  if (e) { c->err = e == 1 ? "a peer never signalled its accumulators (wait timed out)" : "a peer never reached the barrier (wait timed out)"; return PM_ERR_STATE; }
+  return PM_OK;
+}
+
+int pm_peer_set_timeout(pm_context *c, double seconds) {
+  ARG(c, c != nullptr && seconds > 0.0, "bad timeout");
+  c->pv.timeout_ns = (unsigned long long)(seconds * 1e9);
+  return PM_OK;
+}
+
+// device memory another rank can map: the frame buffer rank 0 lets the other ranks render their bands into
+int pm_shared_alloc(pm_context *c, size_t bytes, void **dev_ptr, void *handle) {
+  ARG(c, c && dev_ptr && bytes > 0, "bad argument");
+  CK(c, cudaSetDevice(c->device));
+  CK(c, cudaMalloc(dev_ptr, bytes));
+  CK(c, cudaMemset(*dev_ptr, 0, bytes));
+  if (handle) {
+    cudaIpcMemHandle_t h;
+    CK(c, cudaIpcGetMemHandle(&h, *dev_ptr));
+    memcpy(handle, &h, sizeof(h));
+  }
+  return PM_OK;
+}
+int pm_shared_open(pm_context *c, const void *handle, void **dev_ptr) {
+  ARG(c, c && handle && dev_ptr, "null argument");
+  CK(c, cudaSetDevice(c->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  CK(c, cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return PM_OK;
+}
+int pm_shared_close(pm_context *c, void *dev_ptr, bool opened) {
+  ARG(c, c && dev_ptr, "null argument");
+  CK(c, cudaSetDevice(c->device));
+  CK(c, cudaStreamSynchronize(c->stream));
+  if (opened) CK(c, cudaIpcCloseMemHandle(dev_ptr)); else CK(c, cudaFree(dev_ptr));
+  return PM_OK;
+}
+
+int pm_set_row_band(pm_context *c, int y0, int y1) {
+  ARG(c, c != nullptr && ((y0 == -1 && y1 == -1) || (y0 >= 0 && y0 <= y1)), "bad row band");
+  c->band_y0 = y0; c->band_y1 = y1;
   return PM_OK;
 }
 

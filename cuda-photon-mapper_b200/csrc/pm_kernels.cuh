@@ -17,7 +17,7 @@ inline uint32_t host_powmod(uint32_t a, unsigned long long e, uint32_t m) {
 }
 
 // pm_trace.cu
-cudaError_t launch_mwc_table(float4 *table, long long first, long long last, uint32_t w0, uint32_t z0, const MwcJump *J, cudaStream_t st);
+cudaError_t launch_mwc_table(float4 *table, long long first, long long last, long long n, uint32_t w0, uint32_t z0, const MwcJump *J, cudaStream_t st);
 cudaError_t launch_philox_table(float4 *table, long long n, unsigned long long seed, cudaStream_t st);
 // each returns the number of kernels launched; *err receives the CUDA status
 int launch_trace_volume(const DeviceScene &sc, const float4 *table, long long first, long long last, unsigned flags, uint32_t w0,
@@ -27,11 +27,30 @@ int launch_trace_volume(const DeviceScene &sc, const float4 *table, long long fi
 int launch_trace(const DeviceScene &sc, const float4 *table, long long first, long long last, unsigned flags, int vol_warps, uint32_t w0,
                  uint32_t z0, const MwcJump *J, unsigned long long *acc, uint32_t *vol_cnt, float4 *rec_pos, float4 *rec_pow,
                  float4 *rec_dir, float4 *vrec_pos, float4 *vrec_pow, long long vrec_cap, unsigned long long *rec_count, long long rec_cap,
-                 int num_sms, cudaStream_t st, cudaError_t *err);
+                 int num_sms, cudaStream_t st, cudaError_t *err, unsigned long long *dbg = nullptr, uint32_t *vox_touched = nullptr);
+constexpr int kTraceDbgWords = 48;   // pm_trace_profile: per CTA [0] start, [1] accumulators zeroed, [2] all warps done, [3] flushed, [8+w] warp w done (ns)
 
 // pm_map.cu
 cudaError_t launch_build_map(const long long *acc, float energy_scale, float *grid, cudaStream_t st);
 cudaError_t launch_build_tables(const float *grid, float4 *vol_table, float4 *surf_table, cudaStream_t st);
+
+// Force-load the kernels of a TU (cudaFuncGetAttributes).  With CUDA's lazy module loading the FIRST launch of a kernel loads its
+// code, which synchronises with work already running on the device: a rank spinning inside peer_reduce_kernel for a peer whose
+// trace kernel is not loaded yet would wait forever (measured: the same-device group test timed out).  pm_peer_connect* preloads.
+cudaError_t preload_trace_kernels();
+cudaError_t preload_map_kernels();
+cudaError_t preload_render_kernels();
+cudaError_t preload_peer_kernels();
+
+// pm_peer.cu -- multi-GPU exchange over peer memory
+struct PeerView {
+  int world, rank;
+  ExchangeHeader *hdr[kMaxPeers];      // every rank's exchange block (own entry: the local one)
+  const long long *acc[kMaxPeers];     // = (long long *)(hdr[p] + 1): two buffers, kAccStride apart
+  unsigned long long timeout_ns;
+};
+cudaError_t launch_peer_reduce(const PeerView &pv, int buf, uint32_t seq, long long *out, int blocks, cudaStream_t st);
+cudaError_t launch_peer_barrier(const PeerView &pv, uint32_t seq, cudaStream_t st);
 
 // pm_render.cu
 cudaError_t launch_render(const DeviceScene &sc, const float4 *vol_table, const float4 *surf_table, int width, int height,

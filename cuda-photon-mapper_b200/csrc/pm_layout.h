@@ -31,6 +31,21 @@ constexpr int    kVolCntEntries  = kVolCntReplicas * 3 * PM_GRID_VOXELS;       /
 constexpr double kHitScale      = 16777216.0;          // 2^24
 constexpr double kVoxScale      = 68719476736.0;       // 2^36
 
+// ---- multi-GPU exchange block (pm_peer.cu): ONE device allocation per context, visible to the other ranks (peer access
+// inside a process, CUDA IPC between processes): a header of flags followed by the two accumulator buffers (frames
+// alternate between them, see pm_peer.cu).
+constexpr int kMaxPeers = 16;
+struct ExchangeHeader {
+  uint32_t arrive[2][kMaxPeers];   // [channel][peer rank]: latest sequence number that peer has signalled (0 = accumulators, 1 = barrier)
+  uint32_t error;                  // != 0: a wait timed out (1 + channel)
+  uint32_t pad[64 - 2 * kMaxPeers - 1];
+};
+static_assert(sizeof(ExchangeHeader) == 256, "exchange header is 256 bytes");
+// each accumulator buffer is followed by 256 bytes of per-buffer flags, cleared with it: word 0 of entry kAccEntries is
+// "vox_touched" (something was deposited into the acc_vox section of this buffer)
+constexpr int    kAccStride = kAccEntries + 32;
+constexpr size_t kExchangeBytes = sizeof(ExchangeHeader) + 2 * sizeof(long long) * (size_t)kAccStride;
+
 // ---- gather tables, rebuilt from the float photon map whenever it changes -------------------------------
 // The reference's gathers depend only on the integer voxel of the query point, so their sums are tabulated
 // once per map, in the reference's own summation order (=> bit-identical to summing per pixel):

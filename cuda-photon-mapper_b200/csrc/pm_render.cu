@@ -125,6 +125,13 @@ __global__ void __launch_bounds__(256) present_float3_kernel(const float *__rest
   pos[i] = o;
 }
 
+cudaError_t preload_render_kernels() {
+  cudaFuncAttributes fa;
+  cudaError_t e = cudaFuncGetAttributes(&fa, render_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, present_float3_kernel);
+  return e;
+}
+
 cudaError_t launch_present_float3(const float *rgb, long long pixels, uchar4 *pos, cudaStream_t st) {
   if (pixels <= 0) return cudaSuccess;
   present_float3_kernel<<<(unsigned)((pixels + 255) / 256), 256, 0, st>>>(rgb, pixels, pos);

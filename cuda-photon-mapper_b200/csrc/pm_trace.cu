@@ -25,11 +25,11 @@ namespace pm {
 // ------------------------------------------------------------------------------------------------------
 // Rows [first, last) are generated, plus rows 0..2 (every photon's medium walk reads them, PMK:1258): a rank of a
 // multi-GPU job only needs its own photon range.
-__global__ void __launch_bounds__(256) mwc_table_kernel(float4 *__restrict__ table, long long first, long long last, uint32_t w0, uint32_t z0,
-                                                        const MwcJump *__restrict__ J) {
+__global__ void __launch_bounds__(256) mwc_table_kernel(float4 *__restrict__ table, long long first, long long last, long long n, uint32_t w0,
+                                                        uint32_t z0, const MwcJump *__restrict__ J) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long i = t < 3 ? t : first + (t - 3);
-  if (i >= last || (t >= 3 && i < 3)) return;
+  if (t < 3 ? i >= n : (i >= last || i < 3)) return;   // rows 0..2 exist whatever the shard (a shard may end below row 3)
   Mwc s;
   uint32_t steps = (uint32_t)(3 * i);
   s.z = mwc_jump(J, 0, z0, steps);
@@ -66,7 +66,14 @@ struct Sink {
   unsigned long long *rec_count; // global append cursor (surface records)
   long long rec_cap;
   uint32_t *vol_cnt;             // kVolCntEntries deposit counters of the medium walk (volume_kernel only)
+  uint32_t *vox_touched;         // set when anything lands in the acc_vox section (pm_layout.h ExchangeHeader), or nullptr
+  unsigned long long *dbg;       // development aid (pm_trace_profile): kTraceDbgWords timestamps per CTA, or nullptr
 };
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 __device__ __forceinline__ void acc_add(unsigned long long *p, long long v) {
   if (v != 0) atomicAdd(p, (unsigned long long)v);
@@ -250,6 +257,7 @@ struct SmemAcc {
 // (Measured: making this and the mirror/glass direction updates real calls costs 17% -- the call ABI spills the walk's state.)
 static __device__ __forceinline__ void splat_offslab(const Sink &sk, int id, int on_slab, int vx, int vy, int vz, v3 e) {
   unsigned long long *vox = sk.acc + kAccHitEntries;
+  if (sk.vox_touched) *sk.vox_touched = 1u;
   {
     unsigned long long *p = vox + ((vx * PM_GRID_N + vy) * PM_GRID_N + vz) * 3;
     acc_add(p + 0, __double2ll_rn((double)e.x * kVoxScale));
@@ -329,10 +337,13 @@ __global__ void __launch_bounds__(kSurfaceThreads, 1) trace_kernel(const __grid_
                                                                    unsigned flags, int vol_warps, uint32_t w0, uint32_t z0,
                                                                    const MwcJump *__restrict__ J, SliceJump jump, Sink sk) {
   extern __shared__ uint32_t smem_u32[];
+  unsigned long long *dbg = sk.dbg ? sk.dbg + (size_t)blockIdx.x * kTraceDbgWords : nullptr;
+  if (dbg && threadIdx.x == 0) dbg[0] = global_ns();
   SmemAcc sa;
   sa.lo = smem_u32; sa.hi = smem_u32 + kAccHitEntries; sa.shadow = smem_u32 + 2 * kAccHitEntries;
   for (int i = threadIdx.x; i < 2 * kAccHitEntries + kShadowEntries; i += blockDim.x) smem_u32[i] = 0u;
   __syncthreads();
+  if (dbg && threadIdx.x == 0) dbg[1] = global_ns();
 
   const bool media = flags & PM_TRACE_MEDIA;
   const bool rec = kRec;
@@ -481,7 +492,9 @@ __global__ void __launch_bounds__(kSurfaceThreads, 1) trace_kernel(const __grid_
   }
 
   // ---- flush the CTA-private accumulators ----
+  if (dbg && (threadIdx.x & 31) == 0) dbg[8 + (threadIdx.x >> 5)] = global_ns();   // when this warp ran out of photons
   __syncthreads();
+  if (dbg && threadIdx.x == 0) dbg[2] = global_ns();
   if (sk.acc) {
     for (int e = threadIdx.x; e < kAccHitEntries; e += blockDim.x) {
       unsigned long long v = (unsigned long long)sa.lo[e] | ((unsigned long long)sa.hi[e] << 32);
@@ -489,16 +502,32 @@ __global__ void __launch_bounds__(kSurfaceThreads, 1) trace_kernel(const __grid_
       if (v) atomicAdd(sk.acc + e, v);
     }
   }
+  if (dbg) {
+    __syncthreads();
+    if (threadIdx.x == 0) dbg[3] = global_ns();
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------------
-cudaError_t launch_mwc_table(float4 *table, long long first, long long last, uint32_t w0, uint32_t z0, const MwcJump *J, cudaStream_t st) {
-  long long n = last - first + 3;
-  if (last <= 0) return cudaSuccess;
-  unsigned blocks = (unsigned)((n + 255) / 256);
-  mwc_table_kernel<<<blocks, 256, 0, st>>>(table, first, last, w0, z0, J);
+cudaError_t preload_trace_kernels() {
+  cudaFuncAttributes fa;
+  cudaError_t e = cudaFuncGetAttributes(&fa, mwc_table_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, philox_table_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, volume_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, fold_volume_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, trace_kernel<false>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, trace_kernel<true>);
+  return e;
+}
+
+cudaError_t launch_mwc_table(float4 *table, long long first, long long last, long long n, uint32_t w0, uint32_t z0, const MwcJump *J,
+                             cudaStream_t st) {
+  long long threads = last - first + 3;
+  if (n <= 0) return cudaSuccess;
+  unsigned blocks = (unsigned)((threads + 255) / 256);
+  mwc_table_kernel<<<blocks, 256, 0, st>>>(table, first, last, n, w0, z0, J);
   return cudaGetLastError();
 }
 
@@ -511,7 +540,7 @@ cudaError_t launch_philox_table(float4 *table, long long n, unsigned long long s
 static Sink make_sink(unsigned flags, unsigned long long *acc, float4 *rec_pos, float4 *rec_pow, float4 *rec_dir,
                       unsigned long long *rec_count, long long rec_cap) {
   Sink sk;
-  sk.vol_cnt = nullptr; sk.vrec_pos = sk.vrec_pow = nullptr; sk.vrec_cap = 0;
+  sk.vol_cnt = nullptr; sk.vrec_pos = sk.vrec_pow = nullptr; sk.vrec_cap = 0; sk.dbg = nullptr; sk.vox_touched = nullptr;
   sk.acc = (flags & PM_TRACE_NO_MAP) ? nullptr : acc;
   sk.rec_pos = rec_pos; sk.rec_pow = rec_pow; sk.rec_dir = rec_dir; sk.rec_count = rec_count; sk.rec_cap = rec_cap;
   return sk;
@@ -551,12 +580,12 @@ int launch_trace_volume(const DeviceScene &sc, const float4 *table, long long fi
 int launch_trace(const DeviceScene &sc, const float4 *table, long long first, long long last, unsigned flags, int vol_warps, uint32_t w0,
                  uint32_t z0, const MwcJump *J, unsigned long long *acc, uint32_t *vol_cnt, float4 *rec_pos, float4 *rec_pow,
                  float4 *rec_dir, float4 *vrec_pos, float4 *vrec_pow, long long vrec_cap, unsigned long long *rec_count, long long rec_cap,
-                 int num_sms, cudaStream_t st, cudaError_t *err) {
+                 int num_sms, cudaStream_t st, cudaError_t *err, unsigned long long *dbg, uint32_t *vox_touched) {
   *err = cudaSuccess;
   long long n = last - first;
   if (n <= 0) return 0;
   Sink sk = make_sink(flags, acc, rec_pos, rec_pow, rec_dir, rec_count, rec_cap);
-  sk.vol_cnt = vol_cnt; sk.vrec_pos = vrec_pos; sk.vrec_pow = vrec_pow; sk.vrec_cap = vrec_cap;
+  sk.vol_cnt = vol_cnt; sk.vrec_pos = vrec_pos; sk.vrec_pow = vrec_pow; sk.vrec_cap = vrec_cap; sk.dbg = dbg; sk.vox_touched = vox_touched;
   const bool rec = (flags & PM_TRACE_RECORDS) != 0;
   auto kernel = rec ? trace_kernel<true> : trace_kernel<false>;
   *err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSurfaceSmem);

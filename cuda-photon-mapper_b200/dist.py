@@ -25,6 +25,39 @@ def row_band(height, rank, world):
     return rank * rows, (rank + 1) * rows
 
 
+def row_band_uneven(height, rank, world):
+    """Contiguous row band of rank `rank` for any height (bands differ by at most one row)."""
+    return height * rank // world, height * (rank + 1) // world
+
+
+def connect_peers(mapper):
+    """One process per GPU: exchange the CUDA IPC handles of every rank's exchange block with torch.distributed and connect
+    them (pm_peer_connect), so that pm_build_map sums the accumulators over NVLink peer memory itself.  No-op for one rank."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return False
+    world, rank = dist.get_world_size(), dist.get_rank()
+    handles = [None] * world
+    dist.all_gather_object(handles, mapper.peer_export())
+    mapper.peer_connect(rank, world, handles)
+    dist.barrier()      # nobody starts signalling before every rank has mapped every block
+    return True
+
+
+def shared_frame(mapper, nbytes):
+    """A device buffer on rank 0 that every rank maps (CUDA IPC): ranks render their row band straight into it over NVLink.
+    Returns (device pointer valid on this rank, opened) -- pass both to mapper.shared_close()."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return mapper.shared_alloc(nbytes)[0], False
+    box = [None]
+    ptr = None
+    if dist.get_rank() == 0:
+        ptr, box[0] = mapper.shared_alloc(nbytes)
+    dist.broadcast_object_list(box, src=0)
+    if dist.get_rank() != 0:
+        return mapper.shared_open(box[0]), True
+    return ptr, False
+
+
 class _RawCuda:
     def __init__(self, ptr, n, typestr):
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}

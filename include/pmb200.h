@@ -13,6 +13,7 @@
  * pointers owned by the caller; host_* are host pointers.  All pm_* calls return 0 on success or a negative
  * pm_status; pm_last_error() gives the text.  pm_* launches are asynchronous on the context's stream unless
  * the name ends in _host or says otherwise.  There is no CPU fallback: without a CUDA device pm_create fails.
+ * Every pm_* call makes its context's device the calling thread's current CUDA device (cudaSetDevice) and leaves it so.
  */
 #ifndef PMB200_H
 #define PMB200_H
@@ -192,6 +193,58 @@ int pm_frame_host(pm_context *ctx, float animTime, bool emitFlag, bool interpola
 int pm_frame_host_async(pm_context *ctx, float animTime, bool emitFlag, bool interpolateFlag, bool participatingMediaFlag,
                         int width, int height, pm_uchar4 *host_rgba, int64_t *ticket);
 int pm_frame_wait(pm_context *ctx, int64_t ticket);
+/* allocate the context-owned device frame buffers of the *_host calls up front (they are otherwise sized on first use) */
+int pm_reserve_frame(pm_context *ctx, int width, int height);
+
+/* ------------------------------------------------------------------------------------------------
+ * multi-GPU (the reference is single-device, simplePBO.cpp:191-195).  The path shards as: rank r traces the
+ * photon range pm_set_photon_range gives it, the exact accumulators of all ranks are SUMMED (the one exchange), every rank
+ * builds the same photon map and renders its own row band.  Once peers are connected pm_build_map performs the exchange
+ * itself: one kernel pulls the other ranks' accumulators over NVLink peer memory, with the rank synchronisation inside it
+ * (csrc/pm_peer.cu) -- no library collective.  All ranks must then call pm_clear_map / pm_trace / pm_build_map in lockstep,
+ * frame by frame.  Integer sums: the map is bit-identical for every number of ranks.
+ *   - ranks as PROCESSES (one per GPU, e.g. under torchrun): pm_peer_export on every rank, exchange the 64-byte handles by
+ *     any means, pm_peer_connect with all of them (CUDA IPC);
+ *   - ranks as contexts of ONE process: pm_peer_connect_local with the member contexts (peer access), or simply the
+ *     pm_group_* calls below, which own the contexts and one host thread per GPU.
+ * ---------------------------------------------------------------------------------------------- */
+#define PM_PEER_HANDLE_BYTES 64
+#define PM_MAX_RANKS 16
+int pm_peer_export(pm_context *ctx, void *handle /* PM_PEER_HANDLE_BYTES */);
+int pm_peer_connect(pm_context *ctx, int rank, int world, const void *handles /* world x PM_PEER_HANDLE_BYTES; entry [rank] unused */);
+int pm_peer_connect_local(pm_context *ctx, int rank, int world, pm_context *const *members /* [world], members[rank] == ctx */);
+int pm_peer_disconnect(pm_context *ctx);
+int pm_peer_info(const pm_context *ctx, int *rank, int *world);
+int pm_peer_barrier(pm_context *ctx);              /* device-side barrier of all ranks, enqueued on the stream */
+int pm_peer_status(pm_context *ctx);               /* synchronises; PM_ERR_STATE if a peer wait timed out (default 5 s) */
+int pm_peer_set_timeout(pm_context *ctx, double seconds);
+/* device memory that another rank can map (CUDA IPC), e.g. the frame buffer every rank renders its band into */
+int pm_shared_alloc(pm_context *ctx, size_t bytes, void **dev_ptr, void *handle /* PM_PEER_HANDLE_BYTES, or NULL */);
+int pm_shared_open(pm_context *ctx, const void *handle, void **dev_ptr);
+int pm_shared_close(pm_context *ctx, void *dev_ptr, bool opened /* true: from pm_shared_open; false: from pm_shared_alloc */);
+/* the rows [y0, y1) this rank renders and copies in pm_render_host / pm_frame_host / pm_frame_host_async (the host pointer
+ * stays the base of the WHOLE frame: every rank copies its own band over its own PCIe link); (-1, -1) = all rows */
+int pm_set_row_band(pm_context *ctx, int y0, int y1);
+
+/* The same as one object, for a single-process host program (the reference's model: one host thread calling display(),
+ * callbacksPBO.cpp:47-101): n contexts on n devices, one worker thread per GPU inside the library, peers connected.
+ * pm_group_frame_host* is display() for the group: (emit: clear + trace 1/n of the photons + exchange + map build) + every
+ * GPU renders its row band and copies it into the caller's HOST frame.  devices may repeat a device (tests). */
+typedef struct pm_group pm_group;
+int         pm_group_create(pm_group **out, const int *devices, int n);
+int         pm_group_destroy(pm_group *g);
+int         pm_group_size(const pm_group *g);
+pm_context *pm_group_context(pm_group *g, int rank);          /* for inspection (maps, accumulators, timings) */
+const char *pm_group_last_error(const pm_group *g);
+int pm_group_set_scene(pm_group *g, const pm_scene *scene);
+int pm_group_set_photon_count(pm_group *g, int64_t n_photons);   /* also shards the photon range across the ranks */
+int pm_group_set_energy_scale(pm_group *g, float scale);
+int pm_group_init_random_table(pm_group *g);
+int pm_group_frame_host(pm_group *g, float animTime, bool emitFlag, bool interpolateFlag, bool participatingMediaFlag,
+                        int width, int height, pm_uchar4 *host_rgba, float *host_rgbf);
+int pm_group_frame_host_async(pm_group *g, float animTime, bool emitFlag, bool interpolateFlag, bool participatingMediaFlag,
+                              int width, int height, pm_uchar4 *host_rgba /* pinned */, int64_t *ticket);
+int pm_group_frame_wait(pm_group *g, int64_t ticket);
 
 /* instrumentation: number of kernels this context has launched so far, and optional per-kernel CUDA-event timing
  * (event pairs recorded on the context's stream around each launch; pm_get_timings synchronises, fills
@@ -201,6 +254,10 @@ int         pm_enable_timing(pm_context *ctx, bool on);
 int         pm_kernel_count(void);
 const char *pm_kernel_name(int kind);
 int         pm_get_timings(pm_context *ctx, double *total_ms, int64_t *launches);
+/* development aid: per-CTA %globaltimer stamps (ns) of the next trace launches -- 48 words per CTA: [0] start,
+ * [1] shared accumulators zeroed, [2] every warp out of photons, [3] accumulators flushed, [8+w] warp w out of photons */
+int         pm_trace_profile(pm_context *ctx, bool on);
+int         pm_get_trace_profile_host(pm_context *ctx, uint64_t *host_out, int64_t max_words, int64_t *words);
 
 #ifdef __cplusplus
 }
