@@ -47,10 +47,15 @@ def parse():
                          "tree built on every rank, row bands) -- for Mode B scaling runs")
     ap.add_argument("--knn", type=int, default=50, help="k of the Mode B estimate")
     ap.add_argument("--no-overlap", action="store_true",
-                    help="Mode A: do not overlap a frame's render + frame gather (side stream) with the next frame's trace")
+                    help="Mode A: one stream, no frames in flight (the headline keeps two frames in flight: exchange + map build + render "
+                         "of frame f run on a second stream under the trace of frame f+1)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="Mode A, N > 1: how the accumulators are summed -- peer (default): our kernel pulls them over NVLink peer "
                          "memory inside pm_build_map (CUDA IPC between the ranks); nccl: dist.all_reduce (round 1's path)")
+    ap.add_argument("--trace-sms", type=int, default=-1,
+                    help="CTAs of the persistent trace kernel (pm_set_trace_sms); -1 (default): every SM at N <= 2, all but 16 at N >= 4, "
+                         "which leaves room for the previous frame's exchange + map build + render on the second stream")
+    ap.add_argument("--no-extras", action="store_true", help="skip Mode B at N, config 5 and the single-GPU side benchmarks")
     ap.add_argument("--passes", type=int, default=1,
                     help="progressive photon mapping (BASELINE config 5): photon passes accumulated per frame, each with a fresh "
                          "direction table from the continuing MWC stream (Mode A)")
@@ -312,6 +317,10 @@ def config2_numbers(pmb200, torch, device):
     return out
 
 
+def _events(torch, n):
+    return [torch.cuda.Event(enable_timing=True) for _ in range(n)]
+
+
 def main():
     a = parse()
     if a.impl == "reference":
@@ -332,25 +341,39 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     W, H, NP = a.width, a.height, a.photons
-    assert H % world == 0, "rows must split evenly across ranks"
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        tt = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
 
     m = pmb200.PhotonMapper(device=local, n_photons=NP)
-    stream = torch.cuda.current_stream()
-    m.set_stream(stream.cuda_stream)
+    main_stream = torch.cuda.current_stream()
+    m.set_stream(main_stream.cuda_stream)
     scene = pmb200.default_scene(sz_img=H)
     scene.cam_ox = -(W - H) / 2.0
     m.set_scene(scene)
     m.set_energy_scale(10000.0 / NP / a.passes)
-    m.init_random_numbers()                       # once, outside the timed region (callbacksPBO.cpp:55-58)
     first, last = pmdist.photon_shard(NP, rank, world)
     m.set_photon_range(first, last)
-    y0, y1 = pmdist.row_band(H, rank, world)
+    m.init_random_numbers()                       # once, outside the timed region (callbacksPBO.cpp:55-58)
+    y0, y1 = pmdist.row_band_uneven(H, rank, world)
     rows = y1 - y0
+    m.set_row_band(y0, y1)
+    trace_sms = a.trace_sms if a.trace_sms >= 0 else (0 if world <= 2 else torch.cuda.get_device_properties(local).multi_processor_count - 16)
+    m.set_trace_sms(trace_sms)
 
-    # Mode A, N > 1: the ranks' exchange blocks are mapped into each other (CUDA IPC) and the frame lives on rank 0, every
-    # rank rendering its row band straight into it over NVLink
+    # N > 1: the ranks' exchange blocks are mapped into each other (CUDA IPC) and the frame lives on rank 0, every rank
+    # rendering its row band straight into it over NVLink
     peers = False
-    if world > 1 and a.mode == "a" and a.exchange == "peer":
+    if world > 1 and a.exchange == "peer":
         ok = torch.ones(1, device="cuda")
         try:
             pmdist.connect_peers(m)
@@ -369,14 +392,64 @@ def main():
     else:
         rgba = torch.zeros((H, W, 4), dtype=torch.uint8, device="cuda")
         rgbf = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
-    acc_ptr, acc_n = m.accumulators()
-    acc = pmdist.device_tensor(acc_ptr, acc_n, "<i8")
+    acc_n = m.accumulators()[1]
 
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(a.steps)]
+    # ------------------------------------------------------------------------------------------------------
+    # Mode A steps
+    # ------------------------------------------------------------------------------------------------------
+    def trace_passes():
+        m.clear_map()
+        m.trace(0.0, media=True)
+        for _ in range(a.passes - 1):             # progressive: further passes accumulate into the same exact accumulators
+            m.init_random_numbers()
+            m.trace(0.0, media=True)
 
-    side_b = torch.cuda.Stream() if (world > 1 and not a.no_overlap) else None
+    def exchange_build_render(e=None):
+        if world > 1 and not peers:
+            pmdist.allreduce_accumulators(pmdist.device_tensor(m.accumulators()[0], acc_n, "<i8"))   # round 1's path
+        if e: e[2].record()
+        m.build_map()                             # peers: the exchange happens in here (peer_reduce_kernel)
+        if e: e[3].record()
+        m.render_device(W, H, 0.0, False, True, rgba=rgba, rgbf=rgbf, y0=y0, y1=y1)
+        if peers:
+            m.peer_barrier()                      # every rank's band has landed in rank 0's frame buffers
+        elif world > 1:
+            pmdist.gather_frame(rgba, y0, y1)
+            pmdist.gather_frame(rgbf, y0, y1)
+
+    def step_serial(e=None):
+        """One frame on one stream, nothing in flight (--no-overlap, and the instrumented pass that splits the frame into stages)."""
+        if e: e[0].record()
+        trace_passes()
+        if e: e[1].record()
+        exchange_build_render(e)
+        if e: e[4].record()
+
+    side = torch.cuda.Stream()
     ev_traced = torch.cuda.Event()
-    main_stream = torch.cuda.current_stream()
+
+    def step_pipelined(e=None):
+        """Two frames in flight: clear + trace on the main stream, exchange + map build + render (+ barrier) on the second one."""
+        if a.passes == 1 and (peers or world == 1):
+            m.frame_device(W, H, rgba=rgba, rgbf=rgbf, t=0.0, emit=True, interp=False, media=True)     # the library's own pipeline
+            return
+        trace_passes()
+        ev_traced.record(main_stream)
+        side.wait_event(ev_traced)
+        m.set_stream(side.cuda_stream)
+        with torch.cuda.stream(side):
+            exchange_build_render()
+        m.set_stream(main_stream.cuda_stream)
+
+    def drain():
+        m.sync()
+        main_stream.wait_stream(side)
+
+    # ------------------------------------------------------------------------------------------------------
+    # Mode B step (records all-gathered with NCCL, trees built on every rank, interleaved rows)
+    # ------------------------------------------------------------------------------------------------------
+    side_b = torch.cuda.Stream() if world > 1 else None
+    keep = {}
 
     def step_b(e=None):
         if e: e[0].record()
@@ -385,7 +458,7 @@ def main():
         if e: e[1].record()
         sp = pmdist.allgather_records(*[m.record_buffers(0)[i] for i in (0, 1, 3)])
         if e: e[2].record()
-        if world > 1 and side_b is not None:      # the volume records travel while the surface tree is being built
+        if world > 1:                             # the volume records travel while the surface tree is being built
             ev_traced.record(main_stream)
             side_b.wait_event(ev_traced)
             with torch.cuda.stream(side_b):
@@ -399,126 +472,97 @@ def main():
         if e: e[3].record()
         # the k-NN gather cost varies strongly over the image: rank r renders rows r, r+N, r+2N, ... and the frames are
         # summed (all other rows are zero, so the sum is exact)
+        fb_u8, fb_f32 = keep["fb"]
         if world > 1:
-            rgba.zero_(); rgbf.zero_()
-        m.render_knn(W, H, 0.0, True, a.knn, float("inf"), 2.0e-4 * 10000.0 / NP, 4.0e-3 * 10000.0 / NP, rgba=rgba, rgbf=rgbf,
+            fb_u8.zero_(); fb_f32.zero_()
+        m.render_knn(W, H, 0.0, True, a.knn, float("inf"), 2.0e-4 * 10000.0 / NP, 4.0e-3 * 10000.0 / NP, rgba=fb_u8, rgbf=fb_f32,
                      y0=rank, y1=H, y_step=world)
         if world > 1:
-            dist.all_reduce(rgbf)
-            dist.all_reduce(rgba)
+            dist.all_reduce(fb_f32)
+            dist.all_reduce(fb_u8)
         if e: e[4].record()
-        step_b.keep = (sp, vp)    # the maps reference the gathered arrays
+        keep["rec"] = (sp, vp)                    # the maps reference the gathered arrays
 
-    # Mode A pipelining: the render + frame gather of frame i run on a side stream while the main stream already traces
-    # frame i+1 (the trace only touches the accumulators, the render only the gather tables).  Dependencies: render(i) waits
-    # for build(i); build(i+1) rewrites the tables and waits for render(i).  Every frame is still rendered and gathered in
-    # full, and the last one completes before the closing barrier.
-    overlap = not a.no_overlap
-    side = torch.cuda.Stream() if overlap else None
-    ev_built, ev_rendered = torch.cuda.Event(), torch.cuda.Event()
-    main_stream = torch.cuda.current_stream()
-    state = {"pending": False}
+    def time_steps(fn, steps, warm, events=None, after=None):
+        for _ in range(warm):
+            fn()
+        if after: after()
+        barrier()
+        t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_beg.record()
+        for i in range(steps):
+            fn(events[i]) if events else fn()
+        if after: after()                         # the last frame's second half is inside the timed span
+        t_end.record()
+        barrier()
+        return max_over_ranks(t_beg.elapsed_time(t_end)) / steps
 
-    def step_a(e=None):
-        if e: e[0].record()
-        m.clear_map()
-        m.trace(0.0, media=True)
-        for _ in range(a.passes - 1):             # progressive: further passes accumulate into the same exact accumulators
-            m.init_random_numbers()
-            m.trace(0.0, media=True)
-        if e: e[1].record()
-        if not peers:
-            pmdist.allreduce_accumulators(pmdist.device_tensor(m.accumulators()[0], acc_n, "<i8"))   # NCCL (no-op at N=1)
-        if e: e[2].record()
-        if overlap and state["pending"]:
-            main_stream.wait_event(ev_rendered)   # the previous frame's render still reads the tables
-        m.build_map()                             # peers: the exchange happens in here (peer_reduce_kernel)
-        if e: e[3].record()
-
-        def render_and_assemble():
-            m.render_device(W, H, 0.0, False, True, rgba=rgba, rgbf=rgbf, y0=y0, y1=y1)
-            if peers:
-                m.peer_barrier()                  # every rank's band has landed in rank 0's frame buffers
-            else:
-                pmdist.gather_frame(rgba, y0, y1)
-                pmdist.gather_frame(rgbf, y0, y1)
-        if overlap:
-            ev_built.record(main_stream)
-            side.wait_event(ev_built)
-            m.set_stream(side.cuda_stream)
-            with torch.cuda.stream(side):
-                render_and_assemble()
-                ev_rendered.record(side)
-            m.set_stream(main_stream.cuda_stream)
-            state["pending"] = True
-        else:
-            render_and_assemble()
-        if e: e[4].record()
-
-    step = step_b if a.mode == "b" else step_a
     if a.mode == "b":
         m.set_record_capacity(int(2.6 * (last - first)) + 4096)
+        keep["fb"] = (torch.zeros((H, W, 4), dtype=torch.uint8, device="cuda"), torch.zeros((H, W, 4), dtype=torch.float32, device="cuda"))
+        step, after = step_b, None
+    elif a.no_overlap:
+        step, after = step_serial, None
+    else:
+        step, after = step_pipelined, drain
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
+    # ---- the headline: K steps, nothing but the frames in the timed region ----
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler: sampler.start()
-    for _ in range(max(a.warmup, 3)):
-        step()
-    barrier()
-    m.enable_timing(True)                         # CUDA-event pairs around every kernel, on the launching stream
     launches0 = m.launch_count()
-    t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_beg.record()
-    for i in range(a.steps):
-        step(ev[i])
-    if side is not None:
-        main_stream.wait_stream(side)             # the last frame's render (+ assembly) is inside the timed span
-    t_end.record()
-    barrier()
-    launches = m.launch_count() - launches0
+    ms_per_step = time_steps(step, a.steps, max(a.warmup, 3), after=after)
+    launches = (m.launch_count() - launches0) * a.steps // (a.steps + max(a.warmup, 3))
+
+    # ---- instrumented pass: the same frames on one stream with CUDA events between the stages and around every kernel ----
+    n_inst = max(3, min(a.steps, 20))
+    ev = [_events(torch, 5) for _ in range(n_inst)]
+    m.enable_timing(True)
+    inst_step = step_b if a.mode == "b" else step_serial
+    latency_ms = time_steps(inst_step, n_inst, 2, events=ev)
     kernel_times = m.timings()
     m.enable_timing(False)
-    total_ms = t_beg.elapsed_time(t_end)
-    if world > 1:
-        tt = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        total_ms = float(tt.item())
-    ms_per_step = total_ms / a.steps
     stages = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(4)] for e in ev]).mean(0)
 
-    # ---- end to end through the C-ABI with HOST buffers (pinned): scene struct in, the reference's uchar4 frame out.
-    #      One GPU: pm_frame_host_async, the copy of frame f runs under the trace of frame f+1 and the host waits for every
-    #      frame (one frame behind).  Multi-GPU / Mode B: step + D2H of the assembled frame on rank 0, synchronous. ----
-    h_rgba2 = [torch.empty((H, W, 4), dtype=torch.uint8).pin_memory() for _ in range(2)]
-    h_rgba = h_rgba2[0]
+    # ---- end to end through the C-ABI with HOST buffers: scene struct in, the reference's uchar4 frame out.  Mode A: every rank
+    #      calls pm_frame_host_async (two frames in flight, exchange inside) and copies ITS row band into one host frame -- pinned
+    #      memory, shared between the rank processes at N > 1 -- over its own PCIe link; the host waits for every frame, one frame
+    #      behind, and rank 0 also waits until every rank has reported its band of that frame. ----
     e2e_steps = max(3, min(a.steps, 30))
-    pipelined = world == 1 and a.mode == "a" and a.passes == 1
+    pipelined = a.mode == "a" and a.passes == 1 and (peers or world == 1)
     pending = []
+    if pipelined:
+        host_frames, done_words, shm_keep = pmdist.shared_host_frames(2, W * H * 4, world)
+    else:
+        host_frames = [torch.empty((H, W, 4), dtype=torch.uint8).pin_memory()]
+    n_sub = [0]
+
+    def e2e_retire():
+        tk, n = pending.pop(0)
+        m.frame_wait(tk)                          # this rank's band of frame n is in host memory
+        if world > 1:
+            done_words[n & 1, rank] = n + 1
+            if rank == 0:                         # ... and so is every other rank's
+                while int(done_words[n & 1].min()) < n + 1:
+                    pass
 
     def e2e_step():
         m.set_scene(scene)                        # the frame's only host input: the scene / parameter block
         if pipelined:
-            tk = m.frame_async(W, H, h_rgba2[e2e_step.n & 1], t=0.0, emit=True, interp=False, media=True)
-            e2e_step.n += 1
-            if pending:
-                m.frame_wait(pending.pop())       # frame f-1 is complete in host memory before frame f+1 is submitted
-            pending.append(tk)
+            n = n_sub[0]; n_sub[0] += 1
+            pending.append((m.frame_async(W, H, host_frames[n & 1], t=0.0, emit=True, interp=False, media=True), n))
+            if len(pending) > 1:
+                e2e_retire()                      # frame f-1 is complete in host memory before frame f+1 is submitted
         else:
             step()
-            if side is not None:
-                main_stream.wait_stream(side)     # the frame gather runs on the side stream
+            if after: after()
             if rank == 0:
-                h_rgba.copy_(rgba, non_blocking=True)
+                fb = keep["fb"][0] if a.mode == "b" else rgba
+                host_frames[0].copy_(fb, non_blocking=True)
             torch.cuda.synchronize()
-    e2e_step.n = 0
 
     def e2e_drain():
         while pending:
-            m.frame_wait(pending.pop())
+            e2e_retire()
 
     for _ in range(3):
         e2e_step()
@@ -529,12 +573,62 @@ def main():
         e2e_step()
     e2e_drain()                                   # the last frame is in host memory too
     barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-    if world > 1:
-        tt = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_ms = float(tt.item())
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / e2e_steps)
     clocks = sampler.stop() if sampler else None
+    peer_ok = True
+    if peers:
+        try:
+            m.peer_status()
+        except pmb200.PmError:
+            peer_ok = False
+
+    # ---- extras carried by the same line, so that the driver's scaling run records them at every N: Mode B at N GPUs
+    #      (BASELINE config 4, k-NN estimator) and progressive photon mapping (config 5: 64 passes x 16M photons, 3840x2160) ----
+    extras = {}
+    if a.mode == "a" and a.passes == 1 and not a.no_extras and NP >= (1 << 20):
+        try:
+            p5 = 64
+            W5, H5 = 3840, 2160
+            y50, y51 = pmdist.row_band_uneven(H5, rank, world)
+            sc5 = pmb200.default_scene(sz_img=H5); sc5.cam_ox = -(W5 - H5) / 2.0
+            m.set_scene(sc5); m.set_energy_scale(10000.0 / NP / p5)
+            fb5 = torch.zeros((H5, W5, 4), dtype=torch.uint8, device="cuda")
+
+            def step5():
+                m.clear_map()
+                for _ in range(p5):               # pass p continues the MWC stream: a fresh direction table per pass
+                    m.init_random_numbers()
+                    m.trace(0.0, media=True)
+                if world > 1 and not peers:
+                    pmdist.allreduce_accumulators(pmdist.device_tensor(m.accumulators()[0], acc_n, "<i8"))
+                m.build_map()
+                m.render_device(W5, H5, 0.0, False, True, rgba=fb5, y0=y50, y1=y51)
+                if peers:
+                    m.peer_barrier()
+            ms5 = time_steps(step5, 3, 1)
+            extras["config5_progressive"] = {"workload": "64 passes x %d photons, 3840x2160, Mode A, row bands left on their GPUs" % NP,
+                                             "ms_per_frame": ms5, "photons_per_s": p5 * NP / (ms5 * 1e-3), "steps": 3}
+            m.set_scene(scene); m.set_energy_scale(10000.0 / NP)
+            del fb5
+        except Exception as ex:
+            extras["config5_progressive"] = {"failed": repr(ex)}
+        if world > 1:
+            try:
+                m.set_record_capacity(int(2.6 * (last - first)) + 4096)
+                keep["fb"] = (torch.zeros((H, W, 4), dtype=torch.uint8, device="cuda"), torch.zeros((H, W, 4), dtype=torch.float32, device="cuda"))
+                evb = [_events(torch, 5) for _ in range(3)]
+                msb = time_steps(step_b, 3, 1, events=evb)
+                st_b = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(4)] for e in evb]).mean(0)
+                extras["mode_b_config4"] = {"workload": "%d photons, k=%d, 11 k-NN gathers per pixel, %dx%d, records all-gathered, trees on every rank, "
+                                                        "rows interleaved" % (NP, a.knn, W, H), "ms_per_frame": msb,
+                                            "gather_queries_per_s": W * H * 11 / (float(st_b[3]) * 1e-3),
+                                            "stages_ms": {"trace_with_records": float(st_b[0]), "allgather_surface_records": float(st_b[1]),
+                                                          "allgather_volume_records||build_surface, build_volume": float(st_b[2]),
+                                                          "knn_render(+sum)": float(st_b[3])}, "steps": 3}
+                keep.clear()
+            except Exception as ex:
+                extras["mode_b_config4"] = {"failed": repr(ex)}
+            torch.cuda.empty_cache()
 
     if rank == 0:
         peaks = {}
@@ -544,75 +638,111 @@ def main():
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md 6.65 TB/s)"
-        n_local = last - first
-        kern = {k: {"avg_ms": v[0] / v[1], "launches": v[1]} for k, v in kernel_times.items() if v[1]}
-        dom = max(kern, key=lambda k: kern[k]["avg_ms"] * kern[k]["launches"])
-        # algorithmic (compulsory) HBM bytes per launch, DESIGN.md "kernels": one float3 direction per photon for the two
-        # trace kernels; one uchar4 + one float4 per pixel for the render kernel
-        alg = {"volume_kernel": 12.0 * n_local, "trace_kernel": 12.0 * n_local, "render_kernel": 20.0 * W * rows}
-        dom_bytes = alg.get(dom, 0.0)
+        n_local = (last - first) * a.passes
+        kern = {k: {"avg_ms": v[0] / v[1], "launches_per_step": v[1] / n_inst} for k, v in kernel_times.items() if v[1]}
+        dom = max(kern, key=lambda k: kern[k]["avg_ms"] * kern[k]["launches_per_step"])
         dom_ms = kern[dom]["avg_ms"]
-        achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
-        traffic, issue_pct = None, None
-        try:   # DRAM bytes per launch / issue-slot utilisation from the committed ncu --set full capture of the same configuration
-            prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-            if prof.get("photons") == NP and world == 1:
-                traffic = prof["dram_bytes_per_launch"].get(dom)
-                issue_pct = prof.get("issue_slots_busy_pct", {}).get(dom)
-        except Exception:
-            pass
+        props = torch.cuda.get_device_properties(local)
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
         line = {
-            "metric": METRIC if a.mode == "a" else METRIC.replace("(trace", "Mode B k=%d (trace" % a.knn), "value": ms_per_step, "unit": "ms", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "metric": METRIC if a.mode == "a" else METRIC.replace("(trace", "Mode B k=%d (trace" % a.knn), "value": ms_per_step, "unit": "ms",
+            "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": workload_config(a, {"parallelism": "photon-range x%d + row-band x%d" % (world, world)}),
-            "photons_per_s": NP / (ms_per_step * 1e-3), "pixels_per_s": W * H / (ms_per_step * 1e-3),
-            "stages_ms": ({"clear+trace": float(stages[0]), "allreduce": float(stages[1]), "build_map+tables": float(stages[2]),
-                           "render(+gather)": float(stages[3])} if a.mode == "a" else
+            "config": workload_config(a, {"parallelism": "photon-range x%d + row-band x%d" % (world, world),
+                                          "exchange": ("peer memory (pm_peer.cu, CUDA IPC)" if peers else "NCCL all-reduce") if world > 1 else "none",
+                                          "frames_in_flight": 1 if (a.no_overlap or a.mode == "b") else 2, "trace_sms": trace_sms or props.multi_processor_count}),
+            "photons_per_s": NP * a.passes / (ms_per_step * 1e-3), "pixels_per_s": W * H / (ms_per_step * 1e-3),
+            "frame_latency_ms": latency_ms,
+            "stages_ms": ({"clear+trace": float(stages[0]), "allreduce": (kern.get("peer_reduce_kernel", {}).get("avg_ms", 0.0) if peers else float(stages[1])),
+                           "build_map+tables": float(stages[2]) - (kern.get("peer_reduce_kernel", {}).get("avg_ms", 0.0) if peers else 0.0),
+                           "render(+assemble)": float(stages[3]),
+                           "note": "one frame on one stream (the instrumented pass; event records between the stages add a few us each); "
+                                   "allreduce = peer_reduce_kernel incl. waiting for the slowest rank"} if a.mode == "a" else
                           {"trace_with_records": float(stages[0]), "allgather_surface_records": float(stages[1]),
                            "allgather_volume_records||build_surface, build_volume": float(stages[2]),
-                           "knn_render(+gather)": float(stages[3])}),
+                           "knn_render(+sum)": float(stages[3])}),
             "gpu_launches": int(launches),
-            "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": C.sizeof(pmb200.Scene),
+            "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": C.sizeof(pmb200.Scene) * world,
                     "d2h_bytes_per_step": W * H * 4, "steps": e2e_steps,
-                    "what": ("pm_frame_host_async + pm_frame_wait per frame: scene struct in, emit + render, the reference's uchar4 "
-                             "frame copied to pinned host memory under the next frame's trace" if pipelined else
+                    "what": ("pm_frame_host_async + pm_frame_wait per frame on every rank: scene struct in, emit (+ exchange) + render, each rank's "
+                             "row band of the reference's uchar4 frame copied into one pinned host frame over its own PCIe link, two frames "
+                             "in flight, every frame waited for" if pipelined else
                              "step + D2H of the assembled uchar4 frame on rank 0, synchronous")},
             "kernels": kern,
-            "roofline": {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_ms,
-                         "issue_slots_busy_pct_ncu": issue_pct,   # the resource the kernel is actually bound by (profiles/, not live)
-                         "note": "Mode A keeps no photon records, so the compulsory HBM traffic of the fused trace kernel is one 12 B "
-                                 "direction per photon: its surface warps are instruction-issue bound and its medium-walk warps "
-                                 "L2-atomic bound (3 REDs per photon), not HBM bound; see DESIGN.md 'rooflines' and profiles/"},
             "clocks": clocks,
         }
+        if peers:
+            line["peer_exchange_ok"] = peer_ok
+        if dom == "trace_kernel":
+            # the Mode A trace keeps no records, so it is bound by FP32 issue (~400 flop per photon for the
+            # intersection / reflection / voxel arithmetic), not by HBM (12 B per photon)
+            flops = 400.0 * n_local
+            peak_tf = props.multi_processor_count * 128 * 2 * sm_mhz * 1e6 / 1e12
+            ach_tf = flops / (dom_ms * 1e-3) / 1e12
+            prof = {}
+            try:
+                prof = json.load(open(os.path.join(ROOT, "profiles", "r2_trace_ncu.json")))
+            except Exception:
+                pass
+            same = prof.get("photons") == NP and world == 1
+            line["roofline"] = {
+                "kernel": dom, "bound": "fp32_issue", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
+                "traffic": prof.get("dram_bytes_per_launch") if same else None,
+                "algorithmic_flop_per_photon": 400.0, "photons_per_launch": n_local, "avg_launch_ms": dom_ms,
+                "peak_source": "%d SMs x 128 FP32 lanes x 2 flop x %.0f MHz (sampled)" % (props.multi_processor_count, sm_mhz),
+                "hbm": {"achieved": 12.0 * n_local / (dom_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": 12.0 * n_local / (dom_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": peak_src,
+                        "algorithmic_bytes_per_photon": 12.0},
+                "ncu": ({k: prof.get(k) for k in ("issue_slots_busy_pct", "warp_instructions", "thread_instructions_per_photon",
+                                                  "active_lanes_per_instruction", "source")} if same else None),
+                "note": "FP32-issue roofline of SURVEY.md 8(d) (400 flop per photon); the HBM figure (one 12 B direction per photon) is "
+                        "given beside it -- the kernel is not HBM-bound; traffic / ncu.* are read from the committed ncu capture of this "
+                        "configuration (profiles/), not measured live"}
+        else:
+            alg = {"render_kernel": 20.0 * W * rows, "knn_render_kernel": 1632.0 * W * rows * 11}
+            bytes_ = alg.get(dom, 0.0)
+            line["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": bytes_ / (dom_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                "frac": bytes_ / (dom_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src}
+        line.update(extras)
         if not a.no_cpu_baseline and world == 1 and a.mode == "a":
             try:
-                v, d = cpu_reference_frame_ms(a)
+                from oracle import refhost
+                v, d = cpu_reference_frame_ms(a, *((1, 1) if refhost.available() else (16, 8)))
                 line["cpu_baseline"] = {"value": v, "unit": "ms", "cores": d["cores"], "kind": d["kind"], "sample": d["sample"],
-                                        "emit_ms_scaled": d["emit_ms_scaled"], "render_ms_scaled": d["render_ms_scaled"]}
+                                        "emit_ms": d["emit_ms"], "render_ms": d["render_ms"]}
             except Exception as ex:   # the baseline is reported, never required for the measurement itself
                 line["cpu_baseline"] = {"value": None, "unit": "ms", "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
-        if not a.no_mode_b and world == 1 and a.mode == "a":
+        if not a.no_mode_b and not a.no_extras and world == 1 and a.mode == "a":
             try:
                 line["mode_b"] = mode_b_numbers(pmb200, torch, a, local)
             except Exception as ex:
                 line["mode_b"] = {"failed": repr(ex)}
-        if not a.no_ref_cuda and world == 1 and a.mode == "a" and a.passes == 1:
+        if not a.no_ref_cuda and not a.no_extras and world == 1 and a.mode == "a" and a.passes == 1:
             try:
                 line["config2"] = config2_numbers(pmb200, torch, local)
             except Exception as ex:
                 line["config2"] = {"failed": repr(ex)}
         if not a.no_ref_cuda and world == 1 and a.mode == "a":
             try:
-                line["reference_cuda_kernel"] = time_reference_cuda(a, m.get_random_table(), rgba)
+                fb = torch.zeros((H, W, 4), dtype=torch.uint8, device="cuda")
+                rc = time_reference_cuda(a, m.get_random_table(), fb)
+                line["reference_cuda_kernel"] = rc
+                if "ms_per_frame" in rc:
+                    line["vs_reference_cuda_kernel"] = {"speedup": rc["ms_per_frame"] / ms_per_step, "e2e_speedup": rc["ms_per_frame"] / e2e_ms,
+                                                        "note": "the reference's own CUDA kernels (sm_100a build) on this GPU, same configuration, timed in this run"}
             except Exception as ex:
                 line["reference_cuda_kernel"] = {"unavailable": repr(ex)}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
+    if pipelined and shm_keep is not None:
+        del host_frames, done_words
+        shm_keep.close()
+    if peers:
+        m.shared_close(rgba_ptr, rgba_opened); m.shared_close(rgbf_ptr, rgbf_opened)
+        m.peer_disconnect()
+    if world > 1:
         dist.destroy_process_group()
 
 

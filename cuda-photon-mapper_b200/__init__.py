@@ -86,6 +86,7 @@ def lib():
             "launch_kernel": (None, [vp, C.c_uint, C.c_uint, f32, vp, vp]),
             "pm_frame_host_async": (i32, [vp, f32, b, b, b, i32, i32, vp, C.POINTER(C.c_int64)]),
             "pm_frame_wait": (i32, [vp, C.c_int64]), "pm_reserve_frame": (i32, [vp, i32, i32]),
+            "pm_frame_device": (i32, [vp, f32, b, b, b, i32, i32, vp, vp]), "pm_set_trace_sms": (i32, [vp, i32]),
             "pm_launch_count": (i64, [vp]),
             "pm_enable_timing": (i32, [vp, b]), "pm_kernel_count": (i32, []), "pm_kernel_name": (C.c_char_p, [i32]),
             "pm_get_timings": (i32, [vp, vp, vp]),
@@ -361,6 +362,13 @@ class PhotonMapper:
 
     def frame_wait(self, ticket):
         self._ck(self.L.pm_frame_wait(self.h, ticket))
+
+    def frame_device(self, w, h, rgba=None, rgbf=None, t=0.0, emit=True, interp=False, media=False):
+        """pm_frame_device: one pipelined frame into DEVICE buffers (this rank's row band; peer barrier when ranks are connected)."""
+        self._ck(self.L.pm_frame_device(self.h, t, emit, interp, media, w, h, _ptr(rgba), _ptr(rgbf)))
+
+    def set_trace_sms(self, sms):
+        self._ck(self.L.pm_set_trace_sms(self.h, sms))
 
     def launch_count(self):
         return self.L.pm_launch_count(self.h)

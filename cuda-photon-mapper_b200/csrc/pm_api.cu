@@ -114,6 +114,10 @@ int pm_create(pm_context **out, int device) {
   memset(&c->pv, 0, sizeof(c->pv));
   c->pv.world = 1; c->pv.rank = 0; c->pv.hdr[0] = (ExchangeHeader *)c->d_xchg; c->pv.acc[0] = c->d_acc;
   c->pv.timeout_ns = 5000000000ull;
+  for (int b = 0; b < kAccBuffers; b++) {
+    if ((e = cudaEventCreateWithFlags(&c->ev_reduced[b], cudaEventDisableTiming)) != cudaSuccess) return fail(e);
+    if ((e = cudaEventCreateWithFlags(&c->ev_cleared[b], cudaEventDisableTiming)) != cudaSuccess) return fail(e);
+  }
   if ((e = cudaMalloc(&c->d_grid, sizeof(float) * PM_GRID_FLOATS)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&c->d_vol, sizeof(float4) * kVolTableEntries)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&c->d_surf, sizeof(float4) * kSurfTableEntries)) != cudaSuccess) return fail(e);
@@ -147,6 +151,12 @@ int pm_destroy(pm_context *c) {
     if (c->ev_copied[k]) cudaEventDestroy(c->ev_copied[k]);
   }
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+  if (c->ev_traced) cudaEventDestroy(c->ev_traced);
+  for (int b = 0; b < kAccBuffers; b++) {
+    if (c->ev_reduced[b]) cudaEventDestroy(c->ev_reduced[b]);
+    if (c->ev_cleared[b]) cudaEventDestroy(c->ev_cleared[b]);
+  }
   knn_free(c->knn[0]); knn_free(c->knn[1]); cudaFree(c->d_work);
   for (auto &sp : c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
   delete c;
@@ -183,7 +193,9 @@ int pm_set_stream(pm_context *c, void *stream) {
 }
 int pm_sync(pm_context *c) {
   if (!c) return PM_ERR_ARG;
+  CK(c, cudaSetDevice(c->device));
   CK(c, cudaStreamSynchronize(c->stream));
+  if (c->aux_stream) CK(c, cudaStreamSynchronize(c->aux_stream));   // the second half of pipelined frames
   return PM_OK;
 }
 
@@ -291,12 +303,22 @@ int pm_get_random_table_host(pm_context *c, float *xyz, int64_t n) {
 int pm_clear_map(pm_context *c) {
   ARG(c, c != nullptr, "null context");
   CK(c, cudaSetDevice(c->device));
-  if (c->world > 1) {   // frames alternate between the two accumulator buffers (pm_peer.cu): peers may still be reading the other one
-    c->cur ^= 1;
-    c->d_acc = (long long *)((ExchangeHeader *)c->d_xchg + 1) + (size_t)c->cur * kAccStride;
-  }
+  // Frames rotate through the accumulator buffers: the pipelined frame calls build the map of frame f on a second stream while
+  // this stream already clears and traces frame f+1, and with peers connected other ranks may still be reading frame f's buffer.
+  c->frame_no++;
+  c->cur = (int)(c->frame_no % kAccBuffers);
+  c->d_acc = (long long *)((ExchangeHeader *)c->d_xchg + 1) + (size_t)c->cur * kAccStride;
   c->acc_summed = false;
-  CK(c, cudaMemsetAsync(c->d_acc, 0, sizeof(long long) * kAccStride, c->stream));   // the buffer and its flag words
+  if (c->precleared[c->cur]) {   // pm_build_map of two frames ago has already cleared it (off this stream): wait for that only
+    CK(c, cudaStreamWaitEvent(c->stream, c->ev_cleared[c->cur], 0));
+    c->precleared[c->cur] = false;
+  } else {
+    // this buffer was last used three frames ago: our own reader of it (map build or reduce) has run ...
+    CK(c, cudaStreamWaitEvent(c->stream, c->ev_reduced[c->cur], 0));
+    // ... and every PEER has finished reading it once our reduce of the frame after that one has run (see pm_peer.cu): two frames old
+    if (c->world > 1 && c->frame_no >= 2) CK(c, cudaStreamWaitEvent(c->stream, c->ev_reduced[(c->frame_no - 2) % kAccBuffers], 0));
+    CK(c, cudaMemsetAsync(c->d_acc, 0, sizeof(long long) * kAccStride, c->stream));   // the buffer and its flag words
+  }
   if (c->d_rec_count) CK(c, cudaMemsetAsync(c->d_rec_count, 0, sizeof(unsigned long long), c->stream));
   c->vrec_count = 0;
   c->tables_valid = false;
@@ -322,6 +344,12 @@ int pm_set_record_capacity(pm_context *c, int64_t cap) {
 int pm_set_volume_warps(pm_context *c, int warps) {
   ARG(c, c != nullptr && warps >= 1 && warps <= 16, "volume warps must be 1..16");
   c->vol_warps = warps;
+  return PM_OK;
+}
+
+int pm_set_trace_sms(pm_context *c, int sms) {
+  ARG(c, c != nullptr && sms >= 0, "bad SM count");
+  c->trace_sms = sms;
   return PM_OK;
 }
 
@@ -360,7 +388,8 @@ int pm_trace(pm_context *c, float t, unsigned flags) {
     const int vol_warps = ((flags & PM_TRACE_MEDIA) && !(flags & PM_TRACE_SPLIT)) ? c->vol_warps : 0;
     c->launches += launch_trace(c->dsc, c->d_table, c->first, c->last, flags, vol_warps, c->mwc_w, c->mwc_z, c->d_jump,
                                 (unsigned long long *)c->d_acc, c->d_vol_cnt, c->d_rec_pos, c->d_rec_pow, c->d_rec_dir, c->d_vrec_pos,
-                                c->d_vrec_pow, c->vrec_cap, c->d_rec_count, c->rec_cap, c->num_sms, c->stream, &terr, c->d_trace_dbg,
+                                c->d_vrec_pow, c->vrec_cap, c->d_rec_count, c->rec_cap,
+                                (c->trace_sms > 0 && c->trace_sms < c->num_sms) ? c->trace_sms : c->num_sms, c->stream, &terr, c->d_trace_dbg,
                                 (uint32_t *)(c->d_acc + kAccEntries));
   }
   CK(c, terr);
@@ -404,6 +433,7 @@ int pm_accumulators(pm_context *c, void **dev_ptr, size_t *n) {
 int pm_get_accumulators_host(pm_context *c, int64_t *out) {
   ARG(c, c && out, "null argument");
   CK(c, cudaSetDevice(c->device));
+  if (c->aux_stream) CK(c, cudaStreamSynchronize(c->aux_stream));
   CK(c, cudaMemcpyAsync(out, c->acc_summed ? c->d_acc_sum : c->d_acc, sizeof(long long) * kAccEntries, cudaMemcpyDeviceToHost, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));
   return PM_OK;
@@ -419,6 +449,7 @@ int pm_build_map(pm_context *c) {
     // ranks that share a device (tests) must leave SMs for each other's trace while they spin
     const int blocks = c->peer_on_same_device ? 16 : c->num_sms;
     CK(c, launch_peer_reduce(c->pv, c->cur, ++c->seq[0], c->d_acc_sum, blocks, c->stream));
+    CK(c, cudaEventRecord(c->ev_reduced[c->cur], c->stream));
     c->launches++;
     c->acc_summed = true;
     src = c->d_acc_sum;
@@ -426,6 +457,18 @@ int pm_build_map(pm_context *c) {
   {
     SpanGuard g(c, K_BUILD_MAP);
     CK(c, launch_build_map(src, c->energy_scale, c->d_grid, c->stream));
+  }
+  if (c->world == 1) CK(c, cudaEventRecord(c->ev_reduced[c->cur], c->stream));   // the last reader of this accumulator buffer
+  // The PREVIOUS frame's buffer can be cleared for its next use (two frames from now) as soon as this frame's reader has run: without
+  // peers its own reader ran earlier; with peers our reduce of this frame has seen every peer's signal, which each peer sends only
+  // after its reads of the previous frame's buffers.  Doing it here keeps the 1.2 MB memset off the stream the next trace runs on.
+  if (c->frame_no >= 1 && c->preclear_frame != c->frame_no) {
+    const int prev = (int)((c->frame_no - 1) % kAccBuffers);
+    CK(c, cudaStreamWaitEvent(c->stream, c->ev_reduced[prev], 0));
+    CK(c, cudaMemsetAsync((long long *)((ExchangeHeader *)c->d_xchg + 1) + (size_t)prev * kAccStride, 0, sizeof(long long) * kAccStride, c->stream));
+    CK(c, cudaEventRecord(c->ev_cleared[prev], c->stream));
+    c->precleared[prev] = true;
+    c->preclear_frame = c->frame_no;
   }
   {
     SpanGuard g(c, K_BUILD_TABLES);
@@ -438,6 +481,7 @@ int pm_build_map(pm_context *c) {
 int pm_get_map_host(pm_context *c, float *grid) {
   ARG(c, c && grid, "null argument");
   CK(c, cudaSetDevice(c->device));
+  if (c->aux_stream) CK(c, cudaStreamSynchronize(c->aux_stream));
   CK(c, cudaMemcpyAsync(grid, c->d_grid, sizeof(float) * PM_GRID_FLOATS, cudaMemcpyDeviceToHost, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));
   return PM_OK;
@@ -785,6 +829,42 @@ int pm_frame_host(pm_context *c, float t, bool emit, bool interp, bool media, in
   return pm_render_host(c, t, interp, media, width, height, host_rgba, host_rgbf);
 }
 
+// One frame with two frames in flight: (emit: clear + trace) on the context's stream, then exchange + map build + render -- and the
+// rank barrier when asked -- on the auxiliary stream, so the next frame's trace does not wait for them (the accumulators
+// rotate through three buffers for exactly that, pm_peer.cu).  At 8 GPUs the part after the trace is a chain of small,
+// latency-bound kernels about half as long as the trace itself.
+static int frame_stages(pm_context *c, float t, bool emit, bool interp, bool media, int width, int height, int y0, int y1,
+                        pm_uchar4 *dev_rgba, float *dev_rgbf, cudaEvent_t wait_before_render, bool barrier_after) {
+  if (!c->aux_stream) {
+    CK(c, cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+    CK(c, cudaEventCreateWithFlags(&c->ev_traced, cudaEventDisableTiming));
+  }
+  int rc;
+  if (emit) {
+    if ((rc = pm_clear_map(c)) != PM_OK) return rc;
+    if ((rc = pm_trace(c, t, media ? PM_TRACE_MEDIA : 0u)) != PM_OK) return rc;
+  }
+  CK(c, cudaEventRecord(c->ev_traced, c->stream));
+  CK(c, cudaStreamWaitEvent(c->aux_stream, c->ev_traced, 0));
+  if (wait_before_render) CK(c, cudaStreamWaitEvent(c->aux_stream, wait_before_render, 0));
+  cudaStream_t main_stream = c->stream;
+  c->stream = c->aux_stream;   // pm_build_map / pm_render / pm_peer_barrier launch on the context's current stream
+  rc = emit ? pm_build_map(c) : PM_OK;
+  if (rc == PM_OK) rc = pm_render(c, t, interp, media, width, height, y0, y1, dev_rgba, dev_rgbf);
+  if (rc == PM_OK && barrier_after) rc = pm_peer_barrier(c);
+  c->stream = main_stream;
+  return rc;
+}
+
+int pm_frame_device(pm_context *c, float t, bool emit, bool interp, bool media, int width, int height, pm_uchar4 *dev_rgba, float *dev_rgbf) {
+  ARG(c, c != nullptr, "null context");
+  ARG(c, width > 0 && height > 0, "bad frame geometry");
+  CK(c, cudaSetDevice(c->device));
+  int y0, y1;
+  frame_rows(c, height, &y0, &y1);
+  return frame_stages(c, t, emit, interp, media, width, height, y0, y1, dev_rgba, dev_rgbf, nullptr, c->world > 1);
+}
+
 int pm_frame_host_async(pm_context *c, float t, bool emit, bool interp, bool media, int width, int height, pm_uchar4 *host_rgba,
                         int64_t *ticket) {
   ARG(c, c != nullptr && host_rgba != nullptr && ticket != nullptr, "null argument");
@@ -797,17 +877,12 @@ int pm_frame_host_async(pm_context *c, float t, bool emit, bool interp, bool med
   }
   const int64_t tk = c->next_ticket;
   const int k = (int)(tk & 1);
-  CK(c, cudaStreamWaitEvent(c->stream, c->ev_copied[k], 0));   // the copy two frames ago has drained this buffer
-  int rc;
-  if (emit) {
-    if ((rc = pm_clear_map(c)) != PM_OK) return rc;
-    if ((rc = pm_trace(c, t, media ? PM_TRACE_MEDIA : 0u)) != PM_OK) return rc;
-    if ((rc = pm_build_map(c)) != PM_OK) return rc;
-  }
   int y0, y1;
   frame_rows(c, height, &y0, &y1);
-  if ((rc = pm_render(c, t, interp, media, width, height, y0, y1, (pm_uchar4 *)c->d_fb_async[k], nullptr)) != PM_OK) return rc;
-  CK(c, cudaEventRecord(c->ev_rendered[k], c->stream));
+  // the render waits until the copy two frames ago has drained this frame buffer
+  int rc = frame_stages(c, t, emit, interp, media, width, height, y0, y1, (pm_uchar4 *)c->d_fb_async[k], nullptr, c->ev_copied[k], false);
+  if (rc != PM_OK) return rc;
+  CK(c, cudaEventRecord(c->ev_rendered[k], c->aux_stream));
   CK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_rendered[k], 0));
   const size_t off = (size_t)y0 * width, cnt = (size_t)(y1 - y0) * width;
   if (cnt) CK(c, cudaMemcpyAsync(host_rgba + off, c->d_fb_async[k] + off, sizeof(uchar4) * cnt, cudaMemcpyDeviceToHost, c->copy_stream));
@@ -875,6 +950,8 @@ static void peer_finish(pm_context *c, int rank, int world) {
   c->pv.hdr[rank] = (ExchangeHeader *)c->d_xchg;
   for (int p = 0; p < world; p++) c->pv.acc[p] = (const long long *)(c->pv.hdr[p] + 1);
   c->cur = 0; c->d_acc = (long long *)((ExchangeHeader *)c->d_xchg + 1);
+  c->frame_no = 0; c->preclear_frame = -1;
+  for (int b = 0; b < kAccBuffers; b++) c->precleared[b] = false;
   c->acc_summed = false;
 }
 
@@ -969,6 +1046,7 @@ int pm_peer_status(pm_context *c) {
   ARG(c, c != nullptr, "null context");
   CK(c, cudaSetDevice(c->device));
   CK(c, cudaStreamSynchronize(c->stream));
+  if (c->aux_stream) CK(c, cudaStreamSynchronize(c->aux_stream));
   uint32_t e = 0;
   CK(c, cudaMemcpy(&e, &((ExchangeHeader *)c->d_xchg)->error, sizeof(e), cudaMemcpyDeviceToHost));
   if (e) { c->err = e == 1 ? "a peer never signalled its accumulators (wait timed out)" : "a peer never reached the barrier (wait timed out)"; return PM_ERR_STATE; }

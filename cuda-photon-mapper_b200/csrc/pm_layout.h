@@ -32,8 +32,8 @@ constexpr double kHitScale      = 16777216.0;          // 2^24
 constexpr double kVoxScale      = 68719476736.0;       // 2^36
 
 // ---- multi-GPU exchange block (pm_peer.cu): ONE device allocation per context, visible to the other ranks (peer access
-// inside a process, CUDA IPC between processes): a header of flags followed by the two accumulator buffers (frames
-// alternate between them, see pm_peer.cu).
+// inside a process, CUDA IPC between processes): a header of flags followed by kAccBuffers accumulator buffers (frames
+// rotate through them, see pm_peer.cu).
 constexpr int kMaxPeers = 16;
 struct ExchangeHeader {
   uint32_t arrive[2][kMaxPeers];   // [channel][peer rank]: latest sequence number that peer has signalled (0 = accumulators, 1 = barrier)
@@ -44,7 +44,8 @@ static_assert(sizeof(ExchangeHeader) == 256, "exchange header is 256 bytes");
 // each accumulator buffer is followed by 256 bytes of per-buffer flags, cleared with it: word 0 of entry kAccEntries is
 // "vox_touched" (something was deposited into the acc_vox section of this buffer)
 constexpr int    kAccStride = kAccEntries + 32;
-constexpr size_t kExchangeBytes = sizeof(ExchangeHeader) + 2 * sizeof(long long) * (size_t)kAccStride;
+constexpr int    kAccBuffers = 3;
+constexpr size_t kExchangeBytes = sizeof(ExchangeHeader) + kAccBuffers * sizeof(long long) * (size_t)kAccStride;
 
 // ---- gather tables, rebuilt from the float photon map whenever it changes -------------------------------
 // The reference's gathers depend only on the integer voxel of the query point, so their sums are tabulated

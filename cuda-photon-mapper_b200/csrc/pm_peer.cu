@@ -13,10 +13,12 @@
 //            same bits).  The acc_vox section (786 KB of the 1.2 MB, all zero unless a wall lies off the map boundary) is
 //            only read from ranks whose vox_touched flag is set.
 //
-// The accumulators are double-buffered per frame: a rank clears buffer b again two frames later, after its reduce of the
-// frame in between has seen every peer's signal -- which each peer sends only after finishing its own reads of buffer b
-// (stream order), so no "consumed" handshake is needed.  A peer that never arrives trips a timeout (error word) instead
-// of hanging the GPU.
+// The accumulators rotate through three buffers, so that a frame's trace never waits for the previous frame's exchange (the
+// host side runs clear + trace on one stream and exchange + map build + render on another, two frames in flight).  A rank
+// clears buffer b again three frames later, after its OWN reduce of frame f+1 has completed (an event wait in pm_clear_map,
+// two frames old by then): that reduce saw every peer's signal f+1, which each peer sends only after finishing its reduce of
+// frame f -- its reads of buffer b -- in stream order.  So no "consumed" handshake is needed.  A peer that never arrives trips
+// a timeout (error word) instead of hanging the GPU.
 #include "pm_kernels.cuh"
 
 namespace pm {

@@ -324,7 +324,10 @@ enum : int { ST_IDLE = 0, ST_PRIMARY, ST_SHADOW, ST_CHAIN_R, ST_CHAIN_F1, ST_CHA
 
 constexpr int kSurfaceThreads = 1024;
 constexpr int kRefillLanes = 8;   // measured: 4 is 13% slower, 12 and 16 are the same as 8; taking chunks off a CTA-wide cursor
-                                  // instead of static per-warp slices is 20% slower; prefetching the table rows changes nothing
+                                  // instead of static per-warp slices is 20% slower; prefetching the table rows changes nothing.
+                                  // Round 2 (the slowest warp of a CTA ends 5% after the mean at 16M photons, 11% at 2M): pooling only the
+                                  // last 1/8..1/2 of every slice in 32..256-photon chunks, 32-bit cursors, no spills: still 4-27% slower
+                                  // (0.985 -> 1.03..1.25 ms) -- every refill at a chunk boundary leaves lanes idle for an iteration
 constexpr int kShadowEntries = kAccHitEntries / 4;                                      // one per wall texel
 constexpr size_t kSurfaceSmem = sizeof(uint32_t) * (2 * kAccHitEntries + kShadowEntries);   // 184 320 B
 

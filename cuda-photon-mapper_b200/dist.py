@@ -58,6 +58,56 @@ def shared_frame(mapper, nbytes):
     return ptr, False
 
 
+def shared_host_frames(count, nbytes, world):
+    """`count` page-locked host frames of `nbytes` that EVERY rank process can write (POSIX shared memory, registered with CUDA in
+    each process), plus an int64 [count, world] array of completion words in the same segment.  Every rank copies its own row band
+    of a frame into it over its own PCIe link; rank 0 reads the assembled frame.  Single process: plain pinned tensors.
+    Returns (frames, done_words, keepalive)."""
+    import numpy as np
+    if world == 1 or not (dist.is_available() and dist.is_initialized()):
+        return [torch.empty(nbytes, dtype=torch.uint8).pin_memory() for _ in range(count)], np.zeros((count, 1), np.int64), None
+    from multiprocessing import shared_memory, resource_tracker
+    stride = (nbytes + 4095) // 4096 * 4096
+    total = count * stride + 4096
+    box = [None]
+    if dist.get_rank() == 0:
+        shm = shared_memory.SharedMemory(create=True, size=total)
+        box[0] = shm.name
+    dist.broadcast_object_list(box, src=0)
+    if dist.get_rank() != 0:
+        shm = shared_memory.SharedMemory(name=box[0])
+        try:    # only the creating process owns (and unlinks) the segment
+            resource_tracker.unregister(shm._name, "shared_memory")
+        except Exception:
+            pass
+    buf = np.ndarray((total,), np.uint8, buffer=shm.buf)
+    rc = torch.cuda.cudart().cudaHostRegister(buf.ctypes.data, total, 0)
+    if int(rc) != 0:
+        raise RuntimeError("cudaHostRegister failed: %r" % (rc,))
+    frames = [buf[i * stride:i * stride + nbytes] for i in range(count)]
+    done = np.ndarray((count, world), np.int64, buffer=shm.buf, offset=count * stride)
+    if dist.get_rank() == 0:
+        done[:] = 0
+    dist.barrier()
+
+    class _Keep:
+        def __init__(self, shm, ptr):
+            self.shm, self.ptr = shm, ptr
+
+        def close(self):
+            try:
+                torch.cuda.cudart().cudaHostUnregister(self.ptr)
+            except Exception:
+                pass
+            try:
+                self.shm.close()
+                if dist.get_rank() == 0:
+                    self.shm.unlink()
+            except Exception:
+                pass
+    return frames, done, _Keep(shm, buf.ctypes.data)
+
+
 class _RawCuda:
     def __init__(self, ptr, n, typestr):
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}

@@ -113,6 +113,10 @@ int pm_clear_map(pm_context *ctx);                                 /* init_photo
 int pm_trace(pm_context *ctx, float animTime, unsigned flags);
 /* tuning: how many of a CTA's 32 warps run the medium walk in the fused trace kernel (default 6; 1..16) */
 int pm_set_volume_warps(pm_context *ctx, int warps);
+/* tuning: CTAs of the persistent trace kernel (default 0 = one per SM).  Fewer leaves SMs free for the previous frame's exchange +
+ * map build + render, which the pipelined frame calls run on a second stream (worth it when those are a large part of the frame,
+ * i.e. at 4-8 GPUs) */
+int pm_set_trace_sms(pm_context *ctx, int sms);
 /* the exact (int64 fixed-point) accumulators the trace adds into; sum them across GPUs (e.g. NCCL
  * all-reduce, ncclInt64/ncclSum) between pm_trace and pm_build_map for multi-GPU runs */
 int pm_accumulators(pm_context *ctx, void **dev_ptr, size_t *n_int64);
@@ -193,6 +197,13 @@ int pm_frame_host(pm_context *ctx, float animTime, bool emitFlag, bool interpola
 int pm_frame_host_async(pm_context *ctx, float animTime, bool emitFlag, bool interpolateFlag, bool participatingMediaFlag,
                         int width, int height, pm_uchar4 *host_rgba, int64_t *ticket);
 int pm_frame_wait(pm_context *ctx, int64_t ticket);
+/* the same pipeline with the frame left in DEVICE memory (dev_rgba / dev_rgbf: whole-frame buffers, either may be NULL; the
+ * rows of pm_set_row_band are written).  Everything is enqueued: (emit: clear + trace) on the context's stream, exchange +
+ * map build + render on a second stream, so two frames are in flight.  With peers connected, dev_* may be another rank's
+ * memory (pm_shared_open): every rank renders its band straight into rank 0's frame over NVLink, and a device-side barrier
+ * follows -- when a rank's pm_sync returns, every band of that frame has landed. */
+int pm_frame_device(pm_context *ctx, float animTime, bool emitFlag, bool interpolateFlag, bool participatingMediaFlag,
+                    int width, int height, pm_uchar4 *dev_rgba, float *dev_rgbf);
 /* allocate the context-owned device frame buffers of the *_host calls up front (they are otherwise sized on first use) */
 int pm_reserve_frame(pm_context *ctx, int width, int height);
 

@@ -155,3 +155,25 @@ def test_ipc_ranks_bit_identical(pm, world):
     for f in range(3):
         assert np.array_equal(z["u8_%d" % f], ref[f][0]), f
         assert z["map_%d" % f].tobytes() == ref[f][2].tobytes(), f
+
+
+def test_frame_device_pipeline_matches_serial_frames(pm):
+    """pm_frame_device (clear + trace on one stream, map build + render on a second, accumulators rotating through three buffers)
+    gives the frames of the one-stream pm_frame_host, bit for bit, also when several frames are enqueued back to back."""
+    import torch
+    ref = _single(pm, True, 0.0, frames=5)
+    m = pm.PhotonMapper(n_photons=N)
+    sc = pm.default_scene(sz_img=H); sc.cam_ox = -(W - H) / 2.0
+    m.set_scene(sc)
+    m.init_random_numbers()
+    u8 = [torch.zeros((H, W, 4), dtype=torch.uint8, device="cuda") for _ in range(5)]
+    f32 = [torch.zeros((H, W, 4), dtype=torch.float32, device="cuda") for _ in range(5)]
+    torch.cuda.synchronize()
+    for f in range(5):
+        m.frame_device(W, H, rgba=u8[f], rgbf=f32[f], t=0.1 * f, emit=True, interp=False, media=True)
+    m.sync()
+    for f in range(5):
+        assert np.array_equal(u8[f].cpu().numpy(), ref[f][0]), f
+        assert f32[f].cpu().numpy().tobytes() == ref[f][1].tobytes(), f
+    assert m.get_map().tobytes() == ref[4][2].tobytes()
+    m.close()
