@@ -385,10 +385,12 @@ def main():
         if not peers:
             m.peer_disconnect()
     if peers:
+        # the reference's output, the uchar4 frame, is assembled on rank 0 (7/8 of 8.3 MB inbound at 8 GPUs); the headless float4
+        # framebuffer stays distributed, every rank keeping its band (assembling its 33 MB on one GPU saturated rank 0's NVLink
+        # ingress: 40 us per frame at 8 GPUs)
         rgba_ptr, rgba_opened = pmdist.shared_frame(m, W * H * 4)
-        rgbf_ptr, rgbf_opened = pmdist.shared_frame(m, W * H * 16)
         rgba = pmdist.device_tensor(rgba_ptr, W * H * 4, "|u1").view(H, W, 4) if rank == 0 else rgba_ptr
-        rgbf = pmdist.device_tensor(rgbf_ptr, W * H * 4, "<f4").view(H, W, 4) if rank == 0 else rgbf_ptr
+        rgbf = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
     else:
         rgba = torch.zeros((H, W, 4), dtype=torch.uint8, device="cuda")
         rgbf = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
@@ -415,7 +417,6 @@ def main():
             m.peer_barrier()                      # every rank's band has landed in rank 0's frame buffers
         elif world > 1:
             pmdist.gather_frame(rgba, y0, y1)
-            pmdist.gather_frame(rgbf, y0, y1)
 
     def step_serial(e=None):
         """One frame on one stream, nothing in flight (--no-overlap, and the instrumented pass that splits the frame into stages)."""
@@ -531,7 +532,7 @@ def main():
     pipelined = a.mode == "a" and a.passes == 1 and (peers or world == 1)
     pending = []
     if pipelined:
-        host_frames, done_words, shm_keep = pmdist.shared_host_frames(2, W * H * 4, world)
+        host_frames, done_words, shm_keep = pmdist.shared_host_frames(3, W * H * 4, world)
     else:
         host_frames = [torch.empty((H, W, 4), dtype=torch.uint8).pin_memory()]
     n_sub = [0]
@@ -540,18 +541,18 @@ def main():
         tk, n = pending.pop(0)
         m.frame_wait(tk)                          # this rank's band of frame n is in host memory
         if world > 1:
-            done_words[n & 1, rank] = n + 1
+            done_words[n % 3, rank] = n + 1
             if rank == 0:                         # ... and so is every other rank's
-                while int(done_words[n & 1].min()) < n + 1:
+                while int(done_words[n % 3].min()) < n + 1:
                     pass
 
     def e2e_step():
         m.set_scene(scene)                        # the frame's only host input: the scene / parameter block
         if pipelined:
             n = n_sub[0]; n_sub[0] += 1
-            pending.append((m.frame_async(W, H, host_frames[n & 1], t=0.0, emit=True, interp=False, media=True), n))
-            if len(pending) > 1:
-                e2e_retire()                      # frame f-1 is complete in host memory before frame f+1 is submitted
+            pending.append((m.frame_async(W, H, host_frames[n % 3], t=0.0, emit=True, interp=False, media=True), n))
+            if len(pending) > 2:
+                e2e_retire()                      # frame f-2 is complete in host memory before frame f+1 is submitted
         else:
             step()
             if after: after()
@@ -666,8 +667,8 @@ def main():
             "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": C.sizeof(pmb200.Scene) * world,
                     "d2h_bytes_per_step": W * H * 4, "steps": e2e_steps,
                     "what": ("pm_frame_host_async + pm_frame_wait per frame on every rank: scene struct in, emit (+ exchange) + render, each rank's "
-                             "row band of the reference's uchar4 frame copied into one pinned host frame over its own PCIe link, two frames "
-                             "in flight, every frame waited for" if pipelined else
+                             "row band of the reference's uchar4 frame copied into one pinned host frame over its own PCIe link, up to three "
+                             "frames in flight, every frame waited for" if pipelined else
                              "step + D2H of the assembled uchar4 frame on rank 0, synchronous")},
             "kernels": kern,
             "clocks": clocks,
@@ -740,7 +741,7 @@ def main():
         del host_frames, done_words
         shm_keep.close()
     if peers:
-        m.shared_close(rgba_ptr, rgba_opened); m.shared_close(rgbf_ptr, rgbf_opened)
+        m.shared_close(rgba_ptr, rgba_opened)
         m.peer_disconnect()
     if world > 1:
         dist.destroy_process_group()

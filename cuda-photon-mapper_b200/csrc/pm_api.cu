@@ -145,7 +145,7 @@ int pm_destroy(pm_context *c) {
   cudaFree(c->d_table); cudaFree(c->d_xchg); cudaFree(c->d_acc_sum); cudaFree(c->d_vol_cnt); cudaFree(c->d_grid); cudaFree(c->d_vol); cudaFree(c->d_surf);
   cudaFree(c->d_jump); cudaFree(c->d_rec_pos); cudaFree(c->d_rec_pow); cudaFree(c->d_rec_dir); cudaFree(c->d_rec_count);
   cudaFree(c->d_fb_u8); cudaFree(c->d_fb_f32); cudaFree(c->d_vrec_pos); cudaFree(c->d_vrec_pow); cudaFree(c->d_trace_dbg);
-  for (int k = 0; k < 2; k++) {
+  for (int k = 0; k < pm_context::kFrameRing; k++) {
     cudaFree(c->d_fb_async[k]);
     if (c->ev_rendered[k]) cudaEventDestroy(c->ev_rendered[k]);
     if (c->ev_copied[k]) cudaEventDestroy(c->ev_copied[k]);
@@ -768,7 +768,7 @@ static void frame_rows(const pm_context *c, int height, int *y0, int *y1) {
 static int ensure_async_buffers(pm_context *c, int64_t pixels) {
   if (!c->copy_stream) {
     CK(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < pm_context::kFrameRing; k++) {
       CK(c, cudaEventCreateWithFlags(&c->ev_rendered[k], cudaEventDisableTiming));
       CK(c, cudaEventCreateWithFlags(&c->ev_copied[k], cudaEventDisableTiming));
     }
@@ -776,11 +776,11 @@ static int ensure_async_buffers(pm_context *c, int64_t pixels) {
   if (pixels > c->async_pixels) {
     CK(c, cudaStreamSynchronize(c->stream));
     CK(c, cudaStreamSynchronize(c->copy_stream));
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < pm_context::kFrameRing; k++) {
       cudaFree(c->d_fb_async[k]); c->d_fb_async[k] = nullptr;
     }
     c->async_pixels = 0;
-    for (int k = 0; k < 2; k++) CK(c, cudaMalloc(&c->d_fb_async[k], sizeof(uchar4) * (size_t)pixels));
+    for (int k = 0; k < pm_context::kFrameRing; k++) CK(c, cudaMalloc(&c->d_fb_async[k], sizeof(uchar4) * (size_t)pixels));
     c->async_pixels = pixels;
   }
   return PM_OK;
@@ -876,10 +876,10 @@ int pm_frame_host_async(pm_context *c, float t, bool emit, bool interp, bool med
     if (rc0 != PM_OK) return rc0;
   }
   const int64_t tk = c->next_ticket;
-  const int k = (int)(tk & 1);
+  const int k = (int)(tk % pm_context::kFrameRing);
   int y0, y1;
   frame_rows(c, height, &y0, &y1);
-  // the render waits until the copy two frames ago has drained this frame buffer
+  // the render waits until the copy three frames ago has drained this frame buffer
   int rc = frame_stages(c, t, emit, interp, media, width, height, y0, y1, (pm_uchar4 *)c->d_fb_async[k], nullptr, c->ev_copied[k], false);
   if (rc != PM_OK) return rc;
   CK(c, cudaEventRecord(c->ev_rendered[k], c->aux_stream));
@@ -894,9 +894,9 @@ int pm_frame_host_async(pm_context *c, float t, bool emit, bool interp, bool med
 
 int pm_frame_wait(pm_context *c, int64_t ticket) {
   ARG(c, c != nullptr, "null context");
-  ARG(c, ticket >= 0 && ticket < c->next_ticket && ticket + 2 >= c->next_ticket, "ticket is not one of the two most recent frames");
+  ARG(c, ticket >= 0 && ticket < c->next_ticket && ticket + pm_context::kFrameRing >= c->next_ticket, "ticket is not one of the three most recent frames");
   CK(c, cudaSetDevice(c->device));
-  CK(c, cudaEventSynchronize(c->ev_copied[ticket & 1]));
+  CK(c, cudaEventSynchronize(c->ev_copied[ticket % pm_context::kFrameRing]));
   return PM_OK;
 }
 

@@ -35,7 +35,7 @@ struct pm_group {
   std::vector<std::unique_ptr<Worker>> workers;
   std::string err;
   int64_t next_ticket = 0;
-  int64_t ctx_ticket[2][kMaxPeers];
+  int64_t ctx_ticket[pm_context::kFrameRing][kMaxPeers];
   int64_t n_photons = 0;
   int64_t reserved_pixels = 0;
 };
@@ -231,7 +231,7 @@ int pm_group_frame_host_async(pm_group *g, float t, bool emit, bool interp, bool
     if (rc != PM_OK) return rc;
   }
   const int64_t tk = g->next_ticket++;
-  int64_t *slot = g->ctx_ticket[tk & 1];
+  int64_t *slot = g->ctx_ticket[tk % pm_context::kFrameRing];
   post_all(g, [=](pm_context *c, int r) {
     int rc = pm_set_row_band(c, (int)((int64_t)height * r / n), (int)((int64_t)height * (r + 1) / n));
     if (rc != PM_OK) return rc;
@@ -243,11 +243,11 @@ int pm_group_frame_host_async(pm_group *g, float t, bool emit, bool interp, bool
 
 int pm_group_frame_wait(pm_group *g, int64_t ticket) {
   if (!g) return PM_ERR_ARG;
-  if (!(ticket >= 0 && ticket < g->next_ticket && ticket + 2 >= g->next_ticket)) { g->err = "ticket is not one of the two most recent frames"; return PM_ERR_ARG; }
+  if (!(ticket >= 0 && ticket < g->next_ticket && ticket + pm_context::kFrameRing >= g->next_ticket)) { g->err = "ticket is not one of the three most recent frames"; return PM_ERR_ARG; }
   int rc = collect(g);   // every rank has enqueued its part of every submitted frame
   if (rc != PM_OK) return rc;
   for (int r = 0; r < g->n; r++) {
-    rc = pm_frame_wait(g->ctx[r], g->ctx_ticket[ticket & 1][r]);
+    rc = pm_frame_wait(g->ctx[r], g->ctx_ticket[ticket % pm_context::kFrameRing][r]);
     if (rc != PM_OK) { g->err = "rank " + std::to_string(r) + ": " + pm_last_error(g->ctx[r]); return rc; }
   }
   return PM_OK;

@@ -191,9 +191,10 @@ int pm_frame_host(pm_context *ctx, float animTime, bool emitFlag, bool interpola
                   int width, int height, pm_uchar4 *host_rgba, float *host_rgbf);
 /* the same frame, pipelined: everything is enqueued and the call returns at once with a ticket.  The uchar4 frame (the
  * reference's out_data) is copied to host_rgba -- pinned memory, or the copy is not asynchronous -- on the context's
- * copy stream from one of two device frame buffers, so the copy of frame f runs under the trace of frame f+1.
- * pm_frame_wait blocks until the frame of that ticket is in host memory; only the two most recent tickets are valid,
- * so wait for ticket f-1 (at the latest) before submitting frame f+1. */
+ * copy stream from a ring of three device frame buffers, so the copy of frame f runs under the trace of frame f+1.
+ * pm_frame_wait blocks until the frame of that ticket is in host memory; only the three most recent tickets are valid
+ * (three device frame buffers), so wait for ticket f-2 at the latest before submitting frame f+1 -- and give every frame in
+ * flight its own host buffer. */
 int pm_frame_host_async(pm_context *ctx, float animTime, bool emitFlag, bool interpolateFlag, bool participatingMediaFlag,
                         int width, int height, pm_uchar4 *host_rgba, int64_t *ticket);
 int pm_frame_wait(pm_context *ctx, int64_t ticket);

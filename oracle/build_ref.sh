@@ -12,6 +12,7 @@
 #   P1  '#define nrPhotons 10000'  ->  '#define nrPhotons PM_REF_CAPACITY'   (it is an in-file #define, -D cannot override it)
 #   P2  host build only: the photon grid and the MWC state become thread_local (private per OpenMP thread)
 #   P3  host build only: a record hook as the first statement of storePhoton / storeVolumePhoton
+#   P4  CUDA "atomic" flavour only: the three racy grid `+=` become atomicAdd (see below)
 # Nothing else is touched; the reference's own build system (none exists) is not used.
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
@@ -52,6 +53,21 @@ if [ -f "$HERE/ref_cuda_harness.cu" ] && command -v nvcc >/dev/null 2>&1; then
     nvcc -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -shared -w -Xlinker -Bsymbolic \
          -I"$HERE" -I"$HERE/shim" -DPM_REF_CAPACITY="$CAP" -DPM_REF_STAGED="\"$TMP/pmk_cuda.inc\"" \
          "$HERE/ref_cuda_harness.cu" -o "$OUT/libpmref_cuda_$CAP.so" &
+  done
+  wait
+  # ---- deterministic-deposit flavour: the reference kernel with its three racy `photons[..] += ..` sites (PMK:1068, :1158, :1177)
+  #      turned into atomicAdd and compiled -fmad=false.  What is left between it and the product / the oracle is the DEVICE
+  #      arithmetic of the reference -- rsqrtf in normalize (rsqrt.approx, 2 ulp) where the host build and the oracle use 1/sqrtf --
+  #      and the order of the float sums.  tests/test_gpu_fullsize.py measures the image distance against this build (P4).
+  sed -e 's/^#define nrPhotons 10000/#define nrPhotons PM_REF_CAPACITY/' \
+      -e 's/photons\[i\]\[j\]\[k\] += \(SPLAT_ENERGY_WEIGHT\*energy\/dist\);/pm_atomic_add3(\&photons[i][j][k], \1);/' \
+      -e 's/photons\[voxelPoint.x\]\[voxelPoint.y\]\[voxelPoint.z\] += energy;/pm_atomic_add3(\&photons[voxelPoint.x][voxelPoint.y][voxelPoint.z], energy);/' \
+      "$SRC" > "$TMP/pmk_cuda_atomic.inc"
+  [ "$(grep -c 'pm_atomic_add3' "$TMP/pmk_cuda_atomic.inc")" = "3" ]
+  for CAP in ${PM_REF_CAPACITIES_CUDA_ATOMIC:-65536 1048576}; do
+    nvcc -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -Xcompiler -fPIC -shared -w -Xlinker -Bsymbolic \
+         -I"$HERE" -I"$HERE/shim" -DPM_REF_ATOMIC -DPM_REF_CAPACITY="$CAP" -DPM_REF_STAGED="\"$TMP/pmk_cuda_atomic.inc\"" \
+         "$HERE/ref_cuda_harness.cu" -o "$OUT/libpmref_cuda_atomic_$CAP.so" &
   done
   wait
   ls "$OUT"/libpmref_cuda_*.so

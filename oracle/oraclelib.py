@@ -48,6 +48,8 @@ class Oracle:
         L.pmo_rand_float.restype = C.c_float
         L.pmo_rand_float.argtypes = [C.c_void_p, C.c_void_p, C.c_float]
         L.pmo_mwc_table.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.pmo_mwc_skip.argtypes = [C.c_void_p, C.c_void_p, C.c_long]
+        L.pmo_set_shadow_grid64.argtypes = [C.c_void_p]
         L.pmo_philox_table.argtypes = [C.c_uint64, C.c_void_p, C.c_int]
         L.pmo_position_objects.argtypes = [C.POINTER(Scene), C.c_float]
         L.pmo_emit.restype = C.c_long
@@ -85,6 +87,12 @@ class Oracle:
         self.lib.pmo_mwc_table(C.c_void_p(st.ctypes.data), C.c_void_p(st.ctypes.data + 4), _p(tab), n)
         return tab, (int(st[0]), int(st[1]))
 
+    def mwc_skip(self, n, w=6548, z=316):
+        """(w, z) after n serial draws."""
+        st = np.array([w, z], np.uint32)
+        self.lib.pmo_mwc_skip(C.c_void_p(st.ctypes.data), C.c_void_p(st.ctypes.data + 4), C.c_long(n))
+        return int(st[0]), int(st[1])
+
     def mwc_draws(self, n, w=6548, z=316):
         st = np.array([w, z], np.uint32)
         out = np.zeros(n, np.uint32)
@@ -104,8 +112,10 @@ class Oracle:
 
     # -- stage 1 -----------------------------------------------------------------------------------
     def emit(self, scene, table, n0, n1, t=0.0, media=False, rng=(6548, 316), grid=None, max_records=0,
-             want_grid=True):
-        """Returns (grid, records, rng_state_after).  grid is accumulated into (not cleared) if given."""
+             want_grid=True, shadow64=None):
+        """Returns (grid, records, rng_state_after).  grid is accumulated into (not cleared) if given.  shadow64: a float64
+        [32,32,32,3] array that receives the same deposits summed in double."""
+        self.lib.pmo_set_shadow_grid64(_p(shadow64) if shadow64 is not None else None)
         table = np.ascontiguousarray(table, np.float32)
         st = np.array(rng, np.uint32)
         if grid is None and want_grid:
@@ -114,6 +124,7 @@ class Oracle:
         cnt = self.lib.pmo_emit(C.byref(scene), t, _p(table), n0, n1, int(media),
                                 C.c_void_p(st.ctypes.data), C.c_void_p(st.ctypes.data + 4),
                                 _p(grid) if want_grid else None, _p(rec), max_records)
+        self.lib.pmo_set_shadow_grid64(None)
         if rec is not None:
             assert cnt <= max_records, (cnt, max_records)
             rec = rec[:cnt]

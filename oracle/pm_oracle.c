@@ -66,6 +66,11 @@ void pmo_mwc_table(uint32_t *w, uint32_t *z, float *xyz, int n) {
     xyz[3 * i + 2] = pmo_rand_float(w, z, 1.0f);
   }
 }
+/* n serial steps of the generator (get_random, PMK:1029-1037), results discarded: where the stream stands after the draws of the
+ * photons before a given one (9 per photon in the medium walk, PMK:1258-1262) -- the reference's one-thread loop, no jump-ahead */
+void pmo_mwc_skip(uint32_t *w, uint32_t *z, long n) {
+  for (long i = 0; i < n; i++) (void)pmo_mwc_next(w, z);
+}
 /* Philox4x32-10 (Salmon et al., SC'11; Random123) -- the counter-based alternative to the reference's MWC table for
  * throughput runs: row i of the table = randFloat-style mapping of the first three words of
  * philox(counter = (i, 0, 0, 0), key = (seed_lo, seed_hi)).  Not part of the reference; defined here, mirrored in
@@ -236,7 +241,19 @@ static void record(rec_sink *rs, int type, int id, int index, int kind, v3 loc, 
   }
   if (rs) rs->count++;
 }
-static inline void deposit(float *g, v3 e) { g[0] += e.x; g[1] += e.y; g[2] += e.z; }
+/* Every deposit is the reference's `photons[..] += e` in FP32 (PMK:1068, :1158, :1177).  Test aid: when a shadow grid is set
+ * (pmo_set_shadow_grid64) the SAME FP32 deposit values are also summed in double there -- what the deposits add up to without the
+ * rounding (and, at millions of photons, the saturation) of the reference's float voxels. */
+static double *g_shadow64 = NULL;
+static const float *g_shadow_base = NULL;
+void pmo_set_shadow_grid64(double *grid64) { g_shadow64 = grid64; }
+static inline void deposit(float *g, v3 e) {
+  g[0] += e.x; g[1] += e.y; g[2] += e.z;
+  if (g_shadow64 && g_shadow_base) {
+    double *d = g_shadow64 + (g - g_shadow_base);
+    d[0] += (double)e.x; d[1] += (double)e.y; d[2] += (double)e.z;
+  }
+}
 
 static void splat_neighbor(float *grid, v3 energy, const int v[3], int i, int j, int k) {
   if (v[0] != i || v[1] != j || v[2] != k) {
@@ -354,6 +371,7 @@ long pmo_emit(const pm_scene *scene, float t, const float *table, int n0, int n1
   pm_scene sc = *scene;
   pmo_position_objects(&sc, t);
   rec_sink rs; rs.rec = rec; rs.cap = max_rec; rs.count = 0;
+  g_shadow_base = grid;
   for (int i = n0; i < n1; i++) emit_one(&sc, table, i, media, w, z, grid, &rs);
   return rs.count;
 }

@@ -14,6 +14,7 @@ extern "C" {
 uint32_t pmo_mwc_next(uint32_t *w, uint32_t *z);
 float    pmo_rand_float(uint32_t *w, uint32_t *z, float max);
 void     pmo_mwc_table(uint32_t *w, uint32_t *z, float *xyz, int n);
+void     pmo_mwc_skip(uint32_t *w, uint32_t *z, long n);
 
 void     pmo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 void     pmo_philox_table(uint64_t seed, float *xyz, int n);
@@ -26,6 +27,8 @@ void pmo_voxel(const float p[3], int v[3]);
  * cleared; may be NULL) and/or `rec` (first max_rec store calls; may be NULL).  `table` is the whole random
  * table (entries 0..2 are also read by the medium scattering).  (w,z) is the MWC state the medium draws
  * continue from (the state left by pmo_mwc_table).  Returns the number of store calls. */
+/* test aid: also sum the (FP32) deposit values in double into grid64[32*32*32*3] (NULL switches it off) */
+void pmo_set_shadow_grid64(double *grid64);
 long pmo_emit(const pm_scene *scene, float t, const float *table, int n0, int n1, int media,
               uint32_t *w, uint32_t *z, float *grid, pm_record *rec, long max_rec);
 

@@ -12,6 +12,12 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 
+#ifdef PM_REF_ATOMIC   /* build_ref.sh P4: the deposit sites call this instead of the racy `+=` */
+static __device__ __forceinline__ void pm_atomic_add3(float3 *p, float3 v) {
+  atomicAdd(&p->x, v.x); atomicAdd(&p->y, v.y); atomicAdd(&p->z, v.z);
+}
+#endif
+
 #include PM_REF_STAGED   /* the whole reference file, streamed by build_ref.sh */
 
 #define RCK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "refcu: %s: %s\n", #x, cudaGetErrorString(e_)); return -1; } } while (0)

@@ -1,5 +1,5 @@
 """Error behaviour of the extended C-ABI: bad arguments and call-order violations return a negative pm_status with a
-message (the legacy three symbols abort like checkCUDAError instead, PMK:49-55; not exercised here because they exit)."""
+message (the legacy three symbols abort like checkCUDAError instead, PMK:49-55: tests/test_gpu_cli.py runs them in a subprocess)."""
 import ctypes as C
 
 import numpy as np

@@ -45,7 +45,7 @@ def test_mwc_table_bit_exact(pm, oracle):
 
 @pytest.mark.parametrize("media", [False, True])
 @pytest.mark.parametrize("t", [0.0, 0.7])
-@pytest.mark.parametrize("scene_name", ["default", "cfg1", "backwall5"])
+@pytest.mark.parametrize("scene_name", ["default", "cfg1", "backwall5", "smoke"])
 def test_trace_records_and_map(pm, oracle, media, t, scene_name):
     """Stage 1: photon records bit-exact (position, direction, power, object ids, order), photon map within MAP_TOL."""
     n = 20000
@@ -56,6 +56,8 @@ def test_trace_records_and_map(pm, oracle, media, t, scene_name):
         # back wall at z = 5 (as in the legacy variant, "photonMappingKernel - Copy.cu":28): its hits fall in voxel slab 26, not on
         # the map boundary slab 31 that splatEnergy hard-codes -> exercises the per-photon off-slab fallback of store_photon
         osc.planes[4][1] = 5.0
+    elif scene_name == "smoke":
+        osc.n_spheres = 3      # spheres[2], the large smoke sphere of the reference's screenshots (PMK:65)
     m = _mapper(pm, n, copy_scene(pm.Scene, osc))
     m.init_random_numbers()
     table, st = oracle.mwc_table(n)
@@ -109,6 +111,30 @@ def test_render_bit_exact_on_injected_map(pm, oracle, interp, media, t):
     assert bits_equal(f32[..., :3], oimg)
     assert np.all(f32[..., 3] == 1.0)
     assert np.array_equal(u8, ou8)
+    m.close()
+
+
+@pytest.mark.parametrize("interp", [False, True])
+def test_smoke_sphere_scene_frame(pm, oracle, interp):
+    """The smoke-sphere scene (n_spheres = 3, PMK:65) end to end: eye rays that end on the third sphere gather nothing (integrate /
+    interpolateEnergy return 0 for spheres), the ray-march still sees the medium in front of it.  Float frame bit-exact on the
+    oracle's map; product map within tolerance; the sphere covers a visible part of the frame."""
+    n, w, h, t = 20000, 256, 256, 0.4
+    osc = oracle.default_scene(sz_img=256)
+    osc.n_spheres = 3
+    table, st = oracle.mwc_table(n)
+    ogrid, _, _ = oracle.emit(osc, table, 0, n, t, True, rng=st)
+    oimg, ou8 = oracle.render(osc, ogrid, w, h, t, interp, True)
+    hit, _ = oracle.eye_geometry(osc, w, h, t)
+    on_smoke = (hit[..., 0] > 0) & (hit[..., 1] == 0) & (hit[..., 2] == 2)
+    assert on_smoke.mean() > 0.05
+    m = _mapper(pm, n, copy_scene(pm.Scene, osc))
+    m.init_random_numbers()
+    m.emit(t, media=True)
+    assert np.abs(m.get_map() - ogrid).max() <= MAP_TOL * np.abs(ogrid).max()
+    m.set_map(ogrid)
+    u8, f32 = m.render(w, h, t, interp, True)
+    assert bits_equal(f32[..., :3], oimg) and np.array_equal(u8, ou8)
     m.close()
 
 
@@ -301,7 +327,7 @@ def test_fused_trace_equals_split_trace(pm, oracle, warps):
 
 def test_pipelined_frames_equal_synchronous_frames(pm, oracle):
     """pm_frame_host_async / pm_frame_wait: five animated frames submitted back to back (copy of frame f under the trace of
-    frame f+1, two device frame buffers) are byte-identical to the same frames through the synchronous pm_frame_host."""
+    frame f+1, a ring of three device frame buffers) are byte-identical to the same frames through the synchronous pm_frame_host."""
     import torch
     w, h, n = 640, 360, 40000
     times = [0.0, 0.2, 0.4, 0.6, 0.8]
@@ -328,7 +354,7 @@ def test_pipelined_frames_equal_synchronous_frames(pm, oracle):
     for f in range(len(times)):
         assert np.array_equal(got[f], want[f]), f
     with pytest.raises(pm.PmError):
-        m.frame_wait(0)          # only the two most recent tickets can be waited for
+        m.frame_wait(0)          # only the three most recent tickets can be waited for
     m.close()
 
 

@@ -14,7 +14,7 @@ BACKWALL5_PLANES = np.array([[0, 1.5], [1, -1.5], [0, -1.5], [1, 1.5], [2, 5.0]]
 
 
 @pytest.mark.parametrize("scene_name,t,media", [("default", 0.0, False), ("default", 2.3, True), ("cfg1", 1.1, True),
-                                                 ("backwall5", 0.7, True)])
+                                                 ("backwall5", 0.7, True), ("smoke", 0.7, True), ("smoke", 0.0, False)])
 def test_frame_bit_exact(oracle, refhost, scene_name, t, media):
     n, w, h = 30000, 96, 96
     table, st = oracle.mwc_table(n)
@@ -26,6 +26,12 @@ def test_frame_bit_exact(oracle, refhost, scene_name, t, media):
     elif scene_name == "backwall5":
         sc.planes[4][1] = 5.0
         refhost.set_scene(planes=BACKWALL5_PLANES, sz_img=w)
+    elif scene_name == "smoke":
+        # the third sphere of the reference's scene table (spheres[2], the large "smoke" sphere of the screenshots, PMK:65), which
+        # nrObjects = {2, 5} leaves out: switched on with nrObjects = {3, 5}.  It is neither mirror nor glass: photons bounce off it
+        # through the diffuse branch (reflect3 with the sphere normal) and deposit nothing there (storePhoton ignores type 0)
+        sc.n_spheres = 3
+        refhost.set_scene(nr_objects=(3, 5), sz_img=w)
     else:
         refhost.set_scene(sz_img=w)
     refhost.set_table(table); refhost.set_rng(*st); refhost.clear_grid()
