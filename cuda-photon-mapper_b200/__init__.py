@@ -69,7 +69,7 @@ def lib():
             "pm_set_record_capacity": (i32, [vp, i64]), "pm_record_count": (i32, [vp, C.POINTER(i64)]),
             "pm_get_records_host": (i32, [vp, vp, i64]),
             "pm_record_buffers": (i32, [vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i64)]),
-            "pm_knn_set_curve": (i32, [vp, i32]), "pm_knn_build": (i32, [vp, i32]), "pm_knn_build_points": (i32, [vp, i32, vp, vp, i64, b]),
+            "pm_knn_set_curve": (i32, [vp, i32]), "pm_knn_set_batched": (i32, [vp, b]), "pm_knn_build": (i32, [vp, i32]), "pm_knn_build_points": (i32, [vp, i32, vp, vp, i64, b]),
             "pm_knn_size": (i32, [vp, i32, C.POINTER(i64), C.POINTER(C.c_int32)]),
             "pm_knn_query": (i32, [vp, i32, vp, i64, i32, f32, vp, vp, vp]),
             "pm_knn_radiance": (i32, [vp, i32, vp, i64, i32, f32, vp]),
@@ -295,6 +295,9 @@ class PhotonMapper:
     def knn_set_curve(self, curve):
         """0 = Morton (Z-order) sort key, 1 = Hilbert (default)."""
         self._ck(self.L.pm_knn_set_curve(self.h, curve))
+
+    def knn_set_batched(self, on=True):
+        self._ck(self.L.pm_knn_set_batched(self.h, on))
 
     def knn_build(self, which=0):
         self._ck(self.L.pm_knn_build(self.h, which))

@@ -325,8 +325,18 @@ int pm_clear_map(pm_context *c) {
   return PM_OK;
 }
 
+// the record buffers a k-NN map points into (positions, powers) are about to be rewritten or freed
+static void records_changed(pm_context *c, int which) {
+  if (c->knn_from_records[which] && c->knn[which].n > 0) c->knn_stale[which] = true;
+}
+static int knn_usable(pm_context *c, int which) {
+  if (c->knn_stale[which]) { c->err = "the photon records changed since pm_knn_build: rebuild the map"; return PM_ERR_STATE; }
+  return PM_OK;
+}
+
 int pm_set_record_capacity(pm_context *c, int64_t cap) {
   ARG(c, c != nullptr && cap >= 0, "bad capacity");
+  records_changed(c, PM_MAP_SURFACE);
   CK(c, cudaSetDevice(c->device));
   CK(c, cudaStreamSynchronize(c->stream));
   cudaFree(c->d_rec_pos); cudaFree(c->d_rec_pow); cudaFree(c->d_rec_dir);
@@ -363,6 +373,10 @@ int pm_trace(pm_context *c, float t, unsigned flags) {
   CK(c, cudaSetDevice(c->device));
   c->dsc = make_device_scene(c->scene, t);
   cudaError_t terr = cudaSuccess;
+  if (flags & PM_TRACE_RECORDS) {   // the record buffers are rewritten: maps built over them no longer match
+    records_changed(c, PM_MAP_SURFACE);
+    if (flags & PM_TRACE_MEDIA) records_changed(c, PM_MAP_VOLUME);
+  }
   if (flags & PM_TRACE_MEDIA) {
     if (flags & PM_TRACE_RECORDS) {   // the volume set has a fixed slot per (photon, step)
       int64_t need = 3 * (c->last - c->first);
@@ -592,6 +606,7 @@ int pm_knn_build_points(pm_context *c, int which, const float *pos4, const float
     e = knn_build(c->knn[which], (const float4 *)pos4, (const float4 *)pow4, n, (records && which == PM_MAP_SURFACE) ? 1 : 0, c->knn_curve,
                   c->stream, &launches);
   }
+  c->knn_from_records[which] = false; c->knn_stale[which] = false;
   c->launches += launches;
   CK(c, e);
   return PM_OK;
@@ -609,6 +624,7 @@ int pm_knn_build(pm_context *c, int which) {
     SpanGuard g(c, K_KNN_BUILD);
     e = knn_build(c->knn[which], (const float4 *)pos, (const float4 *)pw, n, which == PM_MAP_SURFACE ? 1 : 0, c->knn_curve, c->stream, &launches);
   }
+  c->knn_from_records[which] = true; c->knn_stale[which] = false;
   c->launches += launches;
   CK(c, e);
   return PM_OK;
@@ -616,6 +632,11 @@ int pm_knn_build(pm_context *c, int which) {
 int pm_knn_set_curve(pm_context *c, int curve) {
   ARG(c, c && (curve == PM_CURVE_MORTON || curve == PM_CURVE_HILBERT), "bad curve id");
   c->knn_curve = curve;
+  return PM_OK;
+}
+int pm_knn_set_batched(pm_context *c, bool on) {
+  ARG(c, c != nullptr, "null context");
+  c->knn_batched = on;
   return PM_OK;
 }
 int pm_knn_size(pm_context *c, int which, int64_t *n, int32_t *levels) {
@@ -630,6 +651,7 @@ static int knn_query_common(pm_context *c, int which, const float *q4, int64_t n
   ARG(c, k >= 1 && k <= 128, "k must be in [1, 128]");
   ARG(c, nq >= 0 && (nq == 0 || q4), "null queries");
   ARG(c, !(max_r2 < 0.0f), "negative radius");
+  if (knn_usable(c, which) != PM_OK) return PM_ERR_STATE;
   CK(c, cudaSetDevice(c->device));
   if (rgb4 && !c->knn[which].power && c->knn[which].n > 0) { c->err = "map was built without powers"; return PM_ERR_STATE; }
   {
@@ -657,13 +679,14 @@ int pm_render_knn_rows(pm_context *c, float t, bool media, int width, int height
   ARG(c, width > 0 && height > 0 && y0 >= 0 && y0 <= y1 && y1 <= height && y_step >= 1, "bad frame geometry");
   ARG(c, k >= 1 && k <= 128, "k must be in [1, 128]");
   if ((c->knn[0].n > 0 && !c->knn[0].power) || (media && c->knn[1].n > 0 && !c->knn[1].power)) { c->err = "maps were built without powers"; return PM_ERR_STATE; }
+  if (knn_usable(c, PM_MAP_SURFACE) != PM_OK || (media && knn_usable(c, PM_MAP_VOLUME) != PM_OK)) return PM_ERR_STATE;
   CK(c, cudaSetDevice(c->device));
   c->dsc = make_device_scene(c->scene, t);
   {
     SpanGuard g(c, K_KNN_RENDER);
     if (!c->d_work) CK(c, cudaMalloc(&c->d_work, sizeof(unsigned long long)));
     CK(c, knn_render(c->dsc, c->knn[0], c->knn[1], k, max_r2, w_surface, w_volume, width, height, y0, y1, y_step, media, c->d_work, (uchar4 *)dev_rgba,
-                     (float4 *)dev_rgbf, c->num_sms, c->stream));
+                     (float4 *)dev_rgbf, c->num_sms, c->stream, c->knn_batched));
   }
   if (y1 > y0) c->launches++;
   return PM_OK;
@@ -691,6 +714,7 @@ int pm_knn_radiance_cone(pm_context *c, const float *q4, int64_t nq, int k, floa
   ARG(c, nq >= 0 && (nq == 0 || q4), "null queries");
   ARG(c, sq_radius >= 0.0f && exposure != 0.0f, "bad radius / exposure");
   const KnnMap &m = c->knn[PM_MAP_SURFACE];
+  if (knn_usable(c, PM_MAP_SURFACE) != PM_OK) return PM_ERR_STATE;
   if (m.n > 0 && (m.src_pos != c->d_rec_pos || !c->d_rec_dir)) { c->err = "the cone filter needs the surface map built from the record buffers (pm_knn_build)"; return PM_ERR_STATE; }
   CK(c, cudaSetDevice(c->device));
   // inward wall normals: surfaceNormal(1, id, p, gOrigin) = normalize(e_axis * (0 - offset)), photonMappingKernel - Copy.cu:193

@@ -82,7 +82,7 @@ cudaError_t knn_query(const KnnMap &m, const float4 *queries, long long nq, int 
                       const float4 *cone_dir = nullptr, const float *cone_normals15 = nullptr, float exposure = 1.0f);
 cudaError_t knn_render(const DeviceScene &sc, const KnnMap &ms, const KnnMap &mv, int k, float max_r2, float w_surf, float w_vol, int width,
                        int height, int y0, int y1, int y_step, bool media, unsigned long long *work_counter, uchar4 *rgba, float4 *rgbf, int num_sms,
-                       cudaStream_t st);
+                       cudaStream_t st, bool batched = false);
 void knn_free(KnnMap &m);
 
 }  // namespace pm

@@ -689,6 +689,379 @@ __global__ void __launch_bounds__(kQueryThreads) knn_render_kernel(const __grid_
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Batched search (round 2): one warp = 32 NEIGHBOURING queries, one lane = one query.
+//
+// The warp-per-query search above spends its instructions on warp-wide machinery per candidate: 7 600 warp instructions per query
+// (ncu, 16M photons, k = 50), a bitonic sort + merge network for every 32 candidates, a node step per visited child.  The queries
+// of a frame are coherent -- the pixels of an 8 x 4 tile at the same march step lie within a fraction of the search radius of each
+// other -- so here the 32 lanes walk the tree ONCE for their common bounding box and every lane tests every visited photon against
+// its own query (8 thread instructions per test, all lanes busy):
+//   * traversal: warp-uniform depth-first walk; the 32 lanes test the 32 children of a node against the batch's box expanded by the
+//     largest search radius (conservative in FP32 for the same reason as above), the set of children to visit is computed once per
+//     node and parked in a lane register per level; before a leaf is read, every lane tests the leaf's box against ITS sphere;
+//   * a leaf = 32 photons = one coalesced 512-byte load, staged in shared memory and broadcast to the lanes;
+//   * candidates (d2 <= the lane's limit) are appended to a per-lane list in shared memory ([slot][lane]: conflict-free); when a
+//     list could overflow during the next leaf, the lane selects its k smallest keys in place (max-heap) and tightens its limit;
+//   * the limit comes from a neighbouring query's k-th distance (x 1.2, as above); a lane that finds fewer than k photons inside
+//     it is searched again with the bound (r_k(neighbour) + distance to the neighbour)^2, which cannot fail (triangle inequality);
+//   * the result -- the k smallest keys (bits(d2) << 32 | original index) -- is the same set the warp-per-query search and the
+//     brute-force oracle return; only the summation order of the radiance estimate differs.
+// ---------------------------------------------------------------------------------------------------------
+#ifdef PM_KNN_BSTATS
+// development counters of the batched search: 0 batches (batch_search calls), 1 tree walks, 2 node visits, 3 leaves listed by the
+// common test, 4 leaves some lane needed, 5 selections, 6 seed searches, 7 lanes searched one by one, 8.. cycles: 8 walks,
+// 9 selections, 10 seeds, 11 one-by-one, 12 radiance, 13 candidates appended (thread count), 14 whole tile
+__device__ unsigned long long g_bstats[16];
+#define BSTAT(i, v) do { if (lane == 0) atomicAdd(&g_bstats[i], (unsigned long long)(v)); } while (0)
+#define BCLK() clock64()
+#else
+#define BSTAT(i, v) do { } while (0)
+#define BCLK() 0ll
+#endif
+
+constexpr int kBatchStrip = 4;           // tiles per work unit (every unit starts with one seed search per query kind)
+template <int KL>
+struct BatchShared {                     // per warp
+  static constexpr int kCand = 32 * KL + 32;
+  float d2[kCand][32];
+  uint32_t idx[kCand][32];
+  float4 leaf[32];
+  float hint[11][32];                    // per lane: k-th squared distance of the last search per query kind (10 march steps + wall)
+  u64 pend[64];                          // scratch of the warp-per-query search that seeds a strip
+};
+
+__device__ __forceinline__ u64 cand_key(float d2, uint32_t idx) { return ((u64)__float_as_uint(d2) << 32) | idx; }
+
+// in place: the k smallest keys of slots [0, cnt) end up in slots [0, k), the k-th smallest in slot k-1.  cnt > k.  Quickselect
+// (Hoare partition, median-of-three pivot) on the lane's own list: every pass streams over its range with independent
+// shared-memory loads.  (A first version kept a max-heap: its sift-downs are chains of dependent loads, 60-70 K cycles per
+// selection with the handful of warps an SM holds here -- 70% of the kernel.)  Keys are distinct (they contain the photon index).
+template <int KL>
+__device__ __forceinline__ void select_k(BatchShared<KL> &sm, int lane, int cnt, int k) {
+  auto key = [&](int i) { return cand_key(sm.d2[i][lane], sm.idx[i][lane]); };
+  int lo = 0, hi = cnt - 1;
+  const int target = k - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const u64 a = key(lo), b = key(mid), c = key(hi);
+    const u64 pivot = a < b ? (b < c ? b : (a < c ? c : a)) : (a < c ? a : (b < c ? c : b));   // median of three
+    int i = lo, j = hi;
+    while (i <= j) {
+      while (key(i) < pivot) i++;
+      while (key(j) > pivot) j--;
+      if (i <= j) {
+        const float di = sm.d2[i][lane], dj = sm.d2[j][lane];
+        const uint32_t xi = sm.idx[i][lane], xj = sm.idx[j][lane];
+        sm.d2[i][lane] = dj; sm.idx[i][lane] = xj; sm.d2[j][lane] = di; sm.idx[j][lane] = xi;
+        i++; j--;
+      }
+    }
+    if (target <= j) hi = j;
+    else if (target >= i) lo = i;
+    else break;
+  }
+}
+
+__device__ __forceinline__ float warp_min_f(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// One walk of the tree for the whole warp.  Lane state: query (qx, qy, qz), lim = accept d2 <= lim (negative: the lane takes no
+// part), cnt = candidates collected so far (slots [0, cnt) of the lane's list).  On return slots [0, min(cnt, k)) hold the lane's
+// k smallest keys among all photons with d2 <= the lim it was called with (as the k-th smallest in slot k-1 when cnt >= k), and lim may have shrunk.
+template <int KL>
+__device__ __forceinline__ void batch_collect(const TreeView &tv, BatchShared<KL> &sm, float qx, float qy, float qz, float &lim, int k, int lane,
+                                              int &cnt) {
+  constexpr int kCand = BatchShared<KL>::kCand;
+  const float inf = cuda::std::numeric_limits<float>::infinity();
+  cnt = 0;
+  if (tv.n <= 0) return;
+  const bool act = lim >= 0.0f;
+  // the batch's bounding box and largest radius (inactive lanes do not widen them)
+  const float blx = warp_min_f(act ? qx : inf), bly = warp_min_f(act ? qy : inf), blz = warp_min_f(act ? qz : inf);
+  const float bhx = warp_max_f(act ? qx : -inf), bhy = warp_max_f(act ? qy : -inf), bhz = warp_max_f(act ? qz : -inf);
+  float max_lim = warp_max_f(act ? lim : -1.0f);
+  if (!(max_lim >= 0.0f)) return;
+  BSTAT(1, 1);
+  long long my_node = 0; unsigned my_pend = 0;      // lane l parks the state of level l: node index, children still to visit
+  float lx = 0.f, ly = 0.f, lz = 0.f, hx = 0.f, hy = 0.f, hz = 0.f;   // this lane's child box of the node entered last
+  int level = tv.levels;                            // the virtual level above the top: node 0's children are the top-level entities
+  bool enter = true;
+  long long j = 0;
+  for (;;) {
+    if (enter) {   // first visit of node j at `level`: which of its 32 children can hold a candidate of ANY lane
+      const int cl = level - 1;
+      const long long e = j * 32 + lane;
+      bool ok = false;
+      if (e < tv.cnt[cl]) {
+        const float *b = tv.box[cl]; const long long p = tv.pad[cl];
+        lx = __ldg(b + e); ly = __ldg(b + p + e); lz = __ldg(b + 2 * p + e); hx = __ldg(b + 3 * p + e); hy = __ldg(b + 4 * p + e); hz = __ldg(b + 5 * p + e);
+        const float dx = fmaxf(fmaxf(lx - bhx, 0.0f), blx - hx), dy = fmaxf(fmaxf(ly - bhy, 0.0f), bly - hy), dz = fmaxf(fmaxf(lz - bhz, 0.0f), blz - hz);
+        ok = (dx * dx + dy * dy) + dz * dz <= max_lim;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, ok);
+      BSTAT(2, 1); if (level == 1) BSTAT(3, __popc(m));
+      if (lane == level) { my_node = j; my_pend = m; }
+      enter = false;
+    }
+    unsigned pend = __shfl_sync(0xffffffffu, my_pend, level);
+    if (!pend) {                                    // nothing left under this node
+      level++;
+      if (level > tv.levels) break;
+      continue;
+    }
+    const int c = __ffs(pend) - 1;
+    if (lane == level) my_pend = pend & (pend - 1);
+    j = __shfl_sync(0xffffffffu, my_node, level);
+    const long long child = j * 32 + c;
+    if (level > 1) { level--; j = child; enter = true; continue; }
+    // ---- leaf `child`: its box sits in lane c's registers (the node entered last is this leaf's parent) ----
+    {
+      const float clx = __shfl_sync(0xffffffffu, lx, c), cly = __shfl_sync(0xffffffffu, ly, c), clz = __shfl_sync(0xffffffffu, lz, c);
+      const float chx = __shfl_sync(0xffffffffu, hx, c), chy = __shfl_sync(0xffffffffu, hy, c), chz = __shfl_sync(0xffffffffu, hz, c);
+      const bool need = lim >= 0.0f && box_dist2(clx, cly, clz, chx, chy, chz, qx, qy, qz) <= lim;
+      if (!__ballot_sync(0xffffffffu, need)) continue;
+      BSTAT(4, 1);
+      if (__ballot_sync(0xffffffffu, cnt > kCand - 32)) {   // a list could overflow in this leaf: keep the k best, tighten the limit
+        BSTAT(5, 1);
+        const long long t_sel = BCLK();
+        if (cnt > k) {
+          select_k<KL>(sm, lane, cnt, k);
+          cnt = k;
+          lim = fminf(lim, sm.d2[k - 1][lane]);
+        }
+        __syncwarp();
+        BSTAT(9, BCLK() - t_sel);
+        max_lim = warp_max_f(lim);   // (the batch box is left as it is: conservative)
+      }
+      const long long i = child * 32 + lane;
+      float4 p = make_float4(inf, inf, inf, 0.0f);
+      if (i < tv.n) p = __ldg(tv.spos + i);
+      __syncwarp();
+      sm.leaf[lane] = p;
+      __syncwarp();
+      if (need) {
+#pragma unroll 8
+        for (int t = 0; t < 32; t++) {
+          const float4 s = sm.leaf[t];
+          const float dx = s.x - qx, dy = s.y - qy, dz = s.z - qz;
+          const float d2 = (dx * dx + dy * dy) + dz * dz;
+          if (d2 <= lim) { sm.d2[cnt][lane] = d2; sm.idx[cnt][lane] = __float_as_uint(s.w); cnt++; }
+#ifdef PM_KNN_BSTATS
+          if (d2 <= lim) atomicAdd(&g_bstats[13], 1ull);
+#endif
+        }
+      }
+    }
+  }
+  {
+    BSTAT(5, 1);
+    const long long t_sel = BCLK();
+    if (cnt > k) { select_k<KL>(sm, lane, cnt, k); cnt = k; lim = fminf(lim, sm.d2[k - 1][lane]); }
+    __syncwarp();
+    BSTAT(9, BCLK() - t_sel);
+  }
+}
+
+// radiance estimate of the lane's result (slots [0, n)): sum of the powers / (pi r_k^2) or (4/3 pi r_k^3); returns r_k^2 in .w
+template <int KL>
+__device__ __forceinline__ float4 batch_radiance(const BatchShared<KL> &sm, int lane, int n, const float4 *__restrict__ power, int volume) {
+  float r = 0.0f, g = 0.0f, b = 0.0f, rk2 = 0.0f;
+  for (int i = 0; i < n; i++) {
+    const float4 pw = __ldg(power + sm.idx[i][lane]);
+    r += pw.x; g += pw.y; b += pw.z;
+    rk2 = fmaxf(rk2, sm.d2[i][lane]);
+  }
+  const float PI = 3.14159265358979323846f;
+  const float den = volume ? (4.0f / 3.0f) * PI * rk2 * __fsqrt_rn(rk2) : PI * rk2;
+  const float inv = den > 0.0f ? __fdiv_rn(1.0f, den) : 0.0f;
+  return make_float4(r * inv, g * inv, b * inv, rk2);
+}
+
+// The exact k nearest photons of every lane's query (active = false: the lane has none).  hint_r2: a neighbouring query's k-th
+// squared distance (inf: none).  Lanes without a usable limit -- no hint, or fewer than k photons inside 1.44 x the hint -- are
+// seeded: the warp-per-query search finds the k-th distance r of the first such lane's point p, and r_k(q) <= r + |q - p| bounds
+// every other one (triangle inequality), so the second walk cannot fail.  Returns the number found (k unless the map holds fewer
+// within max_r2); the lane's result sits in slots [0, n) of its list.
+template <int KL>
+__device__ __forceinline__ int batch_search(const TreeView &tv, BatchShared<KL> &sm, bool active, float qx, float qy, float qz, int k, float max_r2,
+                                            float hint_r2, int lane) {
+  const float inf = cuda::std::numeric_limits<float>::infinity();
+  BSTAT(0, 1);
+  bool seed = active && !(hint_r2 * 1.44f < max_r2);    // no finite limit of its own
+  bool todo = active;
+  float lim = -1.0f;
+  int cnt = 0;
+  for (int round = 0; round < 2; round++) {
+    const unsigned sm_mask = __ballot_sync(0xffffffffu, seed);
+    float bound = inf;
+    if (sm_mask) {
+      BSTAT(6, 1);
+      const long long t_seed = BCLK();
+      const int src = __ffs(sm_mask) - 1;
+      const float sx = __shfl_sync(0xffffffffu, qx, src), sy = __shfl_sync(0xffffffffu, qy, src), sz = __shfl_sync(0xffffffffu, qz, src);
+      TopK<KL> top;
+      knn_search<KL>(tv, nullptr, sm.pend, sx, sy, sz, k, max_r2, lane, top);
+      const u64 kth = top.at(k - 1);
+      if (kth != kMaxKey) {   // a relative 2e-5 and a denormal cover the FP32 rounding of the bound itself
+        const float dx = qx - sx, dy = qy - sy, dz = qz - sz;
+        const float rb = __fsqrt_rn(__uint_as_float((uint32_t)(kth >> 32))) + __fsqrt_rn((dx * dx + dy * dy) + dz * dz) * 1.000001f;
+        bound = rb * rb * 1.00002f + 1e-30f;
+      }
+      BSTAT(10, BCLK() - t_seed);
+    }
+    lim = !todo ? -1.0f : (seed ? fminf(max_r2, bound) : fminf(max_r2, hint_r2 * 1.44f));
+    const bool guaranteed = seed;
+    // A common walk only pays while the queries are neighbours.  The pixels of a tile that straddles a silhouette, or that see the
+    // scene through the mirror / glass sphere, have wall points all over the scene: their common box would hold the whole map.
+    // Such a batch (box diagonal > 8 x the largest radius) is searched lane by lane with the warp-per-query search instead.
+    {
+      const float blx = warp_min_f(todo ? qx : inf), bly = warp_min_f(todo ? qy : inf), blz = warp_min_f(todo ? qz : inf);
+      const float bhx = warp_max_f(todo ? qx : -inf), bhy = warp_max_f(todo ? qy : -inf), bhz = warp_max_f(todo ? qz : -inf);
+      const float ex = bhx - blx, ey = bhy - bly, ez = bhz - blz;
+      const float max_lim = warp_max_f(todo ? lim : -1.0f);
+      unsigned tm = __ballot_sync(0xffffffffu, todo);
+      if (tm && !((ex * ex + ey * ey) + ez * ez <= 64.0f * max_lim)) {
+        BSTAT(7, __popc(tm));
+        const long long t_one = BCLK();
+        while (tm) {
+          const int src = __ffs(tm) - 1;
+          tm &= tm - 1;
+          const float sx = __shfl_sync(0xffffffffu, qx, src), sy = __shfl_sync(0xffffffffu, qy, src), sz = __shfl_sync(0xffffffffu, qz, src);
+          float l = __shfl_sync(0xffffffffu, lim, src);
+          TopK<KL> top;
+          for (;;) {
+            knn_search<KL>(tv, nullptr, sm.pend, sx, sy, sz, k, l, lane, top);
+            if (top.at(k - 1) != kMaxKey || !(l < max_r2)) break;
+            l = max_r2;                                   // the limit was too tight: unbounded (nearest-first) retry
+          }
+          int found = 0;
+#pragma unroll
+          for (int i = 0; i < KL; i++) {                   // the sorted list (position i*32+lane) goes into lane src's candidate list
+            const int pos = i * 32 + lane;
+            const bool have = pos < k && top.s[i] != kMaxKey;
+            if (have) { sm.d2[pos][src] = __uint_as_float((uint32_t)(top.s[i] >> 32)); sm.idx[pos][src] = (uint32_t)(top.s[i] & 0xffffffffu); }
+            found += __popc(__ballot_sync(0xffffffffu, have));
+          }
+          if (lane == src) cnt = found;
+          __syncwarp();
+        }
+        BSTAT(11, BCLK() - t_one);
+        break;
+      }
+    }
+    int c = 0;
+    const long long t_walk = BCLK();
+    if (__ballot_sync(0xffffffffu, todo)) batch_collect<KL>(tv, sm, qx, qy, qz, lim, k, lane, c);
+    BSTAT(8, BCLK() - t_walk);
+    if (todo) cnt = c;
+    // a lane whose heuristic limit held fewer than k photons goes again, seeded; everything else is final (a lane that sits out
+    // has lim < 0 and its list is not touched by the second walk)
+    seed = todo && !guaranteed && c < k;
+    todo = seed;
+    if (!__ballot_sync(0xffffffffu, todo)) break;
+  }
+  return cnt;
+}
+
+template <int KL>
+__global__ void __launch_bounds__(256) knn_render_batched_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ TreeView tvs,
+                                                                 const __grid_constant__ TreeView tvv, const float4 *__restrict__ pow_s,
+                                                                 const float4 *__restrict__ pow_v, int k, float max_r2, float w_surf, float w_vol,
+                                                                 int width, int height, int y0, int y1, int y_step, int media,
+                                                                 uchar4 *__restrict__ rgba, float4 *__restrict__ rgbf,
+                                                                 unsigned long long *__restrict__ work_counter) {
+  extern __shared__ __align__(128) unsigned char dyn[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  BatchShared<KL> &sm = reinterpret_cast<BatchShared<KL> *>(dyn)[w];
+  const float inf = cuda::std::numeric_limits<float>::infinity();
+  const int nrows = (y1 - y0 + y_step - 1) / y_step;   // rows y0, y0+y_step, ... < y1
+  // Work unit: a strip of kStrip tiles of 8 x 4 pixels along a row of tiles, fetched from a global counter (the cost of a pixel
+  // varies by orders of magnitude over the image); lane = (ty, tx) of the tile.  A tile takes its limits from the tile before it
+  // in the strip (the lane of the same row in its last column); the first tile of a strip has no neighbour and is seeded.
+  constexpr int kTileW = 8, kTileH = 4, kStrip = kBatchStrip;
+  const int tx = lane & 7, ty = lane >> 3;
+  const int tiles_x = (width + kTileW - 1) / kTileW, strips_x = (tiles_x + kStrip - 1) / kStrip, tiles_y = (nrows + kTileH - 1) / kTileH;
+  const long long units = (long long)strips_x * tiles_y;
+  // one query kind (march step 0..9, wall point = 10) for all 32 pixels of the tile at a time
+  auto run_kind = [&](const TreeView &tv, const float4 *__restrict__ power, int kind, bool first_tile, bool active, v3 q, int volume) -> v3 {
+    const float prev_r2 = __shfl_sync(0xffffffffu, sm.hint[kind][lane], ty * 8 + 7);
+    const int n = batch_search<KL>(tv, sm, active, q.x, q.y, q.z, k, max_r2, first_tile ? inf : prev_r2, lane);
+    float4 e = make_float4(0.0f, 0.0f, 0.0f, inf);
+    const long long t_rad = BCLK();
+    if (active) e = batch_radiance<KL>(sm, lane, n, power, volume);
+    __syncwarp();
+    BSTAT(12, BCLK() - t_rad);
+    sm.hint[kind][lane] = (active && n >= k) ? e.w : inf;
+    __syncwarp();
+    return V(e.x, e.y, e.z);
+  };
+  for (;;) {
+    long long u = 0;
+    if (lane == 0) u = (long long)atomicAdd(work_counter, 1ull);
+    u = __shfl_sync(0xffffffffu, u, 0);
+    if (u >= units) break;
+    const int tile_row = (int)(u / strips_x), strip = (int)(u % strips_x);
+    const int row = tile_row * kTileH + ty;
+    for (int tile = 0; tile < kStrip; tile++) {
+      if ((strip * kStrip + tile) * kTileW >= width) break;
+#ifdef PM_KNN_BSTATS
+      const long long t_tile = clock64();
+#endif
+      const int px = (strip * kStrip + tile) * kTileW + tx;
+      const bool in_frame = px < width && row < nrows;
+      const int py = y0 + row * y_step;
+      const long long pix = (long long)py * width + px;
+      const float x = (float)px + sc.cam_ox, y = (float)py + sc.cam_oy;
+      v3 rgb = V(0.0f, 0.0f, 0.0f);
+      const v3 origin = V(0.0f, 0.0f, 0.0f);
+      v3 ray = V((float)((double)__fdiv_rn(x, sc.sz_img) - 0.5), (float)(-((double)__fdiv_rn(y, sc.sz_img) - 0.5)), 1.0f);
+      if (media) {
+        v3 prev = origin;
+#pragma unroll 1
+        for (int i = 0; i < 10; i++) {
+          prev = add(mul(ray, 0.6f), prev);
+          const v3 e = run_kind(tvv, pow_v, i, tile == 0, in_frame, prev, 1);
+          rgb = add(rgb, mul(e, w_vol));
+        }
+      }
+      Hit h; h.hit = 0; h.type = 0; h.idx = 0; h.dist = -1.0f;
+      raytrace(sc, ray, origin, h);
+      bool wall = false;
+      v3 P = V(0.0f, 0.0f, 0.0f);
+      if (h.hit) {
+        P = mul(ray, h.dist);
+        if (h.type == 0 && h.idx == 1) follow_specular(sc, ray, origin, h, P, 1);
+        else if (h.type == 0 && h.idx == 0) follow_specular(sc, ray, origin, h, P, 0);
+        wall = h.hit && h.type == 1;
+      }
+      {
+        const bool active = in_frame && wall;
+        const v3 e = run_kind(tvs, pow_s, 10, tile == 0, active, P, 0);
+        if (active) {
+          const v3 c = mul(e, w_surf);
+          rgb = media ? add(rgb, mul(c, 0.15f)) : add(rgb, c);
+        }
+      }
+      if (in_frame) {
+        if (rgbf) rgbf[pix] = make_float4(rgb.x, rgb.y, rgb.z, 1.0f);
+        if (rgba) rgba[pix] = make_uchar4(quantise_u8(rgb.x), quantise_u8(rgb.y), quantise_u8(rgb.z), 0);
+      }
+#ifdef PM_KNN_BSTATS
+      BSTAT(14, clock64() - t_tile);
+#endif
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // host side of the build / query
 // ---------------------------------------------------------------------------------------------------------
 static cudaError_t ensure(void **p, size_t *cap, size_t bytes) {
@@ -797,11 +1170,36 @@ cudaError_t knn_query(const KnnMap &m, const float4 *queries, long long nq, int 
   return cudaGetLastError();
 }
 
+static TreeView make_view_unstaged(const KnnMap &m) {
+  TreeView tv = make_view(m);
+  tv.staged_from = m.levels; tv.staged_floats = 0;   // every level is read through L1 / L2
+  return tv;
+}
+
 cudaError_t knn_render(const DeviceScene &sc, const KnnMap &ms, const KnnMap &mv, int k, float max_r2, float w_surf, float w_vol, int width,
-                       int height, int y0, int y1, int y_step, bool media, unsigned long long *work_counter, uchar4 *rgba, float4 *rgbf, int num_sms, cudaStream_t st) {
+                       int height, int y0, int y1, int y_step, bool media, unsigned long long *work_counter, uchar4 *rgba, float4 *rgbf, int num_sms,
+                       cudaStream_t st, bool batched) {
   if (y_step < 1) y_step = 1;
   long long n = (long long)((y1 - y0 + y_step - 1) / y_step) * width;
   if (n <= 0) return cudaSuccess;
+  if (batched) {   // one warp = one 8 x 4 pixel tile, one lane = one pixel (see "Batched search")
+    TreeView tvs = make_view_unstaged(ms), tvv = make_view_unstaged(mv);
+    KCK(cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), st));
+    const int nrows = (y1 - y0 + y_step - 1) / y_step;
+    const long long units = (long long)(((width + 7) / 8 + kBatchStrip - 1) / kBatchStrip) * ((nrows + 3) / 4);
+#define LAUNCH_BATCHED(KL, WARPS)                                                                                               \
+    do {                                                                                                                        \
+      const size_t smem = sizeof(BatchShared<KL>) * WARPS;                                                                      \
+      KCK(cudaFuncSetAttribute(knn_render_batched_kernel<KL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+      long long want = (units + WARPS - 1) / WARPS;                                                                             \
+      unsigned grid = (unsigned)(want < (long long)num_sms ? want : (long long)num_sms);                                        \
+      knn_render_batched_kernel<KL><<<grid, WARPS * 32, smem, st>>>(sc, tvs, tvv, ms.power, mv.power, k, max_r2, w_surf, w_vol, width, height, \
+                                                                     y0, y1, y_step, media ? 1 : 0, rgba, rgbf, work_counter);              \
+    } while (0)
+    if (k <= 32) LAUNCH_BATCHED(1, 8); else if (k <= 64) LAUNCH_BATCHED(2, 8); else LAUNCH_BATCHED(4, 5);
+#undef LAUNCH_BATCHED
+    return cudaGetLastError();
+  }
   TreeView tvs = make_view(ms), tvv = make_view(mv);
   long long want = (long long)((width + 15) / 16) * (((y1 - y0 + y_step - 1) / y_step + 7) / 8), cap = (long long)num_sms * 16;   // 8x16-pixel tiles
   unsigned grid = (unsigned)(want < cap ? want : cap);
@@ -817,6 +1215,14 @@ cudaError_t knn_render(const DeviceScene &sc, const KnnMap &ms, const KnnMap &mv
 #undef LAUNCH_RENDER
   return cudaGetLastError();
 }
+
+#ifdef PM_KNN_BSTATS
+extern "C" void pm_debug_knn_bstats(unsigned long long *out, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_bstats, sizeof(unsigned long long) * 16);
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_bstats, z, sizeof(z)); }
+}
+#endif
 
 #ifdef PM_KNN_STATS
 extern "C" void pm_debug_knn_stats(unsigned long long *out, int reset) {

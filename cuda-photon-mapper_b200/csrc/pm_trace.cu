@@ -5,16 +5,18 @@
 // identical to the sequential oracle (pm_math.cuh), but the work is organised for the hardware:
 //   * the MWC generator is index-addressed (jump-ahead), so the table fill and the medium-scatter draws are
 //     fully parallel yet bit-identical to the reference's serial stream;
-//   * the medium walk (3 fixed steps, PMK:1239-1272) does not influence the surface walk, so it runs as its
-//     own fully convergent kernel (volume_kernel);
-//   * the surface walk (surface_kernel) is a persistent kernel, one CTA per SM: every lane runs a small state
-//     machine with ONE ray-scene intersection site per iteration, and a lane that finishes its photon is
-//     refilled from its warp's contiguous photon range.  Primary rays, shadow rays, wall bounces and the
-//     mirror/glass chain therefore share the same instructions instead of diverging (the first version of
-//     this kernel ran 17 of 32 lanes on average and stalled on instruction fetch);
-//   * deposits go into exact int64 fixed-point accumulators keyed by wall voxel (pm_layout.h) instead of
-//     ~65 racy float RMWs per photon; the accumulators are privatised per CTA in shared memory (123 KB, split
-//     into 32-bit halves because shared memory has no native 64-bit add) and flushed once per CTA;
+//   * the medium walk (3 fixed steps, PMK:1239-1272) does not influence the surface walk.  It is bound by L2 atomics and leaves
+//     the issue slots idle, the surface walk is bound by instruction issue and makes no L2 traffic: trace_kernel is warp-specialised,
+//     warps [0, vol_warps) of every 1024-thread CTA run the medium walk of the CTA's photon range, the other warps the surface
+//     walk (PM_TRACE_SPLIT keeps the medium walk as its own launch, volume_kernel, for measurement);
+//   * the surface walk is persistent, one CTA per SM: every lane runs a small state machine with ONE ray-scene intersection site
+//     per iteration, and a lane that finishes its photon is refilled from its warp's contiguous photon slice.  Primary rays,
+//     shadow rays, wall bounces and the mirror/glass chain therefore share the same instructions instead of diverging (the first
+//     version of this kernel ran 17 of 32 lanes on average and stalled on instruction fetch);
+//   * deposits go into exact int64 fixed-point accumulators keyed by wall voxel (pm_layout.h) instead of ~65 racy float RMWs per
+//     photon; the wall accumulators are privatised per CTA in shared memory (184 320 B: 20 480 entries as 32-bit halves, because
+//     shared memory has no native 64-bit add, plus 5 120 shadow-photon counters) and flushed once per CTA; medium deposits are
+//     COUNTED in replicated 32-bit L2 counters and turned into energy by fold_volume_kernel;
 //   * photon records (Mode B) are appended to SoA float4 buffers with warp-aggregated atomics.
 #include "pm_kernels.cuh"
 

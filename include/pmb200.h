@@ -145,6 +145,9 @@ int pm_record_buffers(pm_context *ctx, int which, float **dev_pos_meta /* float4
 #define PM_CURVE_MORTON  0   /* 30-bit Morton (Z-order) key of the 10-bit cell coordinates */
 #define PM_CURVE_HILBERT 1   /* the same cell along the 3-D Hilbert curve (default: tighter leaf / node boxes) */
 int pm_knn_set_curve(pm_context *ctx, int curve);
+/* Mode B frames (pm_render_knn*): false (default) = one warp per pixel; true = one warp per 8 x 4 pixel tile, one lane per pixel, the
+ * tree walked once per tile (experimental: same k-nearest sets, currently slower -- DESIGN.md 8). */
+int pm_knn_set_batched(pm_context *ctx, bool on);
 int pm_knn_build(pm_context *ctx, int which);
 int pm_knn_build_points(pm_context *ctx, int which, const float *dev_pos4, const float *dev_power4, int64_t n,
                         bool records /* true: rows are photon records (w = meta); the surface map keeps wall hits only */);

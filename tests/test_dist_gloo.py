@@ -58,8 +58,9 @@ def _worker(rank, world, port, n, w, h, out_dir):
     dist.destroy_process_group()
 
 
-def test_partition_helpers(pm):
-    from pmb200 import dist as pd
+def test_partition_helpers():
+    sys.path.insert(0, ROOT)
+    from pmb200 import dist as pd      # pure Python: does not load libpmb200.so
     for n, world in ((10, 3), (16777216, 8), (7, 8), (1000003, 4)):
         shards = [pd.photon_shard(n, r, world) for r in range(world)]
         assert shards[0][0] == 0 and shards[-1][1] == n
@@ -67,9 +68,12 @@ def test_partition_helpers(pm):
     assert [pd.row_band(1080, r, 8) for r in (0, 7)] == [(0, 135), (945, 1080)]
     with pytest.raises(ValueError):
         pd.row_band(1080, 0, 7)
+    bands = [pd.row_band_uneven(1080, r, 7) for r in range(7)]
+    assert bands[0][0] == 0 and bands[-1][1] == 1080 and all(bands[i][1] == bands[i + 1][0] for i in range(6))
+    assert max(b - a for a, b in bands) - min(b - a for a, b in bands) <= 1
 
 
-def test_two_rank_exchange_is_exact(oracle, pm, tmp_path):
+def test_two_rank_exchange_is_exact(oracle, tmp_path):
     n, w, h = 6001, 40, 30
     port = 29500 + os.getpid() % 2000
     mp.spawn(_worker, args=(2, port, n, w, h, str(tmp_path)), nprocs=2, join=True)

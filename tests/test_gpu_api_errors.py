@@ -57,3 +57,26 @@ def test_null_handles(pm):
     assert L.pm_sync(None) == -2 and L.pm_destroy(None) == -2 and L.pm_clear_map(None) == -2
     assert L.pm_create(None, 0) == -2
     assert L.pm_last_error(None) == b"null context"
+
+
+def test_knn_map_goes_stale_when_its_records_are_rewritten(pm):
+    """A k-NN map built over the context's record buffers points into them; re-tracing with records (or resizing the buffers)
+    invalidates it: queries return PM_ERR_STATE until pm_knn_build runs again (they used to read rewritten / freed memory)."""
+    import torch
+    L = pm.lib()
+    m = pm.PhotonMapper(n_photons=5000)
+    m.init_random_numbers()
+    m.set_record_capacity(40000)
+    m.clear_map(); m.trace(0.0, records=True, no_map=True)
+    m.knn_build(0)
+    q = torch.zeros((4, 4), dtype=torch.float32, device="cuda")
+    out = torch.zeros((4, 4), dtype=torch.float32, device="cuda")
+    assert L.pm_knn_radiance(m.h, 0, C.c_void_p(q.data_ptr()), 4, 8, C.c_float(float("inf")), C.c_void_p(out.data_ptr())) == 0
+    m.clear_map(); m.trace(0.1, records=True, no_map=True)          # rewrites the buffers the map points into
+    assert L.pm_knn_radiance(m.h, 0, C.c_void_p(q.data_ptr()), 4, 8, C.c_float(float("inf")), C.c_void_p(out.data_ptr())) == -3
+    assert b"rebuild" in L.pm_last_error(m.h)
+    m.knn_build(0)
+    assert L.pm_knn_radiance(m.h, 0, C.c_void_p(q.data_ptr()), 4, 8, C.c_float(float("inf")), C.c_void_p(out.data_ptr())) == 0
+    m.set_record_capacity(50000)                                     # frees them
+    assert L.pm_knn_radiance(m.h, 0, C.c_void_p(q.data_ptr()), 4, 8, C.c_float(float("inf")), C.c_void_p(out.data_ptr())) == -3
+    m.close()

@@ -169,11 +169,13 @@ def test_knn_on_traced_photons(pm, oracle, media):
     m.close()
 
 
+@pytest.mark.parametrize("batched", [True, False])
 @pytest.mark.parametrize("media", [False, True])
-def test_render_knn_vs_oracle(pm, oracle, media):
+def test_render_knn_vs_oracle(pm, oracle, media, batched):
     """Mode B frame (pm_render_knn) against the oracle composition: eye-ray geometry from pm_oracle.c, brute-force k-NN
     estimates from knn_oracle.c, composited as documented in include/pmb200.h.  Tolerance 5e-5 of the frame maximum
-    (FP32 lane-order power sums vs double)."""
+    (FP32 power sums vs double).  batched: one lane per pixel, the tree walked once per 8 x 4 tile (pm_knn_set_batched);
+    otherwise the warp-per-pixel renderer (the default)."""
     import torch
     from pmb200 import dist as pd
     n, w, h, k = 20000, 64, 48, 50
@@ -184,6 +186,7 @@ def test_render_knn_vs_oracle(pm, oracle, media):
     m.set_scene(copy_scene(pm.Scene, osc))
     m.init_random_numbers()
     m.set_record_capacity(16 * n)
+    m.knn_set_batched(batched)
     m.clear_map()
     m.trace(0.0, media=media, records=True, no_map=True)
     m.knn_build(0)

@@ -37,8 +37,16 @@ if media:
     out["volume_points"] = m.knn_size(1)[0]
 rgba = torch.zeros((H, W, 4), dtype=torch.uint8, device="cuda")
 rgbf = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
-ms = ev(lambda: m.render_knn(W, H, 0.0, media, k, float("inf"), 1e-4, 1e-2, rgba=rgba, rgbf=rgbf), reps=2)
 nq = W * H * (11 if media else 1)
+if len(sys.argv) > 4 and sys.argv[4] == "both":      # round 1's warp-per-pixel renderer next to the batched one
+    m.knn_set_batched(False)
+    ms0 = ev(lambda: m.render_knn(W, H, 0.0, media, k, float("inf"), 1e-4, 1e-2, rgba=rgba, rgbf=rgbf), reps=2)
+    out["render_knn_warp_per_pixel_ms"] = ms0
+    ref = rgbf.clone()
+    m.knn_set_batched(True)
+ms = ev(lambda: m.render_knn(W, H, 0.0, media, k, float("inf"), 1e-4, 1e-2, rgba=rgba, rgbf=rgbf), reps=2)
+if len(sys.argv) > 4 and sys.argv[4] == "both":
+    out["max_rel_diff_between_renderers"] = float(((rgbf - ref).abs().max() / ref.abs().max()).item())
 out["render_knn_ms"] = ms
 out["queries_per_s"] = nq / (ms * 1e-3)
 out["frame_ms"] = out["trace_records_ms"] + out["build_surface_ms"] + out.get("build_volume_ms", 0.0) + ms
