@@ -513,7 +513,7 @@ def launch_photon_mapping_kernel(pos, image_width, image_height, animTime, inter
     lib().launch_photon_mapping_kernel(_ptr(pos), image_width, image_height, animTime, interpolateFlag, participatingMediaFlag)
 
 
-# -- the older variant's two launchers (kernelPBO.cu:295, :317), declared but never called by simplePBO.cpp ------------
+# -- the older variant's two launchers (kernelPBO.cu:295, :317); dead in the reference (declarations and calls commented out) ---
 def launch_render_kernel(pos, image_width, image_height, time, pixelData):
     lib().launch_render_kernel(_ptr(pos), image_width, image_height, time, _ptr(pixelData))
 

@@ -50,8 +50,9 @@ void launch_emit_photons_kernel(pm_uchar4 *pos, unsigned int image_width, unsign
 void launch_photon_mapping_kernel(pm_uchar4 *pos, unsigned int image_width, unsigned int image_height,
                                   float animTime, bool interpolateFlag, bool participatingMediaFlag);
 
-/* The two launchers of the older variant (kernelPBO.cu), still declared by the caller (simplePBO.cpp:21-24) although
- * every call site is commented out (simplePBO.cpp:118, :158, :176).  Provided so that the caller's declarations resolve.
+/* The two launchers of the older variant (kernelPBO.cu).  They are dead in the reference: the caller's declarations
+ * (simplePBO.cpp:21-24) sit inside a comment block (:20-25) and every call site is commented out (:118, :158, :176).  Exported anyway
+ * (round 1) so that they would resolve if re-enabled.
  * launch_render_kernel (kernelPBO.cu:295-313 + render_kernel :268-291): uploads a HOST array of image_width*image_height
  * float3 pixels and writes pos[i] = {(unsigned char)r, (unsigned char)g, (unsigned char)b, 0} into the DEVICE buffer pos --
  * no scaling, conversion as nvcc compiles it (cvt.rzi.u32.f32, low byte: negatives and NaN give 0, 300.0f gives 44).
@@ -117,8 +118,9 @@ int pm_set_volume_warps(pm_context *ctx, int warps);
  * map build + render, which the pipelined frame calls run on a second stream (worth it when those are a large part of the frame,
  * i.e. at 4-8 GPUs) */
 int pm_set_trace_sms(pm_context *ctx, int sms);
-/* the exact (int64 fixed-point) accumulators the trace adds into; sum them across GPUs (e.g. NCCL
- * all-reduce, ncclInt64/ncclSum) between pm_trace and pm_build_map for multi-GPU runs */
+/* the exact (int64 fixed-point) accumulators of the CURRENT frame (they rotate through three buffers, one per pm_clear_map).  Multi-GPU:
+ * connect the ranks (pm_peer_* / pm_group_*, below) and pm_build_map sums them itself over NVLink; summing them by hand between
+ * pm_trace and pm_build_map (e.g. ncclAllReduce, ncclInt64 / ncclSum -- round 1's path) still works when no peers are connected */
 int pm_accumulators(pm_context *ctx, void **dev_ptr, size_t *n_int64);
 int pm_get_accumulators_host(pm_context *ctx, int64_t *host_out /* n_int64 entries */);
 int pm_build_map(pm_context *ctx);                                 /* accumulators -> float photon map + gather tables */
