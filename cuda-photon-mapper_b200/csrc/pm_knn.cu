@@ -700,17 +700,29 @@ __global__ void __launch_bounds__(kQueryThreads) knn_render_kernel(const __grid_
 //     largest search radius (conservative in FP32 for the same reason as above), the set of children to visit is computed once per
 //     node and parked in a lane register per level; before a leaf is read, every lane tests the leaf's box against ITS sphere;
 //   * a leaf = 32 photons = one coalesced 512-byte load, staged in shared memory and broadcast to the lanes;
-//   * candidates (d2 <= the lane's limit) are appended to a per-lane list in shared memory ([slot][lane]: conflict-free); when a
-//     list could overflow during the next leaf, the lane selects its k smallest keys in place (max-heap) and tightens its limit;
-//   * the limit comes from a neighbouring query's k-th distance (x 1.2, as above); a lane that finds fewer than k photons inside
-//     it is searched again with the bound (r_k(neighbour) + distance to the neighbour)^2, which cannot fail (triangle inequality);
-//   * the result -- the k smallest keys (bits(d2) << 32 | original index) -- is the same set the warp-per-query search and the
-//     brute-force oracle return; only the summation order of the radiance estimate differs.
+//   * the limit of a lane comes from a neighbouring query's k-th distance (x 1.2, as above); lanes without one, or whose limit holds
+//     fewer than k photons, are seeded: the warp-per-query search gives the k-th distance r of one of their points p, and
+//     r_k(q) <= r + |q - p| (triangle inequality) bounds the others, so the second attempt cannot fail;
+//   * selection without per-lane lists: the tree is walked TWICE.  Walk 1 only counts, per lane, the photons inside the limit in 32
+//     bins of d2.  The bin j that holds the k-th nearest splits them: every photon in a lower bin is one of the k nearest and is
+//     accumulated directly in walk 2 (power sum, largest distance); the photons of bin j -- a handful -- go to a short per-lane
+//     list, of which the k - (count below) smallest keys are then extracted.  Both walks classify a photon with the same expression,
+//     and bin(d2) is monotone in d2, so the selected set is exactly the k smallest keys (bits(d2) << 32 | original index).
+//     (A first version collected every candidate in a 96-entry list per lane and selected with a heap or quickselect: data-dependent
+//     loops that 32 lanes execute one after the other, 60-70 K cycles per selection, and 27 KB of shared memory per warp -- 8 warps
+//     per SM.  It was 2x slower than the warp-per-query renderer.)
+//
+// MEASURED (B200, tools/time_knn.py, tools/knn_bstats.py): exact -- the frames agree with the warp-per-query renderer to 1e-8 -- but
+// SLOWER: 135 ms vs 16.1 ms (4M photons, k = 100) and 667 ms vs 195 ms (16M photons, k = 50, 11 gathers per pixel).  The premise does
+// not hold at BASELINE's densities: with 38 M wall photons a pixel's 50 nearest lie within 1.3 pixel spacings, so neighbouring
+// pixels share almost no photons; a tile's common walk touches 108 leaves where one query needs 16-30, every lane tests all of
+// them (a lane's test of a 32-photon leaf costs what the warp-per-query search pays per leaf: ~12 vs ~15 instructions per
+// (query, leaf) pair), and 16 warps per SM sustain a third of the issue rate.  Kept behind pm_knn_set_batched (off by default) as a
+// tested alternative; it wins only where the search radius spans many pixels.
 // ---------------------------------------------------------------------------------------------------------
 #ifdef PM_KNN_BSTATS
-// development counters of the batched search: 0 batches (batch_search calls), 1 tree walks, 2 node visits, 3 leaves listed by the
-// common test, 4 leaves some lane needed, 5 selections, 6 seed searches, 7 lanes searched one by one, 8.. cycles: 8 walks,
-// 9 selections, 10 seeds, 11 one-by-one, 12 radiance, 13 candidates appended (thread count), 14 whole tile
+// development counters: 0 batches, 1 walks, 2 node visits, 3 leaves listed, 4 leaves needed, 5 boundary overflows, 6 seeds,
+// 7 lanes searched one by one, 8 cycles in walks, 9 cycles selecting, 10 cycles seeding, 11 cycles one by one, 14 cycles per tile
 __device__ unsigned long long g_bstats[16];
 #define BSTAT(i, v) do { if (lane == 0) atomicAdd(&g_bstats[i], (unsigned long long)(v)); } while (0)
 #define BCLK() clock64()
@@ -720,48 +732,19 @@ __device__ unsigned long long g_bstats[16];
 #endif
 
 constexpr int kBatchStrip = 4;           // tiles per work unit (every unit starts with one seed search per query kind)
-template <int KL>
-struct BatchShared {                     // per warp
-  static constexpr int kCand = 32 * KL + 32;
-  float d2[kCand][32];
-  uint32_t idx[kCand][32];
+constexpr int kBins = 32;                // bins of d2 over [0, limit]
+constexpr int kBoundary = 32;            // per-lane list for the photons of the bin that holds the k-th nearest
+constexpr int kBatchWarps = 16;          // warps per CTA of the batched renderer
+struct BatchShared {                     // per warp: 12.6 KB
   float4 leaf[32];
+  unsigned short bins[kBins][32];
+  float bd2[kBoundary][32];
+  uint32_t bidx[kBoundary][32];
   float hint[11][32];                    // per lane: k-th squared distance of the last search per query kind (10 march steps + wall)
-  u64 pend[64];                          // scratch of the warp-per-query search that seeds a strip
+  u64 pend[64];                          // scratch of the warp-per-query search (seeds, incoherent tiles)
 };
 
 __device__ __forceinline__ u64 cand_key(float d2, uint32_t idx) { return ((u64)__float_as_uint(d2) << 32) | idx; }
-
-// in place: the k smallest keys of slots [0, cnt) end up in slots [0, k), the k-th smallest in slot k-1.  cnt > k.  Quickselect
-// (Hoare partition, median-of-three pivot) on the lane's own list: every pass streams over its range with independent
-// shared-memory loads.  (A first version kept a max-heap: its sift-downs are chains of dependent loads, 60-70 K cycles per
-// selection with the handful of warps an SM holds here -- 70% of the kernel.)  Keys are distinct (they contain the photon index).
-template <int KL>
-__device__ __forceinline__ void select_k(BatchShared<KL> &sm, int lane, int cnt, int k) {
-  auto key = [&](int i) { return cand_key(sm.d2[i][lane], sm.idx[i][lane]); };
-  int lo = 0, hi = cnt - 1;
-  const int target = k - 1;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    const u64 a = key(lo), b = key(mid), c = key(hi);
-    const u64 pivot = a < b ? (b < c ? b : (a < c ? c : a)) : (a < c ? a : (b < c ? c : b));   // median of three
-    int i = lo, j = hi;
-    while (i <= j) {
-      while (key(i) < pivot) i++;
-      while (key(j) > pivot) j--;
-      if (i <= j) {
-        const float di = sm.d2[i][lane], dj = sm.d2[j][lane];
-        const uint32_t xi = sm.idx[i][lane], xj = sm.idx[j][lane];
-        sm.d2[i][lane] = dj; sm.idx[i][lane] = xj; sm.d2[j][lane] = di; sm.idx[j][lane] = xi;
-        i++; j--;
-      }
-    }
-    if (target <= j) hi = j;
-    else if (target >= i) lo = i;
-    else break;
-  }
-}
-
 __device__ __forceinline__ float warp_min_f(float v) {
 #pragma unroll
   for (int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -773,21 +756,18 @@ __device__ __forceinline__ float warp_max_f(float v) {
   return v;
 }
 
-// One walk of the tree for the whole warp.  Lane state: query (qx, qy, qz), lim = accept d2 <= lim (negative: the lane takes no
-// part), cnt = candidates collected so far (slots [0, cnt) of the lane's list).  On return slots [0, min(cnt, k)) hold the lane's
-// k smallest keys among all photons with d2 <= the lim it was called with (as the k-th smallest in slot k-1 when cnt >= k), and lim may have shrunk.
-template <int KL>
-__device__ __forceinline__ void batch_collect(const TreeView &tv, BatchShared<KL> &sm, float qx, float qy, float qz, float &lim, int k, int lane,
-                                              int &cnt) {
-  constexpr int kCand = BatchShared<KL>::kCand;
+// One walk of the tree for the whole warp.  Lane state: query (qx, qy, qz), lim = visit photons with d2 <= lim (negative: the lane
+// takes no part).  point(d2, original index) is called by a lane for every photon inside its limit.
+template <class PointFn>
+__device__ __forceinline__ void batch_walk(const TreeView &tv, float4 *__restrict__ leaf, float qx, float qy, float qz, float lim, int lane,
+                                           PointFn &&point) {
   const float inf = cuda::std::numeric_limits<float>::infinity();
-  cnt = 0;
   if (tv.n <= 0) return;
   const bool act = lim >= 0.0f;
   // the batch's bounding box and largest radius (inactive lanes do not widen them)
   const float blx = warp_min_f(act ? qx : inf), bly = warp_min_f(act ? qy : inf), blz = warp_min_f(act ? qz : inf);
   const float bhx = warp_max_f(act ? qx : -inf), bhy = warp_max_f(act ? qy : -inf), bhz = warp_max_f(act ? qz : -inf);
-  float max_lim = warp_max_f(act ? lim : -1.0f);
+  const float max_lim = warp_max_f(act ? lim : -1.0f);
   if (!(max_lim >= 0.0f)) return;
   BSTAT(1, 1);
   long long my_node = 0; unsigned my_pend = 0;      // lane l parks the state of level l: node index, children still to visit
@@ -796,7 +776,7 @@ __device__ __forceinline__ void batch_collect(const TreeView &tv, BatchShared<KL
   bool enter = true;
   long long j = 0;
   for (;;) {
-    if (enter) {   // first visit of node j at `level`: which of its 32 children can hold a candidate of ANY lane
+    if (enter) {   // first visit of node j at `level`: which of its 32 children can hold a photon inside ANY lane's limit
       const int cl = level - 1;
       const long long e = j * 32 + lane;
       bool ok = false;
@@ -811,7 +791,7 @@ __device__ __forceinline__ void batch_collect(const TreeView &tv, BatchShared<KL
       if (lane == level) { my_node = j; my_pend = m; }
       enter = false;
     }
-    unsigned pend = __shfl_sync(0xffffffffu, my_pend, level);
+    const unsigned pend = __shfl_sync(0xffffffffu, my_pend, level);
     if (!pend) {                                    // nothing left under this node
       level++;
       if (level > tv.levels) break;
@@ -823,167 +803,212 @@ __device__ __forceinline__ void batch_collect(const TreeView &tv, BatchShared<KL
     const long long child = j * 32 + c;
     if (level > 1) { level--; j = child; enter = true; continue; }
     // ---- leaf `child`: its box sits in lane c's registers (the node entered last is this leaf's parent) ----
-    {
-      const float clx = __shfl_sync(0xffffffffu, lx, c), cly = __shfl_sync(0xffffffffu, ly, c), clz = __shfl_sync(0xffffffffu, lz, c);
-      const float chx = __shfl_sync(0xffffffffu, hx, c), chy = __shfl_sync(0xffffffffu, hy, c), chz = __shfl_sync(0xffffffffu, hz, c);
-      const bool need = lim >= 0.0f && box_dist2(clx, cly, clz, chx, chy, chz, qx, qy, qz) <= lim;
-      if (!__ballot_sync(0xffffffffu, need)) continue;
-      BSTAT(4, 1);
-      if (__ballot_sync(0xffffffffu, cnt > kCand - 32)) {   // a list could overflow in this leaf: keep the k best, tighten the limit
-        BSTAT(5, 1);
-        const long long t_sel = BCLK();
-        if (cnt > k) {
-          select_k<KL>(sm, lane, cnt, k);
-          cnt = k;
-          lim = fminf(lim, sm.d2[k - 1][lane]);
-        }
-        __syncwarp();
-        BSTAT(9, BCLK() - t_sel);
-        max_lim = warp_max_f(lim);   // (the batch box is left as it is: conservative)
-      }
-      const long long i = child * 32 + lane;
-      float4 p = make_float4(inf, inf, inf, 0.0f);
-      if (i < tv.n) p = __ldg(tv.spos + i);
-      __syncwarp();
-      sm.leaf[lane] = p;
-      __syncwarp();
-      if (need) {
+    const float clx = __shfl_sync(0xffffffffu, lx, c), cly = __shfl_sync(0xffffffffu, ly, c), clz = __shfl_sync(0xffffffffu, lz, c);
+    const float chx = __shfl_sync(0xffffffffu, hx, c), chy = __shfl_sync(0xffffffffu, hy, c), chz = __shfl_sync(0xffffffffu, hz, c);
+    const bool need = act && box_dist2(clx, cly, clz, chx, chy, chz, qx, qy, qz) <= lim;
+    if (!__ballot_sync(0xffffffffu, need)) continue;
+    BSTAT(4, 1);
+    const long long i = child * 32 + lane;
+    float4 p = make_float4(inf, inf, inf, 0.0f);
+    if (i < tv.n) p = __ldg(tv.spos + i);
+    __syncwarp();
+    leaf[lane] = p;
+    __syncwarp();
+    if (need) {
 #pragma unroll 8
-        for (int t = 0; t < 32; t++) {
-          const float4 s = sm.leaf[t];
-          const float dx = s.x - qx, dy = s.y - qy, dz = s.z - qz;
-          const float d2 = (dx * dx + dy * dy) + dz * dz;
-          if (d2 <= lim) { sm.d2[cnt][lane] = d2; sm.idx[cnt][lane] = __float_as_uint(s.w); cnt++; }
-#ifdef PM_KNN_BSTATS
-          if (d2 <= lim) atomicAdd(&g_bstats[13], 1ull);
-#endif
-        }
+      for (int t = 0; t < 32; t++) {
+        const float4 s = leaf[t];
+        const float dx = s.x - qx, dy = s.y - qy, dz = s.z - qz;
+        const float d2 = (dx * dx + dy * dy) + dz * dz;
+        if (d2 <= lim) point(d2, __float_as_uint(s.w));
       }
     }
   }
-  {
-    BSTAT(5, 1);
-    const long long t_sel = BCLK();
-    if (cnt > k) { select_k<KL>(sm, lane, cnt, k); cnt = k; lim = fminf(lim, sm.d2[k - 1][lane]); }
-    __syncwarp();
-    BSTAT(9, BCLK() - t_sel);
-  }
+  __syncwarp();
 }
 
-// radiance estimate of the lane's result (slots [0, n)): sum of the powers / (pi r_k^2) or (4/3 pi r_k^3); returns r_k^2 in .w
+// The radiance estimate over the exact k nearest photons of every lane's query (active = false: the lane has none): returns
+// (sum of their powers / (pi r_k^2) or (4/3 pi r_k^3), r_k^2; r_k^2 = inf when fewer than k photons lie within max_r2 -- the estimate is
+// then taken over those).  hint_r2: a neighbouring query's k-th squared distance (inf: none).
 template <int KL>
-__device__ __forceinline__ float4 batch_radiance(const BatchShared<KL> &sm, int lane, int n, const float4 *__restrict__ power, int volume) {
-  float r = 0.0f, g = 0.0f, b = 0.0f, rk2 = 0.0f;
-  for (int i = 0; i < n; i++) {
-    const float4 pw = __ldg(power + sm.idx[i][lane]);
-    r += pw.x; g += pw.y; b += pw.z;
-    rk2 = fmaxf(rk2, sm.d2[i][lane]);
-  }
-  const float PI = 3.14159265358979323846f;
-  const float den = volume ? (4.0f / 3.0f) * PI * rk2 * __fsqrt_rn(rk2) : PI * rk2;
-  const float inv = den > 0.0f ? __fdiv_rn(1.0f, den) : 0.0f;
-  return make_float4(r * inv, g * inv, b * inv, rk2);
-}
-
-// The exact k nearest photons of every lane's query (active = false: the lane has none).  hint_r2: a neighbouring query's k-th
-// squared distance (inf: none).  Lanes without a usable limit -- no hint, or fewer than k photons inside 1.44 x the hint -- are
-// seeded: the warp-per-query search finds the k-th distance r of the first such lane's point p, and r_k(q) <= r + |q - p| bounds
-// every other one (triangle inequality), so the second walk cannot fail.  Returns the number found (k unless the map holds fewer
-// within max_r2); the lane's result sits in slots [0, n) of its list.
-template <int KL>
-__device__ __forceinline__ int batch_search(const TreeView &tv, BatchShared<KL> &sm, bool active, float qx, float qy, float qz, int k, float max_r2,
-                                            float hint_r2, int lane) {
+__device__ __forceinline__ float4 batch_estimate(const TreeView &tv, BatchShared &sm, bool active, float qx, float qy, float qz, int k, float max_r2,
+                                                 float hint_r2, const float4 *__restrict__ power, int volume, int lane) {
   const float inf = cuda::std::numeric_limits<float>::infinity();
   BSTAT(0, 1);
   bool seed = active && !(hint_r2 * 1.44f < max_r2);    // no finite limit of its own
   bool todo = active;
-  float lim = -1.0f;
-  int cnt = 0;
+  float sr = 0.0f, sg = 0.0f, sb = 0.0f, rk2 = 0.0f;     // the lane's result: power sum and largest squared distance of the selected photons
+  int found = 0;
+  auto finish_one_by_one = [&](unsigned tm, const float lim_of_lane) {   // warp-per-query search for every lane of tm, result into that lane
+    BSTAT(7, __popc(tm));
+    const long long t_one = BCLK();
+    while (tm) {
+      const int src = __ffs(tm) - 1;
+      tm &= tm - 1;
+      const float sx = __shfl_sync(0xffffffffu, qx, src), sy = __shfl_sync(0xffffffffu, qy, src), sz = __shfl_sync(0xffffffffu, qz, src);
+      float l = __shfl_sync(0xffffffffu, lim_of_lane, src);
+      TopK<KL> top;
+      for (;;) {
+        knn_search<KL>(tv, nullptr, sm.pend, sx, sy, sz, k, l, lane, top);
+        if (top.at(k - 1) != kMaxKey || !(l < max_r2)) break;
+        l = max_r2;                                     // the limit was too tight: unbounded (nearest-first) retry
+      }
+      float r = 0.0f, g = 0.0f, b = 0.0f, m2 = 0.0f; int n = 0;
+#pragma unroll
+      for (int i = 0; i < KL; i++) {
+        const int pos = i * 32 + lane;
+        if (pos < k && top.s[i] != kMaxKey) {
+          const float4 pw = __ldg(power + (uint32_t)(top.s[i] & 0xffffffffu));
+          r += pw.x; g += pw.y; b += pw.z; n++;
+          m2 = fmaxf(m2, __uint_as_float((uint32_t)(top.s[i] >> 32)));
+        }
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        r += __shfl_xor_sync(0xffffffffu, r, o); g += __shfl_xor_sync(0xffffffffu, g, o); b += __shfl_xor_sync(0xffffffffu, b, o);
+        n += __shfl_xor_sync(0xffffffffu, n, o); m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+      }
+      if (lane == src) { sr = r; sg = g; sb = b; rk2 = m2; found = n; }
+    }
+    BSTAT(11, BCLK() - t_one);
+  };
   for (int round = 0; round < 2; round++) {
-    const unsigned sm_mask = __ballot_sync(0xffffffffu, seed);
+    // Seeding.  The bound (r + |q - p|)^2 is only useful near p: a lane farther than r from the seed point would get a limit holding
+    // many times k photons (and a walk counts all of them), so it waits for a seed of its own -- at worst every lane is searched
+    // alone, which is what the warp-per-query renderer does anyway.
     float bound = inf;
-    if (sm_mask) {
+    bool need_seed = seed;
+    for (;;) {
+      const unsigned seed_mask = __ballot_sync(0xffffffffu, need_seed);
+      if (!seed_mask) break;
       BSTAT(6, 1);
       const long long t_seed = BCLK();
-      const int src = __ffs(sm_mask) - 1;
+      const int src = __ffs(seed_mask) - 1;
       const float sx = __shfl_sync(0xffffffffu, qx, src), sy = __shfl_sync(0xffffffffu, qy, src), sz = __shfl_sync(0xffffffffu, qz, src);
       TopK<KL> top;
       knn_search<KL>(tv, nullptr, sm.pend, sx, sy, sz, k, max_r2, lane, top);
       const u64 kth = top.at(k - 1);
-      if (kth != kMaxKey) {   // a relative 2e-5 and a denormal cover the FP32 rounding of the bound itself
-        const float dx = qx - sx, dy = qy - sy, dz = qz - sz;
-        const float rb = __fsqrt_rn(__uint_as_float((uint32_t)(kth >> 32))) + __fsqrt_rn((dx * dx + dy * dy) + dz * dz) * 1.000001f;
+      if (kth == kMaxKey) {     // the map holds fewer than k photons within max_r2: no finite bound, the lanes go one by one below
+        BSTAT(10, BCLK() - t_seed);
+        break;
+      }
+      const float r2 = __uint_as_float((uint32_t)(kth >> 32));
+      const float dx = qx - sx, dy = qy - sy, dz = qz - sz;
+      const float dd = (dx * dx + dy * dy) + dz * dz;
+      if (need_seed && (dd <= r2 || lane == src)) {   // a relative 2e-5 and a denormal cover the FP32 rounding of the bound itself
+        const float rb = __fsqrt_rn(r2) + __fsqrt_rn(dd) * 1.000001f;
         bound = rb * rb * 1.00002f + 1e-30f;
+        need_seed = false;
       }
       BSTAT(10, BCLK() - t_seed);
     }
-    lim = !todo ? -1.0f : (seed ? fminf(max_r2, bound) : fminf(max_r2, hint_r2 * 1.44f));
+    const float lim = !todo ? -1.0f : (seed ? fminf(max_r2, bound) : fminf(max_r2, hint_r2 * 1.44f));
     const bool guaranteed = seed;
     // A common walk only pays while the queries are neighbours.  The pixels of a tile that straddles a silhouette, or that see the
     // scene through the mirror / glass sphere, have wall points all over the scene: their common box would hold the whole map.
-    // Such a batch (box diagonal > 8 x the largest radius) is searched lane by lane with the warp-per-query search instead.
+    // Such a batch (box diagonal > 8 x the largest radius), and one whose limit is not finite (a map with fewer than k photons),
+    // is searched lane by lane with the warp-per-query search instead.
     {
       const float blx = warp_min_f(todo ? qx : inf), bly = warp_min_f(todo ? qy : inf), blz = warp_min_f(todo ? qz : inf);
       const float bhx = warp_max_f(todo ? qx : -inf), bhy = warp_max_f(todo ? qy : -inf), bhz = warp_max_f(todo ? qz : -inf);
       const float ex = bhx - blx, ey = bhy - bly, ez = bhz - blz;
       const float max_lim = warp_max_f(todo ? lim : -1.0f);
-      unsigned tm = __ballot_sync(0xffffffffu, todo);
-      if (tm && !((ex * ex + ey * ey) + ez * ez <= 64.0f * max_lim)) {
-        BSTAT(7, __popc(tm));
-        const long long t_one = BCLK();
-        while (tm) {
-          const int src = __ffs(tm) - 1;
-          tm &= tm - 1;
-          const float sx = __shfl_sync(0xffffffffu, qx, src), sy = __shfl_sync(0xffffffffu, qy, src), sz = __shfl_sync(0xffffffffu, qz, src);
-          float l = __shfl_sync(0xffffffffu, lim, src);
-          TopK<KL> top;
-          for (;;) {
-            knn_search<KL>(tv, nullptr, sm.pend, sx, sy, sz, k, l, lane, top);
-            if (top.at(k - 1) != kMaxKey || !(l < max_r2)) break;
-            l = max_r2;                                   // the limit was too tight: unbounded (nearest-first) retry
-          }
-          int found = 0;
-#pragma unroll
-          for (int i = 0; i < KL; i++) {                   // the sorted list (position i*32+lane) goes into lane src's candidate list
-            const int pos = i * 32 + lane;
-            const bool have = pos < k && top.s[i] != kMaxKey;
-            if (have) { sm.d2[pos][src] = __uint_as_float((uint32_t)(top.s[i] >> 32)); sm.idx[pos][src] = (uint32_t)(top.s[i] & 0xffffffffu); }
-            found += __popc(__ballot_sync(0xffffffffu, have));
-          }
-          if (lane == src) cnt = found;
-          __syncwarp();
-        }
-        BSTAT(11, BCLK() - t_one);
+      const unsigned tm = __ballot_sync(0xffffffffu, todo);
+      if (tm && !((ex * ex + ey * ey) + ez * ez <= 64.0f * max_lim && max_lim < inf)) {
+        finish_one_by_one(tm, lim);
         break;
       }
     }
-    int c = 0;
+    // ---- walk 1: count the photons inside the limit per bin of d2 ----
     const long long t_walk = BCLK();
-    if (__ballot_sync(0xffffffffu, todo)) batch_collect<KL>(tv, sm, qx, qy, qz, lim, k, lane, c);
+    const float inv_w = todo ? __fdiv_rn((float)kBins, lim) : 0.0f;   // bin(d2) = min(kBins - 1, (int)(d2 * inv_w)): monotone in d2
+    auto bin_of = [&](float d2) { const int b = __float2int_rz(d2 * inv_w); return b < kBins - 1 ? b : kBins - 1; };
+#pragma unroll
+    for (int b = 0; b < kBins; b++) sm.bins[b][lane] = 0;
+    __syncwarp();
+    batch_walk(tv, sm.leaf, qx, qy, qz, lim, lane, [&](float d2, uint32_t) { sm.bins[bin_of(d2)][lane]++; });
+    int jbin = -1, below = 0, total = 0;
+#pragma unroll
+    for (int b = 0; b < kBins; b++) {
+      const int c = sm.bins[b][lane];
+      if (jbin < 0 && total + c >= k) { jbin = b; below = total; }
+      total += c;
+    }
+    // a lane whose limit holds fewer than k photons goes again, seeded -- unless its limit was already max_r2 or a guaranteed bound
+    // (then the map simply holds fewer than k photons within max_r2 and all of them count)
+    const bool short_of_k = todo && total < k;
+    const bool final_short = short_of_k && (guaranteed || !(lim < max_r2));
+    if (final_short) { jbin = kBins; below = total; }            // every bin is "below"
+    const bool take = todo && (jbin >= 0);
+    // ---- walk 2: accumulate the photons of the bins below jbin, list the photons of bin jbin ----
+    // pruning limit: nothing beyond bin jbin matters; (jbin + 1) / inv_w, widened against the rounding of the product in bin_of
+    const float lim2 = !take ? -1.0f : (jbin >= kBins - 1 ? lim : fminf(lim, __fdiv_rn((float)(jbin + 1), inv_w) * 1.00001f));
+    int nb = 0;
+    if (__ballot_sync(0xffffffffu, take))
+      batch_walk(tv, sm.leaf, qx, qy, qz, lim2, lane, [&](float d2, uint32_t idx) {
+        const int b = bin_of(d2);
+        if (b < jbin) {
+          const float4 pw = __ldg(power + idx);
+          sr += pw.x; sg += pw.y; sb += pw.z; rk2 = fmaxf(rk2, d2);
+        } else if (b == jbin) {
+          if (nb < kBoundary) { sm.bd2[nb][lane] = d2; sm.bidx[nb][lane] = idx; }
+          nb++;
+        }
+      });
     BSTAT(8, BCLK() - t_walk);
-    if (todo) cnt = c;
-    // a lane whose heuristic limit held fewer than k photons goes again, seeded; everything else is final (a lane that sits out
-    // has lim < 0 and its list is not touched by the second walk)
-    seed = todo && !guaranteed && c < k;
+    // ---- the k - below smallest keys of the boundary list: repeated extraction of the smallest key above the last one ----
+    const long long t_sel = BCLK();
+    const bool overflow = take && nb > kBoundary;
+    int want = (take && !overflow && jbin < kBins) ? k - below : 0;
+    u64 last = 0ull; bool first = true;
+    const int max_want = __reduce_max_sync(0xffffffffu, want), max_nb = __reduce_max_sync(0xffffffffu, overflow ? 0 : (take ? nb : 0));
+    for (int r = 0; r < max_want; r++) {
+      u64 best = kMaxKey; int bi = -1;
+      for (int i = 0; i < max_nb; i++) {
+        if (i < nb) {
+          const u64 key = cand_key(sm.bd2[i][lane], sm.bidx[i][lane]);
+          if ((first || key > last) && key < best) { best = key; bi = i; }
+        }
+      }
+      if (r < want && bi >= 0) {
+        const float4 pw = __ldg(power + sm.bidx[bi][lane]);
+        sr += pw.x; sg += pw.y; sb += pw.z; rk2 = fmaxf(rk2, sm.bd2[bi][lane]);
+        last = best; first = false;
+      }
+    }
+    BSTAT(9, BCLK() - t_sel);
+    if (take && !overflow) found = final_short ? total : k;
+    // lanes whose boundary bin overflowed the list (a very uneven density inside the limit) are searched one by one
+    const unsigned om = __ballot_sync(0xffffffffu, overflow);
+    if (om) {
+      BSTAT(5, __popc(om));
+      if (overflow) { sr = sg = sb = rk2 = 0.0f; }
+      finish_one_by_one(om, lim);
+    }
+    seed = short_of_k && !final_short;
     todo = seed;
+    if (seed) { sr = sg = sb = rk2 = 0.0f; }
     if (!__ballot_sync(0xffffffffu, todo)) break;
   }
-  return cnt;
+  const float PI = 3.14159265358979323846f;
+  const float den = volume ? (4.0f / 3.0f) * PI * rk2 * __fsqrt_rn(rk2) : PI * rk2;
+  const float inv = den > 0.0f ? __fdiv_rn(1.0f, den) : 0.0f;
+  return make_float4(sr * inv, sg * inv, sb * inv, found >= k ? rk2 : inf);
 }
 
 template <int KL>
-__global__ void __launch_bounds__(256) knn_render_batched_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ TreeView tvs,
-                                                                 const __grid_constant__ TreeView tvv, const float4 *__restrict__ pow_s,
-                                                                 const float4 *__restrict__ pow_v, int k, float max_r2, float w_surf, float w_vol,
-                                                                 int width, int height, int y0, int y1, int y_step, int media,
-                                                                 uchar4 *__restrict__ rgba, float4 *__restrict__ rgbf,
-                                                                 unsigned long long *__restrict__ work_counter) {
+__global__ void __launch_bounds__(kBatchWarps * 32) knn_render_batched_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ TreeView tvs,
+                                                                              const __grid_constant__ TreeView tvv, const float4 *__restrict__ pow_s,
+                                                                              const float4 *__restrict__ pow_v, int k, float max_r2, float w_surf,
+                                                                              float w_vol, int width, int height, int y0, int y1, int y_step, int media,
+                                                                              uchar4 *__restrict__ rgba, float4 *__restrict__ rgbf,
+                                                                              unsigned long long *__restrict__ work_counter) {
   extern __shared__ __align__(128) unsigned char dyn[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  BatchShared<KL> &sm = reinterpret_cast<BatchShared<KL> *>(dyn)[w];
+  BatchShared &sm = reinterpret_cast<BatchShared *>(dyn)[w];
   const float inf = cuda::std::numeric_limits<float>::infinity();
   const int nrows = (y1 - y0 + y_step - 1) / y_step;   // rows y0, y0+y_step, ... < y1
-  // Work unit: a strip of kStrip tiles of 8 x 4 pixels along a row of tiles, fetched from a global counter (the cost of a pixel
+  // Work unit: a strip of kBatchStrip tiles of 8 x 4 pixels along a row of tiles, fetched from a global counter (the cost of a pixel
   // varies by orders of magnitude over the image); lane = (ty, tx) of the tile.  A tile takes its limits from the tile before it
   // in the strip (the lane of the same row in its last column); the first tile of a strip has no neighbour and is seeded.
   constexpr int kTileW = 8, kTileH = 4, kStrip = kBatchStrip;
@@ -993,13 +1018,9 @@ __global__ void __launch_bounds__(256) knn_render_batched_kernel(const __grid_co
   // one query kind (march step 0..9, wall point = 10) for all 32 pixels of the tile at a time
   auto run_kind = [&](const TreeView &tv, const float4 *__restrict__ power, int kind, bool first_tile, bool active, v3 q, int volume) -> v3 {
     const float prev_r2 = __shfl_sync(0xffffffffu, sm.hint[kind][lane], ty * 8 + 7);
-    const int n = batch_search<KL>(tv, sm, active, q.x, q.y, q.z, k, max_r2, first_tile ? inf : prev_r2, lane);
-    float4 e = make_float4(0.0f, 0.0f, 0.0f, inf);
-    const long long t_rad = BCLK();
-    if (active) e = batch_radiance<KL>(sm, lane, n, power, volume);
+    const float4 e = batch_estimate<KL>(tv, sm, active, q.x, q.y, q.z, k, max_r2, first_tile ? inf : prev_r2, power, volume, lane);
     __syncwarp();
-    BSTAT(12, BCLK() - t_rad);
-    sm.hint[kind][lane] = (active && n >= k) ? e.w : inf;
+    sm.hint[kind][lane] = active ? e.w : inf;
     __syncwarp();
     return V(e.x, e.y, e.z);
   };
@@ -1187,16 +1208,16 @@ cudaError_t knn_render(const DeviceScene &sc, const KnnMap &ms, const KnnMap &mv
     KCK(cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), st));
     const int nrows = (y1 - y0 + y_step - 1) / y_step;
     const long long units = (long long)(((width + 7) / 8 + kBatchStrip - 1) / kBatchStrip) * ((nrows + 3) / 4);
-#define LAUNCH_BATCHED(KL, WARPS)                                                                                               \
+#define LAUNCH_BATCHED(KL)                                                                                                      \
     do {                                                                                                                        \
-      const size_t smem = sizeof(BatchShared<KL>) * WARPS;                                                                      \
+      const size_t smem = sizeof(BatchShared) * kBatchWarps;                                                                    \
       KCK(cudaFuncSetAttribute(knn_render_batched_kernel<KL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
-      long long want = (units + WARPS - 1) / WARPS;                                                                             \
+      long long want = (units + kBatchWarps - 1) / kBatchWarps;                                                                 \
       unsigned grid = (unsigned)(want < (long long)num_sms ? want : (long long)num_sms);                                        \
-      knn_render_batched_kernel<KL><<<grid, WARPS * 32, smem, st>>>(sc, tvs, tvv, ms.power, mv.power, k, max_r2, w_surf, w_vol, width, height, \
-                                                                     y0, y1, y_step, media ? 1 : 0, rgba, rgbf, work_counter);              \
+      knn_render_batched_kernel<KL><<<grid, kBatchWarps * 32, smem, st>>>(sc, tvs, tvv, ms.power, mv.power, k, max_r2, w_surf, w_vol, width,   \
+                                                                           height, y0, y1, y_step, media ? 1 : 0, rgba, rgbf, work_counter);    \
     } while (0)
-    if (k <= 32) LAUNCH_BATCHED(1, 8); else if (k <= 64) LAUNCH_BATCHED(2, 8); else LAUNCH_BATCHED(4, 5);
+    if (k <= 32) LAUNCH_BATCHED(1); else if (k <= 64) LAUNCH_BATCHED(2); else LAUNCH_BATCHED(4);
 #undef LAUNCH_BATCHED
     return cudaGetLastError();
   }

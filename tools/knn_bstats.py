@@ -13,12 +13,13 @@ m.knn_build(0)
 if media: m.knn_build(1)
 rgba = torch.zeros((H, W, 4), dtype=torch.uint8, device="cuda")
 L = pmb200.lib()
+m.knn_set_batched(True)
 out = (C.c_ulonglong * 16)()
 L.pm_debug_knn_bstats(out, 1)
 m.render_knn(W, H, 0.0, media, k, float("inf"), 1e-4, 1e-2, rgba=rgba); m.sync()
 L.pm_debug_knn_bstats(out, 1)
 s = [int(x) for x in out]
-names = ["batches", "walks", "node visits", "leaves listed", "leaves needed", "selections", "seeds", "one-by-one lanes", "cyc walks", "cyc selections",
+names = ["batches", "walks", "node visits", "leaves listed", "leaves needed", "boundary overflows", "seeds", "one-by-one lanes", "cyc walks", "cyc selections",
          "cyc seeds", "cyc one-by-one", "cyc radiance", "candidates", "cyc tiles"]
 b = max(s[0], 1)
 for i, nm in enumerate(names):
