@@ -336,7 +336,9 @@ constexpr size_t kSurfaceSmem = sizeof(uint32_t) * (2 * kAccHitEntries + kShadow
 // Warp-specialised: warps [0, vol_warps) of every CTA run the medium walk of the CTA's photon range (L2-atomic bound,
 // nearly no issue slots), the other warps run the surface walk (issue bound, no L2 traffic) -- the two halves of
 // emitPhotons overlap on the same SM instead of running back to back.  vol_warps = 0: surface walk only.
-template <bool kRec>   // kRec: the launch appends photon records (PM_TRACE_RECORDS); Mode A compiles that path out
+// kRec: the launch appends photon records (PM_TRACE_RECORDS); Mode A compiles that path out.  kStd: the scene has the reference's
+// object layout (pm_math.cuh raytrace<kStd>)
+template <bool kRec, bool kStd>
 __global__ void __launch_bounds__(kSurfaceThreads, 1) trace_kernel(const __grid_constant__ DeviceScene sc,
                                                                    const float4 *__restrict__ table, long long first, long long last,
                                                                    unsigned flags, int vol_warps, uint32_t w0, uint32_t z0,
@@ -408,7 +410,7 @@ __global__ void __launch_bounds__(kSurfaceThreads, 1) trace_kernel(const __grid_
     if (state == ST_IDLE) continue;
 
     // ---- the single intersection site ----
-    raytrace(sc, ray, org, h);
+    raytrace<kStd>(sc, ray, org, h);
 
     // ---- mirror / glass chain: handleReflection/handleRefraction{,2,3,4}, PMK:673-827 ----
     if (state >= ST_CHAIN_R) {
@@ -437,7 +439,7 @@ __global__ void __launch_bounds__(kSurfaceThreads, 1) trace_kernel(const __grid_
         if (level == 4 || !(h.type == 0 && h.idx == 1)) chain_done = true;   // not gated on h.hit: stale ids, as PMK:807
         else {
           level++;
-          ray = reflect3(sc, ray, prev, h.type, h.idx, P);
+          ray = reflect3<kStd>(sc, ray, prev, h.type, h.idx, P);
           org = P; state = ST_CHAIN_R;
         }
       }
@@ -473,7 +475,7 @@ __global__ void __launch_bounds__(kSurfaceThreads, 1) trace_kernel(const __grid_
       prev = P;
       if (h.type == 0 && h.idx == 1) {          // mirror sphere
         chain_glass = false; level = 1;
-        ray = reflect3(sc, ray, prev, h.type, h.idx, P);
+        ray = reflect3<kStd>(sc, ray, prev, h.type, h.idx, P);
         org = P; state = ST_CHAIN_R;
       } else if (h.type == 0 && h.idx == 0) {   // glass sphere
         chain_glass = true; level = 1;
@@ -484,11 +486,11 @@ __global__ void __launch_bounds__(kSurfaceThreads, 1) trace_kernel(const __grid_
         // Hazard H1: the wall "normal" is normalize(e_axis * (prev.axis - offset)).  When that offset squares to 0
         // (the hit point lies exactly on the wall, ~88% of bounces) or is NaN, the normal, the reflected ray and hence
         // every intersection test of the next raytrace are NaN: no hit, the photon ends.  Skip straight to that outcome.
-        const int wax = h.type == 1 ? sc.pl_axis[h.idx] : -1;
+        const int wax = h.type == 1 ? (kStd ? std_axis(h.idx) : sc.pl_axis[h.idx]) : -1;
         const float wd = comp(prev, wax) - sc.pl_off[h.type == 1 ? h.idx : 0];
         const float wdd = wd * wd;
         if (h.type == 1 && wax >= 0 && wax <= 2 && (wdd == 0.0f || wdd != wdd)) { state = ST_IDLE; continue; }
-        ray = reflect3(sc, ray, prev, h.type, h.idx, P);
+        ray = reflect3<kStd>(sc, ray, prev, h.type, h.idx, P);
         org = P;
         caustics = false; new_point = true; bounces++;
         state = ST_PRIMARY;
@@ -522,8 +524,10 @@ cudaError_t preload_trace_kernels() {
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, philox_table_kernel);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, volume_kernel);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, fold_volume_kernel);
-  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, trace_kernel<false>);
-  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, trace_kernel<true>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, trace_kernel<false, false>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, trace_kernel<true, false>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, trace_kernel<false, true>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, trace_kernel<true, true>);
   return e;
 }
 
@@ -592,7 +596,14 @@ int launch_trace(const DeviceScene &sc, const float4 *table, long long first, lo
   Sink sk = make_sink(flags, acc, rec_pos, rec_pow, rec_dir, rec_count, rec_cap);
   sk.vol_cnt = vol_cnt; sk.vrec_pos = vrec_pos; sk.vrec_pow = vrec_pow; sk.vrec_cap = vrec_cap; sk.dbg = dbg; sk.vox_touched = vox_touched;
   const bool rec = (flags & PM_TRACE_RECORDS) != 0;
-  auto kernel = rec ? trace_kernel<true> : trace_kernel<false>;
+  // the reference's object layout (only the layout: offsets, centres and radii stay scene data) selects the specialised instantiation
+  bool std_scene = sc.n_spheres == 2 && sc.n_planes == 5;
+  for (int i = 0; i < PM_MAX_PLANES; i++) std_scene = std_scene && sc.pl_axis[i] == std_axis(i);
+#ifdef PM_NO_STD_SCENE
+  std_scene = false;
+#endif
+  auto kernel = rec ? (std_scene ? trace_kernel<true, true> : trace_kernel<true, false>)
+                    : (std_scene ? trace_kernel<false, true> : trace_kernel<false, false>);
   *err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSurfaceSmem);
   if (*err != cudaSuccess) return 0;
   const int cta_warps = kSurfaceThreads / 32;
