@@ -104,6 +104,7 @@ def lib():
             "pm_group_frame_host_async": (i32, [vp, f32, b, b, b, i32, i32, vp, C.POINTER(C.c_int64)]),
             "pm_group_frame_wait": (i32, [vp, C.c_int64]),
             "pm_trace_profile": (i32, [vp, b]), "pm_get_trace_profile_host": (i32, [vp, vp, i64, C.POINTER(i64)]),
+            "pm_selftest_fdiv": (i32, [vp, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
             "launch_init_random_numbers_kernel": (None, []),
             "launch_emit_photons_kernel": (None, [vp, C.c_uint, C.c_uint, f32, b, b]),
             "launch_photon_mapping_kernel": (None, [vp, C.c_uint, C.c_uint, f32, b, b]),
@@ -439,6 +440,12 @@ class PhotonMapper:
         n = C.c_int64()
         self._ck(self.L.pm_get_trace_profile_host(self.h, _ptr(out), out.size, C.byref(n)))
         return out[:n.value].reshape(-1, 48)
+
+    def selftest_fdiv(self, pairs, seed=1):
+        """(violations, accepted): the trace kernel's branch-free wall division against the IEEE one (see pmb200.h)."""
+        bad, acc = C.c_uint64(), C.c_uint64()
+        self._ck(self.L.pm_selftest_fdiv(self.h, pairs, seed, C.byref(bad), C.byref(acc)))
+        return bad.value, acc.value
 
 
 class PhotonGroup:

@@ -229,6 +229,7 @@ int pm_set_photon_count(pm_context *c, int64_t n) {
   }
   // the reference's table is zero-initialised device memory until launch_init_random_numbers_kernel runs
   CK(c, cudaMemsetAsync(c->d_table, 0, sizeof(float4) * (size_t)n, c->stream));
+  CK(c, launch_table_norm(c->d_table, n, c->stream));   // w = 1/|(0,0,0)| = inf: a zero row still normalises to NaN
   c->n_photons = n; c->first = 0; c->last = n;
   c->table_first = 0; c->table_last = n;   // zero rows are valid rows (the reference's uninitialised table)
   return PM_OK;
@@ -285,6 +286,7 @@ int pm_set_random_table_host(pm_context *c, const float *xyz, int64_t n) {
   std::vector<float4> rows((size_t)n);
   for (int64_t i = 0; i < n; i++) rows[i] = make_float4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], 0.0f);
   CK(c, cudaMemcpyAsync(c->d_table, rows.data(), sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  CK(c, launch_table_norm(c->d_table, n, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));
   c->table_first = 0; c->table_last = n;
   return PM_OK;
@@ -435,6 +437,22 @@ int pm_get_trace_profile_host(pm_context *c, uint64_t *out, int64_t max_words, i
   CK(c, cudaSetDevice(c->device));
   CK(c, cudaStreamSynchronize(c->stream));
   CK(c, cudaMemcpy(out, c->d_trace_dbg, sizeof(unsigned long long) * (size_t)*words, cudaMemcpyDeviceToHost));
+  return PM_OK;
+}
+
+int pm_selftest_fdiv(pm_context *c, uint64_t pairs, uint32_t seed, uint64_t *violations, uint64_t *accepted) {
+  ARG(c, c && violations && accepted, "null argument");
+  CK(c, cudaSetDevice(c->device));
+  unsigned long long *d = nullptr, h[4] = {0, 0, 0, 0};
+  CK(c, cudaMalloc(&d, sizeof(h)));
+  cudaError_t e = cudaMemsetAsync(d, 0, sizeof(h), c->stream);
+  if (e == cudaSuccess) e = launch_selftest_fdiv(pairs, seed, d, c->num_sms, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(d);
+  CK(c, e);
+  *violations = h[0]; *accepted = h[1];
+  if (h[0]) { static char msg[96]; snprintf(msg, sizeof(msg), "fdiv_fastpath differs, e.g. a = 0x%08llx, b = 0x%08llx", h[2], h[3]); c->err = msg; }
   return PM_OK;
 }
 

@@ -19,6 +19,8 @@ inline uint32_t host_powmod(uint32_t a, unsigned long long e, uint32_t m) {
 // pm_trace.cu
 cudaError_t launch_mwc_table(float4 *table, long long first, long long last, long long n, uint32_t w0, uint32_t z0, const MwcJump *J, cudaStream_t st);
 cudaError_t launch_philox_table(float4 *table, long long n, unsigned long long seed, cudaStream_t st);
+cudaError_t launch_selftest_fdiv(unsigned long long n, uint32_t seed, unsigned long long *out, int num_sms, cudaStream_t st);
+cudaError_t launch_table_norm(float4 *table, long long n, cudaStream_t st);   // w = 1/sqrt(x*x+y*y+z*z) of rows [0, n)
 // each returns the number of kernels launched; *err receives the CUDA status
 int launch_trace_volume(const DeviceScene &sc, const float4 *table, long long first, long long last, unsigned flags, uint32_t w0,
                         uint32_t z0, const MwcJump *J, unsigned long long *acc, uint32_t *vol_cnt, float4 *rec_pos, float4 *rec_pow,

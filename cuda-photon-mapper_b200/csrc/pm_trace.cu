@@ -27,6 +27,19 @@ namespace pm {
 // ------------------------------------------------------------------------------------------------------
 // Rows [first, last) are generated, plus rows 0..2 (every photon's medium walk reads them, PMK:1258): a rank of a
 // multi-GPU job only needs its own photon range.
+// A table row carries w = 1 / sqrt(x*x + y*y + z*z), the factor of normalize(): emitPhotons normalises the same row in every frame
+// (PMK:1229, :1242), so the two IEEE operations are done once when the row is written and the walks multiply (bit-identical).
+__device__ __forceinline__ float4 table_row(float x, float y, float z) {
+  return make_float4(x, y, z, rcp_rn(__fsqrt_rn(dot(V(x, y, z), V(x, y, z)))));
+}
+__device__ __forceinline__ v3 table_direction(float4 td) {
+#ifdef PM_NO_TABLE_W
+  return normalize(V(td.x, td.y, td.z));
+#else
+  return mul(V(td.x, td.y, td.z), td.w);
+#endif
+}
+
 __global__ void __launch_bounds__(256) mwc_table_kernel(float4 *__restrict__ table, long long first, long long last, long long n, uint32_t w0,
                                                         uint32_t z0, const MwcJump *__restrict__ J) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -37,7 +50,7 @@ __global__ void __launch_bounds__(256) mwc_table_kernel(float4 *__restrict__ tab
   s.z = mwc_jump(J, 0, z0, steps);
   s.w = mwc_jump(J, 1, w0, steps);
   float x = rand_float(s, 1.0f), y = rand_float(s, 1.0f), z = rand_float(s, 1.0f);
-  table[i] = make_float4(x, y, z, 0.0f);
+  table[i] = table_row(x, y, z);
 }
 
 // Philox4x32-10 (Random123) table: row i = the reference's randFloat(1.0) mapping of the first three words of
@@ -54,7 +67,16 @@ __global__ void __launch_bounds__(256) philox_table_kernel(float4 *__restrict__ 
     k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
   }
   auto unit = [](uint32_t u) { float rnd = div65535((float)((int)u)); rnd = rnd * 2.0f * 1.0f; return rnd - 1.0f; };
-  table[i] = make_float4(unit(c0), unit(c1), unit(c2), 0.0f);
+  table[i] = table_row(unit(c0), unit(c1), unit(c2));
+}
+
+// w of rows [0, n) from their (x, y, z): after the table was cleared (the reference's zero-initialised table: w = 1/0 = inf, so that
+// the direction is 0 * inf = NaN like normalize(0)) or uploaded by the host
+__global__ void __launch_bounds__(256) table_norm_kernel(float4 *__restrict__ table, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 t = table[i];
+  table[i] = table_row(t.x, t.y, t.z);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -123,7 +145,7 @@ __device__ __forceinline__ VolumeCtx volume_ctx(const DeviceScene &sc, const flo
 }
 __device__ __forceinline__ void volume_photon(const VolumeCtx &c, const Sink &sk, float4 td, long long gi, Mwc s) {
   v3 rgb = V(10.0f, 10.0f, 10.0f);
-  v3 ray = normalize(V(td.x, td.y, td.z));
+  v3 ray = table_direction(td);
   v3 prev = c.light;
 #pragma unroll
   for (int i = 0; i < 3; i++) {
@@ -388,7 +410,7 @@ __global__ void __launch_bounds__(kSurfaceThreads, 1) trace_kernel(const __grid_
       if (state == ST_IDLE && cand < end) {
         index = (int)cand;
         const float4 td = __ldg(table + cand);
-        ray = normalize(V(td.x, td.y, td.z));
+        ray = table_direction(td);
         rgb = media ? V(7.0f, 7.0f, 7.0f) : V(10.0f, 10.0f, 10.0f);   // the medium walk leaves rgb = 10-1-1-1
         if (index < 100) {   // CAUSTICS_PHOTONS: aimed at the glass sphere, jittered, not re-normalised
           v3 aim = normalize(sub(V(sc.sph[0][0], sc.sph[0][1], sc.sph[0][2]), light));
@@ -516,12 +538,52 @@ __global__ void __launch_bounds__(kSurfaceThreads, 1) trace_kernel(const __grid_
 }
 
 // ------------------------------------------------------------------------------------------------------
+// self-test of fdiv_fastpath (pm_math.cuh) against the IEEE division, on the operand domain ray_walls_std argues about:
+// numerator 0 or 2^-34 <= |a| <= 2^21, |b| < 4 (log-uniform over that exponent range, zeros and denormals included) or inf / NaN.
+// Claim checked per pair: if the IEEE quotient would be accepted by checkDistance (0 < q < 999999.9) the fast path returns the same
+// bits; otherwise the fast path's value is rejected too.  out[0] = pairs violating the claim, out[1] = pairs with an accepted quotient, out[2..3] = operand bits of one violating pair.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mix32(uint32_t x) { x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16; return x; }
+__global__ void __launch_bounds__(256) selftest_fdiv_kernel(unsigned long long n, uint32_t seed, unsigned long long *out) {
+  unsigned long long bad = 0, acc = 0;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint32_t h0 = mix32((uint32_t)i ^ seed), h1 = mix32(h0 + (uint32_t)(i >> 32) + 0x9e3779b9u), h2 = mix32(h1 ^ 0x85ebca6bu);
+    // a: sign, exponent 2^-34 .. 2^21 (biased 93 .. 148), random mantissa; one in 64 is zero, one in 1024 NaN
+    uint32_t abits = (h0 & 0x80000000u) | ((93u + (h0 >> 8) % 56u) << 23) | (h1 & 0x7fffffu);
+    if ((h2 & 63u) == 0u) abits &= 0x80000000u;
+    if ((h2 & 1023u) == 1u) abits = 0x7fc00000u;
+    // b: half of the pairs put b where the quotient lands in (2^-12, 2^22) -- the accepted range and its edges --, the others anywhere
+    uint32_t bbits;
+    if (h2 & 0x40000000u) {
+      const int ea = (int)((abits >> 23) & 255u), eb = ea - ((int)((h2 >> 10) % 34u) - 12);
+      bbits = (h1 & 0x80000000u) | ((uint32_t)(eb < 0 ? 0 : eb) << 23) | (h2 >> 9 & 0x7fffffu ^ (h0 >> 3 & 0x7fffffu));
+    } else {
+      bbits = mix32(h2 + 0x632be59bu);
+    }
+    // b is a component of a (nearly) unit vector or garbage: |b| < 4, or inf / NaN
+    if ((bbits >> 23 & 255u) > 128u && (bbits >> 23 & 255u) != 255u) bbits = (bbits & 0x807fffffu) | ((bbits >> 23 & 255u) % 129u) << 23;
+    const float a = __uint_as_float(abits), b = __uint_as_float(bbits);
+    const float q = __fdiv_rn(a, b), f = fdiv_fastpath(a, b);
+    const bool q_ok = q > 0.0f && q < 999999.9f, f_ok = f > 0.0f && f < 999999.9f;
+    acc += q_ok ? 1 : 0;
+    if (q_ok ? (__float_as_uint(q) != __float_as_uint(f)) : f_ok) { bad++; out[2] = abits; out[3] = bbits; }
+  }
+  if (bad) atomicAdd(out + 0, bad);
+  if (acc) atomicAdd(out + 1, acc);
+}
+cudaError_t launch_selftest_fdiv(unsigned long long n, uint32_t seed, unsigned long long *out, int num_sms, cudaStream_t st) {
+  selftest_fdiv_kernel<<<num_sms * 8, 256, 0, st>>>(n, seed, out);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------------
 cudaError_t preload_trace_kernels() {
   cudaFuncAttributes fa;
   cudaError_t e = cudaFuncGetAttributes(&fa, mwc_table_kernel);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, philox_table_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, table_norm_kernel);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, volume_kernel);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, fold_volume_kernel);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, trace_kernel<false, false>);
@@ -537,6 +599,12 @@ cudaError_t launch_mwc_table(float4 *table, long long first, long long last, lon
   if (n <= 0) return cudaSuccess;
   unsigned blocks = (unsigned)((threads + 255) / 256);
   mwc_table_kernel<<<blocks, 256, 0, st>>>(table, first, last, n, w0, z0, J);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_table_norm(float4 *table, long long n, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  table_norm_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(table, n);
   return cudaGetLastError();
 }
 
@@ -599,6 +667,7 @@ int launch_trace(const DeviceScene &sc, const float4 *table, long long first, lo
   // the reference's object layout (only the layout: offsets, centres and radii stay scene data) selects the specialised instantiation
   bool std_scene = sc.n_spheres == 2 && sc.n_planes == 5;
   for (int i = 0; i < PM_MAX_PLANES; i++) std_scene = std_scene && sc.pl_axis[i] == std_axis(i);
+  std_scene = std_scene && std_walls_ok(sc.pl_off);   // the branch-free wall test's range conditions (pm_math.cuh ray_walls_std)
 #ifdef PM_NO_STD_SCENE
   std_scene = false;
 #endif

@@ -275,6 +275,10 @@ int         pm_get_timings(pm_context *ctx, double *total_ms, int64_t *launches)
  * [1] shared accumulators zeroed, [2] every warp out of photons, [3] accumulators flushed, [8+w] warp w out of photons */
 int         pm_trace_profile(pm_context *ctx, bool on);
 int         pm_get_trace_profile_host(pm_context *ctx, uint64_t *host_out, int64_t max_words, int64_t *words);
+/* self-test of the trace kernel's branch-free wall division (csrc/pm_math.cuh fdiv_fastpath) against the IEEE division on `pairs`
+ * pseudo-random operand pairs of the domain the kernel argues about: *violations = pairs where an acceptable quotient
+ * (0 < q < 999999.9) differs in any bit, or a rejected one comes out acceptable; *accepted = pairs with an acceptable quotient */
+int         pm_selftest_fdiv(pm_context *ctx, uint64_t pairs, uint32_t seed, uint64_t *violations, uint64_t *accepted);
 
 #ifdef __cplusplus
 }

@@ -45,7 +45,7 @@ def test_mwc_table_bit_exact(pm, oracle):
 
 @pytest.mark.parametrize("media", [False, True])
 @pytest.mark.parametrize("t", [0.0, 0.7])
-@pytest.mark.parametrize("scene_name", ["default", "cfg1", "backwall5", "smoke"])
+@pytest.mark.parametrize("scene_name", ["default", "cfg1", "backwall5", "smoke", "shifted", "light_outside", "narrow"])
 def test_trace_records_and_map(pm, oracle, media, t, scene_name):
     """Stage 1: photon records bit-exact (position, direction, power, object ids, order), photon map within MAP_TOL."""
     n = 20000
@@ -58,6 +58,18 @@ def test_trace_records_and_map(pm, oracle, media, t, scene_name):
         osc.planes[4][1] = 5.0
     elif scene_name == "smoke":
         osc.n_spheres = 3      # spheres[2], the large smoke sphere of the reference's screenshots (PMK:65)
+    elif scene_name == "shifted":
+        # asymmetric wall offsets: still the reference's object layout, so the trace kernel's branch-free one-division-per-axis wall test
+        # (pm_math.cuh ray_walls_std) runs on offsets other than +-1.5 / 6
+        for i, off in enumerate((1.2, -1.1, -1.7, 1.6, 5.5)):
+            osc.planes[i][1] = off
+    elif scene_name == "light_outside":
+        # the light beyond the x = +1.5 wall: primary rays see BOTH x walls in front (the nearer one must win), some start on no side
+        osc.light[0] = 2.5
+    elif scene_name == "narrow":
+        # x walls 0.8 apart: fails the separation condition of ray_walls_std, so the generic per-wall instantiation must be selected
+        osc.planes[0][1] = 0.4
+        osc.planes[2][1] = -0.4
     m = _mapper(pm, n, copy_scene(pm.Scene, osc))
     m.init_random_numbers()
     table, st = oracle.mwc_table(n)
@@ -378,3 +390,14 @@ def test_older_variant_launchers(pm):
     before = pos.clone()
     pm.launch_kernel(pos, w, h, 0.0)
     assert torch.equal(pos, before)
+
+
+def test_fast_path_division_selftest(pm):
+    """The trace kernel divides by the ray component without the compiler's range check (pm_math.cuh fdiv_fastpath).  On 2^32
+    operand pairs of the domain it argues about: every quotient checkDistance would accept is bit-identical to the IEEE division,
+    every other one is rejected as well."""
+    m = _mapper(pm, 16)
+    bad, acc = m.selftest_fdiv(1 << 32, seed=12345)
+    assert bad == 0, m.L.pm_last_error(m.h).decode()
+    assert acc > (1 << 28)      # the accepted range is well covered
+    m.close()
