@@ -268,12 +268,13 @@ __global__ void __launch_bounds__(256) fold_volume_kernel(uint32_t *__restrict__
 struct SmemAcc {
   uint32_t *lo, *hi;
   uint32_t *shadow;   // per wall texel: number of shadow photons (each deposits exactly -0.25 grey), folded in at the flush
-  __device__ __forceinline__ void add(int e, long long v) {
-    if (v == 0) return;
-    uint32_t vlo = (uint32_t)v, vhi = (uint32_t)((unsigned long long)v >> 32);
-    uint32_t old = atomicAdd(lo + e, vlo);
-    uint32_t h = vhi + ((uint32_t)(old + vlo) < old ? 1u : 0u);   // carry out of the low half, counted exactly once
-    if (h) atomicAdd(hi + e, h);
+  // A surface deposit is one of 5 * {1, 0} / sqrt(bounces) or 10 (PMK:1296-1298; the shadow photons' -0.25 is counted): 0 <= e <= 10,
+  // so e * 2^24 fits the low half and only the carry reaches the high half.
+  __device__ __forceinline__ void add(int e, float energy) {
+    const uint32_t v = __float2uint_rn(energy * (float)kHitScale);
+    if (v == 0u) return;
+    const uint32_t old = atomicAdd(lo + e, v);
+    if ((uint32_t)(old + v) < old) atomicAdd(hi + e, 1u);   // carry out of the low half, counted exactly once
   }
 };
 
@@ -324,11 +325,11 @@ __device__ __forceinline__ void store_photon(const Sink &sk, SmemAcc &sa, int ty
   if (on_slab == 1) {   // the common case: keyed energy sum, the 6x6 stencil is applied once per voxel in pm_map.cu
     int en = ((id * PM_GRID_N + a) * PM_GRID_N + b) * 4;
     if (shadow) atomicAdd(sa.shadow + (en >> 2), 1u);   // half of all deposits: one 32-bit count instead of a 64-bit add with carry
-    else if (e.x == e.y && e.y == e.z) sa.add(en + 3, __float2ll_rn(e.x * (float)kHitScale));
+    else if (e.x == e.y && e.y == e.z) sa.add(en + 3, e.x);
     else {
-      sa.add(en + 0, __float2ll_rn(e.x * (float)kHitScale));
-      sa.add(en + 1, __float2ll_rn(e.y * (float)kHitScale));
-      sa.add(en + 2, __float2ll_rn(e.z * (float)kHitScale));
+      sa.add(en + 0, e.x);
+      sa.add(en + 1, e.y);
+      sa.add(en + 2, e.z);
     }
     return;
   }
@@ -512,7 +513,21 @@ __global__ void __launch_bounds__(kSurfaceThreads, 1) trace_kernel(const __grid_
         const float wd = comp(prev, wax) - sc.pl_off[h.type == 1 ? h.idx : 0];
         const float wdd = wd * wd;
         if (h.type == 1 && wax >= 0 && wax <= 2 && (wdd == 0.0f || wdd != wdd)) { state = ST_IDLE; continue; }
-        ray = reflect3<kStd>(sc, ray, prev, h.type, h.idx, P);
+        if (kStd) {
+          // planeNormal + reflect3 (PMK:196-209, :664-668) for an axis-aligned wall, scalar: the normal is (0, .., wd / |wd|, .., 0) --
+          // sqrt(RN(wd * wd)) == |wd| in binary floating point when the square neither under- nor overflows (2^-34 <= |wd| <= ~1e6 under
+          // std_walls_ok) --, its two zero components contribute +-0 to the dot product (ray[axis] != 0: the ray has just hit this wall)
+          // and (+0) * k to the subtraction, which is kept because it turns a -0 ray component into +0 when k < 0
+          const float na = wd * rcp_rn(fabsf(wd));
+          const float ra = comp(ray, wax);
+          const float k = 2.0f * (ra * na);
+          const float z = 0.0f * k;
+          v3 rr = V(ray.x - z, ray.y - z, ray.z - z);
+          set_comp(rr, wax, ra - na * k);
+          ray = normalize(rr);
+        } else {
+          ray = reflect3<kStd>(sc, ray, prev, h.type, h.idx, P);
+        }
         org = P;
         caustics = false; new_point = true; bounces++;
         state = ST_PRIMARY;
@@ -540,6 +555,7 @@ __global__ void __launch_bounds__(kSurfaceThreads, 1) trace_kernel(const __grid_
 // ------------------------------------------------------------------------------------------------------
 // self-test of fdiv_fastpath (pm_math.cuh) against the IEEE division, on the operand domain ray_walls_std argues about:
 // numerator 0 or 2^-34 <= |a| <= 2^21, |b| < 4 (log-uniform over that exponent range, zeros and denormals included) or inf / NaN.
+// (Each numerator also checks sqrt(RN(a * a)) == |a|, the identity behind the scalar wall normal of trace_kernel.)
 // Claim checked per pair: if the IEEE quotient would be accepted by checkDistance (0 < q < 999999.9) the fast path returns the same
 // bits; otherwise the fast path's value is rejected too.  out[0] = pairs violating the claim, out[1] = pairs with an accepted quotient, out[2..3] = operand bits of one violating pair.
 // ------------------------------------------------------------------------------------------------------
@@ -566,6 +582,7 @@ __global__ void __launch_bounds__(256) selftest_fdiv_kernel(unsigned long long n
     const float q = __fdiv_rn(a, b), f = fdiv_fastpath(a, b);
     const bool q_ok = q > 0.0f && q < 999999.9f, f_ok = f > 0.0f && f < 999999.9f;
     acc += q_ok ? 1 : 0;
+    if (a == a && __float_as_uint(__fsqrt_rn(a * a)) != (abits & 0x7fffffffu)) { bad++; out[2] = abits; out[3] = abits; }   // the wall normal's identity
     if (q_ok ? (__float_as_uint(q) != __float_as_uint(f)) : f_ok) { bad++; out[2] = abits; out[3] = bbits; }
   }
   if (bad) atomicAdd(out + 0, bad);

@@ -112,7 +112,7 @@ int pm_get_mwc_state(const pm_context *ctx, uint32_t *w, uint32_t *z);
                                   warp-specialised one (same results; kept for measurement and as a cross-check) */
 int pm_clear_map(pm_context *ctx);                                 /* init_photons_kernel, PMK:1503-1521 */
 int pm_trace(pm_context *ctx, float animTime, unsigned flags);
-/* tuning: how many of a CTA's 32 warps run the medium walk in the fused trace kernel (default 6; 1..16) */
+/* tuning: how many of a CTA's 32 warps run the medium walk in the fused trace kernel (default 7; 1..16) */
 int pm_set_volume_warps(pm_context *ctx, int warps);
 /* tuning: CTAs of the persistent trace kernel (default 0 = one per SM).  Fewer leaves SMs free for the previous frame's exchange +
  * map build + render, which the pipelined frame calls run on a second stream (worth it when those are a large part of the frame,

@@ -9,6 +9,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "--one":
     m = pmb200.PhotonMapper(n_photons=16777216)
     m.set_stream(torch.cuda.current_stream().cuda_stream)
     m.init_random_numbers()
+    if os.environ.get("AB_VOL_WARPS"): m.set_volume_warps(int(os.environ["AB_VOL_WARPS"]))
     def t(fn, reps=20):
         for _ in range(3): fn()
         torch.cuda.synchronize()
