@@ -132,6 +132,8 @@ struct VolumeCtx {
   v3 light;
   long long first;     // first photon of the launch (record slots are relative to it)
   bool rec;
+  bool fast;           // volume_photon_fast may be used (see there)
+  float g0, g1;        // its lower bounds on |r'|^2 for the draws scaled by t0 / t1: 4096 |t|^2
 };
 __device__ __forceinline__ VolumeCtx volume_ctx(const DeviceScene &sc, const float4 *__restrict__ table, long long first, unsigned flags,
                                                 int replica, const Sink &sk) {
@@ -141,6 +143,21 @@ __device__ __forceinline__ VolumeCtx volume_ctx(const DeviceScene &sc, const flo
   c.light = V(sc.light[0], sc.light[1], sc.light[2]);
   c.first = first;
   c.rec = (flags & PM_TRACE_RECORDS) != 0;
+  // preconditions of volume_photon_fast's error bounds: finite scale factors that cannot overflow (table rows are 2 u / 65535 - 1 with a
+  // 32-bit u, PMK:1039-1052: up to 65537 in magnitude), the light within 4.9 of the origin (so every deposit point has |coordinate| < 8),
+  // and only counts are wanted
+  bool ok = sk.acc != nullptr && !c.rec && !(flags & PM_TRACE_EXACT_MEDIUM);
+  const float t[6] = {c.t0.x, c.t0.y, c.t0.z, c.t1.x, c.t1.y, c.t1.z};
+#pragma unroll
+  for (int i = 0; i < 6; i++) ok = ok && fabsf(t[i]) <= 1.0e9f;
+  ok = ok && fabsf(c.light.x) < 4.9f && fabsf(c.light.y) < 4.9f && fabsf(c.light.z) < 4.9f;
+  c.g0 = 4096.0f * (t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
+  c.g1 = 4096.0f * (t[3] * t[3] + t[4] * t[4] + t[5] * t[5]);
+  ok = ok && c.g0 > 0.0f && c.g1 > 0.0f;
+#ifdef PM_NO_FAST_VOLUME
+  ok = false;
+#endif
+  c.fast = ok;
   return c;
 }
 __device__ __forceinline__ void volume_photon(const VolumeCtx &c, const Sink &sk, float4 td, long long gi, Mwc s) {
@@ -173,6 +190,63 @@ __device__ __forceinline__ void volume_photon(const VolumeCtx &c, const Sink &sk
   }
 }
 
+// The same photon when only the deposit COUNTS are wanted (Mode A): a floating-point filter.  The voxel of a deposit point does not
+// depend on the last bits of the point unless it lies next to a voxel boundary, so steps 1 and 2 are computed with approximate
+// arithmetic (one multiply for x / 65535, fused multiply-adds, MUFU.RSQ for the normalisation: ~70 instead of ~100 instructions per
+// step) and a photon whose approximate point comes within kVolEps of a boundary, in voxel units, in any coordinate is redone by the
+// exact routine above.  Step 0 (light + table direction) is exact as it is.  Error budget, with |light| < 4.9 (VolumeCtx::fast) and
+// |r'|^2 >= 4096 |m|^2 (checked per step; r = the random vector, r_j = 2 q_j m_j - m_j with |q_j| <= 32768.5 and m = the step's
+// scale row, so |r| ~ 1e4 |m| and the check fails about once in 1e11 draws; ' = approximate):
+//   * r'_j vs r_j: x / 65535 by one multiply is 3 * 2^-24 relative off the rounded quotient, the fused 2 q m - m saves roundings:
+//     |r'_j - r_j| <= 2^-21 (|r_j| + |m_j|), so |r' - r| <= 2^-21 (1 + 1/64) |r|;
+//   * direction: the exact chain (dot, sqrt, 1 / x, multiply) is within 4.5 * 2^-24 of r / |r|, the approximate one (rsqrt.approx:
+//     2 ulp) within 6.5 * 2^-24 of r' / |r'|, and |r' / |r'| - r / |r|| <= 2 |r' - r| / |r|: per component <= 27.3 * 2^-24 = 1.63e-6;
+//   * point: each step adds that plus two roundings of a coordinate below 8 (2 * 2^-24 * 8): 2.6e-6 after step 1, 5.2e-6 after step 2;
+//   * voxel coordinate m = (32 p + 48) / 3 (or 16 p / 3): 10.67 * 5.2e-6 + the evaluation of m' itself (6e-6) = 6.2e-5 < kVolEps = 2^-13.
+// If m' is farther than that from every integer, floor(m') is the exact voxel (pm_math.cuh: voxel = clamp(floor(m))); the one input
+// range where the reference's double arithmetic deviates from that formula, p in [-2^-53, 0), sits 1e-15 from a boundary and falls
+// back like the rest.  ~1.5e-3 of the photons take the fallback.  Checked end to end: the accumulators of a Mode A trace are compared
+// bit for bit with those of the exact (records) trace at 16M photons (tests/test_gpu_fullsize.py).
+#ifndef PM_VOL_EPS
+#define PM_VOL_EPS 0x1p-13f
+#endif
+constexpr float kVolEps = PM_VOL_EPS;
+__device__ __forceinline__ int fast_voxel(float p, float scale, float bias, bool &amb) {
+  const float m = __fmaf_rn(p, scale, bias);
+  const float f = floorf(m);
+  const float d = m - f;
+  amb = amb | (d < kVolEps) | (d > 1.0f - kVolEps);
+  const int k = (int)f;
+  return k < 0 ? 0 : (k < PM_GRID_N ? k : PM_GRID_N - 1);
+}
+// returns false when the photon has to be redone by volume_photon (nothing was deposited)
+__device__ __forceinline__ bool volume_photon_fast(const VolumeCtx &c, float4 td, Mwc s) {
+  bool amb = !(td.w > 0.0f && td.w < 3.0e38f);   // a zero / non-finite row: NaN directions, the exact routine knows what the reference does
+  const v3 P0 = add(table_direction(td), c.light);
+  int idx[3];
+  idx[0] = (voxel_x_clamped(P0.x) * PM_GRID_N + voxel_x_clamped(P0.y)) * PM_GRID_N + voxel_z_clamped(P0.z);
+  v3 P = P0;
+#pragma unroll
+  for (int i = 1; i < 3; i++) {
+    const float4 tr = i == 1 ? c.t0 : c.t1;   // the draws after deposit i - 1 are scaled by row i - 1
+    const float c65535 = 1.0f / 65535.0f;
+    const float qx = (float)((int)mwc_next(s)) * c65535, qy = (float)((int)mwc_next(s)) * c65535, qz = (float)((int)mwc_next(s)) * c65535;
+    const float rx = __fmaf_rn(qx, 2.0f * tr.x, -tr.x), ry = __fmaf_rn(qy, 2.0f * tr.y, -tr.y), rz = __fmaf_rn(qz, 2.0f * tr.z, -tr.z);
+    const float dd = __fmaf_rn(rz, rz, __fmaf_rn(ry, ry, rx * rx));
+    amb = amb | !(dd >= (i == 1 ? c.g0 : c.g1));
+    float inv;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(dd));
+    P = V(__fmaf_rn(rx, inv, P.x), __fmaf_rn(ry, inv, P.y), __fmaf_rn(rz, inv, P.z));
+    const int vx = fast_voxel(P.x, 32.0f / 3.0f, 16.0f, amb), vy = fast_voxel(P.y, 32.0f / 3.0f, 16.0f, amb);
+    const int vz = fast_voxel(P.z, 16.0f / 3.0f, 0.0f, amb);
+    idx[i] = (vx * PM_GRID_N + vy) * PM_GRID_N + vz;
+  }
+  if (amb) return false;
+#pragma unroll
+  for (int i = 0; i < 3; i++) atomicAdd(c.cnt + i * PM_GRID_VOXELS + idx[i], 1u);
+  return true;
+}
+
 // One thread's share of the medium walk, strided: photons gi, gi + stride, ... < last.  cw, cz = a^(9*stride) mod m.
 __device__ __forceinline__ void volume_walk(const DeviceScene &sc, const float4 *__restrict__ table, long long first, long long gi,
                                             long long last, long long stride, unsigned flags, uint32_t w0, uint32_t z0,
@@ -186,7 +260,7 @@ __device__ __forceinline__ void volume_walk(const DeviceScene &sc, const float4 
   for (; gi < last; gi += stride) {
     const float4 td = td_next;
     if (gi + stride < last) td_next = __ldg(table + gi + stride);   // next row in flight under this photon's walk
-    volume_photon(c, sk, td, gi, base);
+    if (!(c.fast && volume_photon_fast(c, td, base))) volume_photon(c, sk, td, gi, base);
     base.z = mulmod(base.z, cz, mwc_modulus(0));
     base.w = mulmod(base.w, cw, mwc_modulus(1));
   }
@@ -224,7 +298,7 @@ __device__ __forceinline__ void volume_walk_sliced(const DeviceScene &sc, const 
     gi = cta_first + s * per + b * 32 + lane;
     valid = b * 32 + lane < per && gi < cta_last;
     if (valid) td_next = __ldg(table + gi);   // in flight under this photon's walk
-    if (valid_now) volume_photon(c, sk, td, gi_now, base);
+    if (valid_now && !(c.fast && volume_photon_fast(c, td, base))) volume_photon(c, sk, td, gi_now, base);
     base.z = mulmod(base.z, wrap ? jump.wz : jump.fz, mwc_modulus(0));
     base.w = mulmod(base.w, wrap ? jump.ww : jump.fw, mwc_modulus(1));
   }

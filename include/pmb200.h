@@ -110,9 +110,12 @@ int pm_get_mwc_state(const pm_context *ctx, uint32_t *w, uint32_t *z);
 #define PM_TRACE_NO_MAP   4u   /* skip the voxel-map accumulation (records only) */
 #define PM_TRACE_SPLIT    8u   /* run the medium walk and the surface walk as two launches instead of the fused,
                                   warp-specialised one (same results; kept for measurement and as a cross-check) */
+#define PM_TRACE_EXACT_MEDIUM 16u /* medium walk: every deposit point with the reference's exact arithmetic.  By default a Mode A trace
+                                  (counts only) computes steps 1-2 approximately and redoes, exactly, the photons that come near a voxel
+                                  boundary (csrc/pm_trace.cu volume_photon_fast) -- same counts; kept as the cross-check */
 int pm_clear_map(pm_context *ctx);                                 /* init_photons_kernel, PMK:1503-1521 */
 int pm_trace(pm_context *ctx, float animTime, unsigned flags);
-/* tuning: how many of a CTA's 32 warps run the medium walk in the fused trace kernel (default 7; 1..16) */
+/* tuning: how many of a CTA's 32 warps run the medium walk in the fused trace kernel (default 6; 1..16) */
 int pm_set_volume_warps(pm_context *ctx, int warps);
 /* tuning: CTAs of the persistent trace kernel (default 0 = one per SM).  Fewer leaves SMs free for the previous frame's exchange +
  * map build + render, which the pipelined frame calls run on a second stream (worth it when those are a large part of the frame,

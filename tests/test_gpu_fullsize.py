@@ -205,6 +205,33 @@ def test_mode_a_full_size_determinism_and_shard_invariance(pm):
     m.close()
 
 
+@pytest.mark.parametrize("t,light", [(0.0, None), (0.7, (0.3, -0.9, 2.5)), (0.0, (1.45, 1.45, 5.9))])
+def test_medium_walk_filter_gives_the_exact_counts_at_16M(pm, t, light):
+    """The Mode A medium walk computes deposit points approximately and redoes photons near a voxel boundary exactly
+    (csrc/pm_trace.cu volume_photon_fast).  Its accumulators must equal, bit for bit, those of the walk that evaluates every point with
+    the reference's arithmetic (PM_TRACE_EXACT_MEDIUM -- the routine the record tests pin to the oracle) on all 16M photons = 50M
+    deposits, for the default light and for lights that put the deposits elsewhere (the last one: a corner, most points clamp)."""
+    n = 16777216
+    m = pm.PhotonMapper(n_photons=n)
+    if light is not None:
+        sc = m.get_scene()
+        for i in range(3):
+            sc.light[i] = light[i]
+        m.set_scene(sc)
+    m.init_random_numbers()
+    st = m.get_mwc_state()
+    m.clear_map()
+    m.trace(t, media=True)
+    fast = m.get_accumulators()
+    m.set_mwc_state(*st)
+    m.clear_map()
+    m.trace(t, media=True, exact_medium=True)
+    exact = m.get_accumulators()
+    assert np.array_equal(fast, exact)
+    assert exact[pm.ACC_HIT_ENTRIES + 32 * 32 * 32 * 3:].sum() != 0
+    m.close()
+
+
 def test_mode_b_full_size_properties(pm, oracle):
     """4M photons (BASELINE config 3): sorted keys are sorted, the permutation is a bijection onto the kept records, and
     64 random k=100 queries agree bit-exactly with brute force over all 9.6M wall photons."""

@@ -401,3 +401,37 @@ def test_fast_path_division_selftest(pm):
     assert bad == 0, m.L.pm_last_error(m.h).decode()
     assert acc > (1 << 28)      # the accepted range is well covered
     m.close()
+
+
+@pytest.mark.parametrize("table", ["zeros", "wide", "tiny_scales", "with_nan", "huge_scales", "zero_scale_row", "mwc"])
+def test_medium_walk_filter_on_hostile_tables(pm, table):
+    """volume_photon_fast's preconditions are checked in the kernel: with a zero table (the reference's state before
+    launch_init_random_numbers_kernel), wide rows, tiny / huge / zero scale rows (rows 0..2 scale every photon's draws), or NaNs, the
+    default trace must still give the accumulators of the exact walk."""
+    n = 8192
+    rng = np.random.default_rng(7)
+    m = _mapper(pm, n)
+    if table == "mwc":
+        m.init_random_numbers()   # the reference's own table: entries up to 65537 in magnitude (randFloat, PMK:1039-1052)
+    elif table != "zeros":
+        tab = rng.uniform(-1.0, 1.0, (n, 3)).astype(np.float32)
+        if table == "huge_scales":
+            tab[:3] *= 1e12
+        elif table == "zero_scale_row":
+            tab[1] = 0.0
+            tab[0, 2] = 0.0
+        if table == "wide":
+            tab *= 50.0
+        elif table == "tiny_scales":
+            tab[:3] *= 1e-4
+        elif table == "with_nan":
+            tab[5::97, 1] = np.nan
+            tab[7::101] = 0.0
+        m.set_random_table(tab)
+    st = m.get_mwc_state()
+    m.clear_map(); m.trace(0.0, media=True)
+    fast = m.get_accumulators()
+    m.set_mwc_state(*st)
+    m.clear_map(); m.trace(0.0, media=True, exact_medium=True)
+    assert np.array_equal(fast, m.get_accumulators())
+    m.close()
