@@ -17,7 +17,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PMB200_LIB") or os.path.join(_HERE, "libpmb200.so")   # PMB200_LIB: development override
 
-PM_TRACE_MEDIA, PM_TRACE_RECORDS, PM_TRACE_NO_MAP, PM_TRACE_SPLIT, PM_TRACE_EXACT_MEDIUM = 1, 2, 4, 8, 16
+PM_TRACE_MEDIA, PM_TRACE_RECORDS, PM_TRACE_NO_MAP, PM_TRACE_SPLIT, PM_TRACE_EXACT_MEDIUM, PM_TRACE_ONE_PHASE = 1, 2, 4, 8, 16, 32
 GRID_N = 32
 ACC_HIT_ENTRIES = 5 * 32 * 32 * 4
 ACC_ENTRIES = ACC_HIT_ENTRIES + 32 * 32 * 32 * 3 + 32 * 32 * 32   # pm_layout.h: hit + vox rgb + grey
@@ -228,9 +228,10 @@ class PhotonMapper:
     def clear_map(self):
         self._ck(self.L.pm_clear_map(self.h))
 
-    def trace(self, t=0.0, media=False, records=False, no_map=False, split=False, exact_medium=False):
+    def trace(self, t=0.0, media=False, records=False, no_map=False, split=False, exact_medium=False, one_phase=False):
         flags = ((PM_TRACE_MEDIA if media else 0) | (PM_TRACE_RECORDS if records else 0) | (PM_TRACE_NO_MAP if no_map else 0)
-                 | (PM_TRACE_SPLIT if split else 0) | (PM_TRACE_EXACT_MEDIUM if exact_medium else 0))
+                 | (PM_TRACE_SPLIT if split else 0) | (PM_TRACE_EXACT_MEDIUM if exact_medium else 0)
+                 | (PM_TRACE_ONE_PHASE if one_phase else 0))
         self._ck(self.L.pm_trace(self.h, t, flags))
 
     def set_volume_warps(self, warps):

@@ -49,6 +49,51 @@ static void position_objects(pm_scene *sc, float t) {
   sc->spheres[1][2] = 3.5f;
 }
 
+// Terms of trace_kernel's two-phase surface walk (csrc/pm_trace.cu).
+//   light_s / light_C: raySphere's ray-independent terms for rays that start at the light, with the kernel's own FP32 operations
+//   (one subtraction per component; x*x + y*y + z*z summed left to right, then - r^2; this file is compiled without FMA contraction).
+//   shadow_need[w], bit i clear: a shadow ray (PMK:1185-1196) that continues a primary ray FROM THE LIGHT behind wall w cannot be
+//   credited with sphere i, so the kernel skips that raySphere.  Condition: the sphere lies on the light's side of the wall's plane
+//   with a margin m = 0.05, i.e. side * (c[axis] - offset) - R >= m.  Argument: the shadow ray starts within 2e-5 of the plane
+//   and moves away from it, so for t >= 0 it stays >= m - 2e-5 from every point of the sphere.  With s = c - o, t* = (s.r)/A:
+//     t* >= 0: the line's closest approach is on the far side, its distance to the centre >= R + m - 2e-5, so the true discriminant is
+//       <= -4A(2Rm + m^2) <= -0.03; the computed one differs by <= 3.3e-6 |s|^2 <= 0.0104 (|s| <= 56 here: t* >= 0 needs the hit point
+//       within |c - light| <= 27.8 of the light), so D <= 0 and raySphere returns without a candidate;
+//     t* < 0 and the computed s.r <= 0: B >= 0 and C > 0 (the origin is outside the sphere by >= m), so the root -B - sqrt(D) <= 0 is
+//       rejected by checkDistance whatever D is;
+//     t* < 0 but the computed s.r > 0: then |s.r| <= 1.8e-7 |s| |r|, which needs near-perpendicularity, i.e. again |s| <= 56, so the
+//       closest approach lies within 1e-5 of the origin and the first case applies.
+//   The bounds used: light, sphere centres and wall offsets within [-8, 8], 0.05 <= R <= 4.
+//   fast_ok: reference layout (2 spheres, 5 walls x,y,x,y,z, std_walls_ok), the bounds above, the light >= m from every wall plane and
+//   outside both spheres with light_C >= 0 (the kernel's rejection test for the primary ray needs raySphere's sign = -1).
+static void two_phase_terms(DeviceScene &d) {
+  const float m = 0.05f;
+  bool ok = d.n_spheres == 2 && d.n_planes == 5 && std_walls_ok(d.pl_off);
+  for (int w = 0; w < PM_MAX_PLANES; w++) ok = ok && d.pl_axis[w] == std_axis(w) && fabsf(d.pl_off[w]) <= 8.0f;
+  for (int j = 0; j < 3; j++) ok = ok && fabsf(d.light[j]) <= 8.0f;
+  for (int i = 0; i < 2; i++) {
+    volatile float s0 = d.sph[i][0] - d.light[0], s1 = d.sph[i][1] - d.light[1], s2 = d.sph[i][2] - d.light[2];
+    volatile float p0 = s0 * s0, p1 = s1 * s1, p2 = s2 * s2;
+    volatile float sum = p0 + p1;
+    sum = sum + p2;
+    d.light_s[i][0] = s0; d.light_s[i][1] = s1; d.light_s[i][2] = s2;
+    d.light_C[i] = sum - d.sph_r2[i];
+    ok = ok && d.light_C[i] >= 0.0f && d.sph[i][3] >= 0.05f && d.sph[i][3] <= 4.0f;
+    for (int j = 0; j < 3; j++) ok = ok && fabsf(d.sph[i][j]) <= 8.0f;
+  }
+  for (int w = 0; w < PM_MAX_PLANES; w++) {
+    d.shadow_need[w] = 3u;
+    if (!ok) continue;
+    const int a = d.pl_axis[w];
+    const float gap = d.light[a] - d.pl_off[w];
+    if (!(fabsf(gap) >= m)) { ok = false; continue; }
+    const float side = gap > 0.0f ? 1.0f : -1.0f;
+    for (int i = 0; i < 2; i++)
+      if (side * (d.sph[i][a] - d.pl_off[w]) - d.sph[i][3] >= m) d.shadow_need[w] &= ~(1u << i);
+  }
+  d.fast_ok = ok ? 1 : 0;
+}
+
 static DeviceScene make_device_scene(const pm_scene &in, float t) {
   pm_scene s = in;
   position_objects(&s, t);
@@ -63,6 +108,7 @@ static DeviceScene make_device_scene(const pm_scene &in, float t) {
   for (int i = 0; i < PM_MAX_PLANES; i++) { d.pl_axis[i] = (int)s.planes[i][0]; d.pl_off[i] = s.planes[i][1]; }
   for (int b = 0; b < 8; b++) d.inv_sqrt_bounce[b] = 1.0f / sqrtf((float)b);   // IEEE sqrt and division, as __fsqrt_rn / __fdiv_rn
   for (int j = 0; j < 3; j++) d.light[j] = s.light[j];
+  two_phase_terms(d);
   d.sz_img = (float)s.sz_img;
   d.cam_ox = s.cam_ox; d.cam_oy = s.cam_oy;
   return d;
@@ -124,6 +170,7 @@ int pm_create(pm_context **out, int device) {
   if ((e = cudaMalloc(&c->d_jump, sizeof(MwcJump))) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&c->d_rec_count, sizeof(unsigned long long))) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&c->d_vol_cnt, sizeof(uint32_t) * kVolCntEntries)) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&c->d_trace_queue, sizeof(uint32_t) * kTraceQueueWordsPerCta * (size_t)c->num_sms)) != cudaSuccess) return fail(e);
   if ((e = cudaMemset(c->d_vol_cnt, 0, sizeof(uint32_t) * kVolCntEntries)) != cudaSuccess) return fail(e);
   if ((e = cudaMemset(c->d_grid, 0, sizeof(float) * PM_GRID_FLOATS)) != cudaSuccess) return fail(e);
   if ((e = cudaMemset(c->d_rec_count, 0, sizeof(unsigned long long))) != cudaSuccess) return fail(e);
@@ -144,7 +191,7 @@ int pm_destroy(pm_context *c) {
   pm_peer_disconnect(c);
   cudaFree(c->d_table); cudaFree(c->d_xchg); cudaFree(c->d_acc_sum); cudaFree(c->d_vol_cnt); cudaFree(c->d_grid); cudaFree(c->d_vol); cudaFree(c->d_surf);
   cudaFree(c->d_jump); cudaFree(c->d_rec_pos); cudaFree(c->d_rec_pow); cudaFree(c->d_rec_dir); cudaFree(c->d_rec_count);
-  cudaFree(c->d_fb_u8); cudaFree(c->d_fb_f32); cudaFree(c->d_vrec_pos); cudaFree(c->d_vrec_pow); cudaFree(c->d_trace_dbg);
+  cudaFree(c->d_fb_u8); cudaFree(c->d_fb_f32); cudaFree(c->d_vrec_pos); cudaFree(c->d_vrec_pow); cudaFree(c->d_trace_dbg); cudaFree(c->d_trace_queue);
   for (int k = 0; k < pm_context::kFrameRing; k++) {
     cudaFree(c->d_fb_async[k]);
     if (c->ev_rendered[k]) cudaEventDestroy(c->ev_rendered[k]);
@@ -406,7 +453,7 @@ int pm_trace(pm_context *c, float t, unsigned flags) {
                                 (unsigned long long *)c->d_acc, c->d_vol_cnt, c->d_rec_pos, c->d_rec_pow, c->d_rec_dir, c->d_vrec_pos,
                                 c->d_vrec_pow, c->vrec_cap, c->d_rec_count, c->rec_cap,
                                 (c->trace_sms > 0 && c->trace_sms < c->num_sms) ? c->trace_sms : c->num_sms, c->stream, &terr, c->d_trace_dbg,
-                                (uint32_t *)(c->d_acc + kAccEntries));
+                                (uint32_t *)(c->d_acc + kAccEntries), c->d_trace_queue);
   }
   CK(c, terr);
   if (flags & PM_TRACE_MEDIA) {   // the medium scattering consumed 9 draws per photon of the WHOLE job

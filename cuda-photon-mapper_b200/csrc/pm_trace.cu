@@ -92,6 +92,7 @@ struct Sink {
   uint32_t *vol_cnt;             // kVolCntEntries deposit counters of the medium walk (volume_kernel only)
   uint32_t *vox_touched;         // set when anything lands in the acc_vox section (pm_layout.h ExchangeHeader), or nullptr
   unsigned long long *dbg;       // development aid (pm_trace_profile): kTraceDbgWords timestamps per CTA, or nullptr
+  uint32_t *queue;               // per-warp queues of the two-phase surface walk (kQueueWords words per warp), or nullptr
 };
 __device__ __forceinline__ unsigned long long global_ns() {
   unsigned long long t;
@@ -410,6 +411,28 @@ __device__ __forceinline__ void store_photon(const Sink &sk, SmemAcc &sa, int ty
   splat_offslab(sk, id, on_slab, vx, vy, vz, e);   // rare: the clamped voxel is off the wall's slab
 }
 
+// store_photon for phase F of the two-phase walk: the hit is on wall `id` of the reference's layout, and the deposit is either a shadow
+// photon or the first bounce's energy, which is one value `v` (fixed point) in one channel `ch` of the wall texel (green wall: g,
+// red wall: r, white walls: the grey plane).  Same voxel, same slab test, same accumulator entries as store_photon.
+__device__ __forceinline__ void store_photon_wall_std(const Sink &sk, SmemAcc &sa, int id, v3 loc, bool shadow, int ch, uint32_t v, v3 e) {
+  if (!sk.acc) return;
+  const int vx = voxel_x_clamped(loc.x), vy = voxel_x_clamped(loc.y), vz = voxel_z_clamped(loc.z);
+  const int ax = std_axis(id);
+  const int slab = ((0x19 >> id) & 1) ? PM_GRID_N - 1 : 0;   // ids 0, 3, 4 lie on the upper boundary of the map
+  const int vfix = ax == 0 ? vx : (ax == 1 ? vy : vz);
+  const int a = ax == 0 ? vy : vx, b = ax == 2 ? vy : vz;
+  if (vfix == slab) {
+    const int tex = (id * PM_GRID_N + a) * PM_GRID_N + b;
+    if (shadow) atomicAdd(sa.shadow + tex, 1u);
+    else {
+      const uint32_t old = atomicAdd(sa.lo + tex * 4 + ch, v);
+      if ((uint32_t)(old + v) < old) atomicAdd(sa.hi + tex * 4 + ch, 1u);
+    }
+    return;
+  }
+  splat_offslab(sk, id, 0, vx, vy, vz, e);
+}
+
 // getColor / filterColor, PMK:605-617
 __device__ __forceinline__ v3 get_color(v3 in, int type, int idx) {
   v3 m = V(1.0f, 1.0f, 1.0f);
@@ -417,6 +440,26 @@ __device__ __forceinline__ v3 get_color(v3 in, int type, int idx) {
   else if (type == 1 && idx == 2) m = V(1.0f, 0.0f, 0.0f);
   return V(fminf(m.x, in.x), fminf(m.y, in.y), fminf(m.z, in.z));
 }
+
+// planeNormal + reflect3 (PMK:196-209, :664-668) for an axis-aligned wall of the reference's layout, scalar: the normal is
+// (0, .., wd / |wd|, .., 0) with wd = P[axis] - offset -- sqrt(RN(wd * wd)) == |wd| in binary floating point when the square neither
+// under- nor overflows (2^-34 <= |wd| <= ~1e6 under std_walls_ok; checked by pm_selftest_fdiv) --, its two zero components contribute
+// +-0 to the dot product (ray[axis] != 0: the ray has just hit this wall) and (+0) * k to the subtraction, which is kept because it
+// turns a -0 ray component into +0 when k < 0.  Callers have ruled out wd * wd == 0 / NaN (hazard H1).
+__device__ __forceinline__ v3 reflect_wall_std(const DeviceScene &sc, v3 ray, v3 P, int id, int wax) {
+  const float wd = comp(P, wax) - sc.pl_off[id];
+  const float na = wd * rcp_rn(fabsf(wd));
+  const float ra = comp(ray, wax);
+  const float k = 2.0f * (ra * na);
+  const float z = 0.0f * k;
+  v3 rr = V(ray.x - z, ray.y - z, ray.z - z);
+  set_comp(rr, wax, ra - na * k);
+  return normalize(rr);
+}
+
+// per-warp queue of the two-phase walk: structure of arrays, word k of entry j at [k * kQueueCap + j]; word 0 = photon index
+// (27 bits) | wall id << 27 | fresh << 31, words 1-3 the incoming ray, 4-6 the hit point (survivors only)
+constexpr int kQueueCap = kTraceQueueCap, kQueueWords = kTraceQueueWords;
 
 // lane states: what the NEXT intersection result means for this lane
 enum : int { ST_IDLE = 0, ST_PRIMARY, ST_SHADOW, ST_CHAIN_R, ST_CHAIN_F1, ST_CHAIN_F2 };
@@ -471,104 +514,212 @@ __global__ void __launch_bounds__(kSurfaceThreads, 1) trace_kernel(const __grid_
   if (cur > end) cur = end;
 
   const v3 light = V(sc.light[0], sc.light[1], sc.light[2]);
-  int state = ST_IDLE, index = 0, seq = 0, bounces = 1, level = 1, t_type = 0, t_idx = 0;
-  bool caustics = false, new_point = true, chain_glass = false;
-  v3 rgb = V(0.0f, 0.0f, 0.0f), ray = rgb, prev = rgb, P = rgb, org = rgb;
-  Hit h; h.hit = 0; h.type = 0; h.idx = 0; h.dist = -1.0f;
+  const v3 rgb0 = media ? V(7.0f, 7.0f, 7.0f) : V(10.0f, 10.0f, 10.0f);   // the medium walk leaves rgb = 10-1-1-1
+  // ---- two-phase walk (Mode A, reference layout, scene conditions checked by the host: DeviceScene::fast_ok) ----
+  // Phase F: 32 fresh photons in lock-step through the common path -- primary ray from the light that provably misses both spheres,
+  // wall hit, deposit, shadow ray, deposit, and the bounce that dies on normalize(0) (hazard H1, ~88% of them).  Everything a lane
+  // cannot finish there goes to the warp's queue: photons aimed at a sphere or at the caustic emitter as their bare index ("fresh"),
+  // survivors of the wall bounce with their state.  Phase G, when the queue is nearly full or the slice is used up: the general state
+  // machine below, its lanes refilled from the queue instead of the slice.  Per photon the operations are those of the machine.
+  constexpr bool kTwoPhase = kStd && !kRec;
+  const bool two_phase = kTwoPhase && sc.fast_ok && sk.queue != nullptr && warp >= vol_warps;
+  uint32_t *const q = sk.queue + ((size_t)blockIdx.x * (kSurfaceThreads / 32) + warp) * kQueueWords;
+  int qn = 0;   // entries in the queue (warp-uniform)
+  // first-bounce energy of a channel the wall's colour lets through: min(1, rgb0) * 1 / sqrt(1) * 5 with the machine's operations
+  const float e1 = fminf(1.0f, rgb0.x) * 1.0f * sc.inv_sqrt_bounce[1] * 5.0f;
+  const uint32_t v1 = __float2uint_rn(e1 * (float)kHitScale);
+  float4 td_next = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  if (kTwoPhase && two_phase && cur + lane < end) td_next = __ldg(table + cur + lane);
 
   for (;;) {
-    // ---- refill idle lanes from the warp's slice (emitPhotons prologue, PMK:1229-1237, :1274-1280).  The prologue
-    //      runs with only the idle lanes active, so it is deferred until a quarter of the warp is idle ----
-    unsigned idle = __ballot_sync(0xffffffffu, state == ST_IDLE);
-    if (cur < end && (__popc(idle) >= kRefillLanes || idle == 0xffffffffu)) {
-      long long cand = cur + __popc(idle & lt_mask);
-      if (state == ST_IDLE && cand < end) {
-        index = (int)cand;
-        const float4 td = __ldg(table + cand);
-        ray = table_direction(td);
-        rgb = media ? V(7.0f, 7.0f, 7.0f) : V(10.0f, 10.0f, 10.0f);   // the medium walk leaves rgb = 10-1-1-1
-        if (index < 100) {   // CAUSTICS_PHOTONS: aimed at the glass sphere, jittered, not re-normalised
-          v3 aim = normalize(sub(V(sc.sph[0][0], sc.sph[0][1], sc.sph[0][2]), light));
-          ray = add(aim, mul(ray, 0.01f));
-        }
-        prev = light; org = light;
-        bounces = 1; seq = media ? 3 : 0;
-        caustics = false; new_point = true;
-        h.type = 0; h.idx = 0;
-        state = ST_PRIMARY;
-      }
-      cur += __popc(idle);
-      if (cur > end) cur = end;
-    }
-    if (__ballot_sync(0xffffffffu, state != ST_IDLE) == 0u) {
-      if (cur >= end) break;
-      continue;
-    }
-    if (state == ST_IDLE) continue;
-
-    // ---- the single intersection site ----
-    raytrace<kStd>(sc, ray, org, h);
-
-    // ---- mirror / glass chain: handleReflection/handleRefraction{,2,3,4}, PMK:673-827 ----
-    if (state >= ST_CHAIN_R) {
-      bool chain_done = false;
-      if (state == ST_CHAIN_R) {
-        if (!h.hit) chain_done = true;
-        else {
-          P = add(mul(ray, h.dist), P);
-          if (!(h.type == 0 && h.idx == 0)) chain_done = true;
+    if (kTwoPhase && two_phase) {
+      while (cur < end && qn <= kQueueCap - 32) {
+        const long long gi = cur + lane;
+        const bool act = gi < end;
+        cur = cur + 32 < end ? cur + 32 : end;
+        const float4 td = td_next;
+        if (cur + lane < end) td_next = __ldg(table + cur + lane);   // the next block's rows are in flight under this block
+        bool push_fresh = false, push_post = false;
+        v3 fr = V(0.0f, 0.0f, 0.0f), fP = fr;
+        int fid = 0;
+        if (act) {
+          fr = table_direction(td);
+          // the primary ray leaves the light: sphere terms that do not depend on the ray come from the host (same operations).  A sphere
+          // is out when D <= 0, or when B >= 0 with the light outside it (light_C >= 0, part of fast_ok: sign = -1, so the root
+          // -B - sqrt(D) is <= 0 and checkDistance rejects it) -- pure FP32 logic, no geometry; anything else goes to the machine.
+          const float A = dot(fr, fr);
+          bool aimed = (int)gi < 100;   // CAUSTICS_PHOTONS
+#pragma unroll
+          for (int i = 0; i < 2; i++) {
+            const float B = -2.0f * dot(V(sc.light_s[i][0], sc.light_s[i][1], sc.light_s[i][2]), fr);
+            const float D = B * B - 4.0f * A * sc.light_C[i];
+            aimed = aimed | ((D > 0.0f) & !(B >= 0.0f));
+          }
+          if (aimed) push_fresh = true;
           else {
-            ray = refract3(sc, ray, P, h.type, h.idx, P, 1.0f);
-            P = add(mul(ray, 0.00001f), P);
-            org = P; state = ST_CHAIN_F1;
+            float dist = 999999.9f;
+            int best = -1;
+            ray_walls_std(sc, fr, light, dist, best);
+            if (best >= 0) {   // bounces == 1
+              const int id = best & 7;
+              fP = add(mul(fr, dist), light);
+              {   // the first bounce's energy: e1 in the wall's colour channels (getColor: green wall 0, red wall 2), PMK:1296-1298
+                const v3 e = V(id == 0 ? 0.0f : e1, id == 2 ? 0.0f : e1, (id == 0 || id == 2) ? 0.0f : e1);
+                store_photon_wall_std(sk, sa, id, fP, false, id == 0 ? 1 : (id == 2 ? 0 : 3), v1, e);
+              }
+              // shadowPhoton: the spheres that lie wholly on the light's side of the wall just crossed cannot be hit again
+              // (DeviceScene::shadow_need, argued in pm_api.cu make_device_scene); the others are tested as usual
+              const v3 o2 = add(fP, mul(fr, 0.00001f));
+              float d2 = 999999.9f;
+              int b2 = -1;
+              const unsigned need = sc.shadow_need[id];
+              if (need & 1u) ray_sphere(sc, 0, fr, o2, A, d2, b2);
+              if (need & 2u) ray_sphere(sc, 1, fr, o2, A, d2, b2);
+              ray_walls_std(sc, fr, o2, d2, b2);
+              if (b2 < 0 || b2 >= 8)   // a miss keeps the primary hit's ids (stale, as in the reference); a sphere stores nothing
+                store_photon_wall_std(sk, sa, b2 >= 0 ? (b2 & 7) : id, add(mul(fr, d2), o2), true, 3, 0u, V(-0.25f, -0.25f, -0.25f));
+              const float wd = comp(fP, std_axis(id)) - sc.pl_off[id];
+              const float wdd = wd * wd;
+              if (!(wdd == 0.0f || wdd != wdd)) { push_post = true; fid = id; }
+            }
           }
         }
-      } else if (state == ST_CHAIN_F1) {
-        P = add(mul(ray, h.dist), P);   // executed even on a miss
-        if (!(h.hit && h.type == 0 && h.idx == 0)) chain_done = true;
-        else {
-          ray = refract3(sc, ray, P, h.type, h.idx, P, -1.0f);
-          P = add(mul(ray, 0.00001f), P);
-          org = P; state = ST_CHAIN_F2;
+        const unsigned mpush = __ballot_sync(0xffffffffu, push_fresh | push_post);
+        if (push_fresh | push_post) {
+          const int j = qn + __popc(mpush & lt_mask);
+          q[j] = (uint32_t)(int)gi | ((uint32_t)fid << 27) | (push_fresh ? 0x80000000u : 0u);
+          if (push_post) {
+            q[1 * kQueueCap + j] = __float_as_uint(fr.x); q[2 * kQueueCap + j] = __float_as_uint(fr.y); q[3 * kQueueCap + j] = __float_as_uint(fr.z);
+            q[4 * kQueueCap + j] = __float_as_uint(fP.x); q[5 * kQueueCap + j] = __float_as_uint(fP.y); q[6 * kQueueCap + j] = __float_as_uint(fP.z);
+          }
         }
-      } else {   // ST_CHAIN_F2
-        P = add(mul(ray, h.dist), P);
-        if (level == 4 || !(h.type == 0 && h.idx == 1)) chain_done = true;   // not gated on h.hit: stale ids, as PMK:807
-        else {
-          level++;
-          ray = reflect3<kStd>(sc, ray, prev, h.type, h.idx, P);
-          org = P; state = ST_CHAIN_R;
-        }
+        qn += __popc(mpush);
+        __syncwarp();
       }
-      if (!chain_done) continue;
-      caustics = chain_glass; new_point = false; bounces++;
-      state = ST_PRIMARY;   // falls through: the while-condition is evaluated on the chain's last intersection
+      if (qn == 0) break;   // the slice is used up as well
     }
 
-    // ---- both remaining states deposit one photon at the intersection just found (single store site) ----
-    v3 loc, e;
-    if (state == ST_PRIMARY) {   // top of the bounce loop, PMK:1289-1301
-      if (!(h.hit && bounces <= 5)) { state = ST_IDLE; continue; }
-      if (new_point) P = add(mul(ray, h.dist), prev);
-      if (caustics) rgb = mul(V(1.0f, 1.0f, 1.0f), 10.0f);
-      else rgb = mul(mul(mul(get_color(rgb, h.type, h.idx), 1.0f), sc.inv_sqrt_bounce[bounces & 7]), 5.0f);   // 1 <= bounces <= 5 here
-      loc = P; e = rgb;
-    } else {                     // shadowPhoton, PMK:1185-1196: -0.25 at the next hit along the same ray
-      loc = add(mul(ray, h.dist), org);
-      e = V(-0.25f, -0.25f, -0.25f);
-    }
-    store_photon(sk, sa, h.type, h.idx, loc, e, state == ST_SHADOW);
-    if (rec) append_record(sk, seq, 0, h.type, h.idx, index, loc, ray, e);
-    seq++;
-    if (state == ST_PRIMARY && !caustics) {
-      t_type = h.type; t_idx = h.idx;
-      org = add(P, mul(ray, 0.00001f));   // the shadow ray starts just beyond the hit
-      state = ST_SHADOW;
-      continue;
-    }
-    if (state == ST_SHADOW) { h.type = t_type; h.idx = t_idx; }   // dist/hit stay clobbered, as in the reference
-    const bool post = true;
-    if (post) {   // PMK:1305-1370: where does the photon go next
+    // ---- phase G / the only phase otherwise: the state machine ----
+    int state = ST_IDLE, index = 0, seq = 0, bounces = 1, level = 1, t_type = 0, t_idx = 0;
+    bool caustics = false, new_point = true, chain_glass = false;
+    v3 rgb = V(0.0f, 0.0f, 0.0f), ray = rgb, prev = rgb, P = rgb, org = rgb;
+    Hit h; h.hit = 0; h.type = 0; h.idx = 0; h.dist = -1.0f;
+    for (;;) {
+      // ---- refill idle lanes from the warp's slice (emitPhotons prologue, PMK:1229-1237, :1274-1280) or from its queue.  The
+      //      prologue runs with only the idle lanes active, so it is deferred until a quarter of the warp is idle ----
+      const unsigned idle = __ballot_sync(0xffffffffu, state == ST_IDLE);
+      const long long avail = (kTwoPhase && two_phase) ? (long long)qn : end - cur;
+      if (avail > 0 && (__popc(idle) >= kRefillLanes || idle == 0xffffffffu)) {
+        const int rank = __popc(idle & lt_mask);
+        if (state == ST_IDLE && rank < avail) {
+          long long cand = cur + rank;
+          bool resumed = false;
+          if (kTwoPhase && two_phase) {
+            const int j = qn - 1 - rank;
+            const uint32_t w0q = q[j];
+            cand = (long long)(w0q & 0x07ffffffu);
+            if (!(w0q & 0x80000000u)) {
+              // a survivor of the first wall bounce: the rest of its bounce (PMK:1365-1369) -- the machine's wall branch, die-check passed
+              resumed = true;
+              const int id = (int)(w0q >> 27) & 7, wax = std_axis(id);
+              const v3 rin = V(__uint_as_float(q[1 * kQueueCap + j]), __uint_as_float(q[2 * kQueueCap + j]), __uint_as_float(q[3 * kQueueCap + j]));
+              P = V(__uint_as_float(q[4 * kQueueCap + j]), __uint_as_float(q[5 * kQueueCap + j]), __uint_as_float(q[6 * kQueueCap + j]));
+              ray = reflect_wall_std(sc, rin, P, id, wax);
+              index = (int)cand;
+              rgb = mul(mul(mul(get_color(rgb0, 1, id), 1.0f), sc.inv_sqrt_bounce[1]), 5.0f);
+              prev = P; org = P;
+              bounces = 2; seq = (media ? 3 : 0) + 2;
+              caustics = false; new_point = true;
+              h.type = 1; h.idx = id;
+              state = ST_PRIMARY;
+            }
+          }
+          if (!resumed) {
+            index = (int)cand;
+            ray = table_direction(__ldg(table + cand));
+            rgb = rgb0;
+            if (index < 100) {   // CAUSTICS_PHOTONS: aimed at the glass sphere, jittered, not re-normalised
+              v3 aim = normalize(sub(V(sc.sph[0][0], sc.sph[0][1], sc.sph[0][2]), light));
+              ray = add(aim, mul(ray, 0.01f));
+            }
+            prev = light; org = light;
+            bounces = 1; seq = media ? 3 : 0;
+            caustics = false; new_point = true;
+            h.type = 0; h.idx = 0;
+            state = ST_PRIMARY;
+          }
+        }
+        const int took = __popc(idle) < avail ? __popc(idle) : (int)avail;
+        if (kTwoPhase && two_phase) qn -= took; else cur += took;
+      }
+      if (__ballot_sync(0xffffffffu, state != ST_IDLE) == 0u) {
+        if (((kTwoPhase && two_phase) ? (long long)qn : end - cur) <= 0) break;
+        continue;
+      }
+      if (state == ST_IDLE) continue;
+
+      // ---- the single intersection site ----
+      raytrace<kStd>(sc, ray, org, h);
+
+      // ---- mirror / glass chain: handleReflection/handleRefraction{,2,3,4}, PMK:673-827 ----
+      if (state >= ST_CHAIN_R) {
+        bool chain_done = false;
+        if (state == ST_CHAIN_R) {
+          if (!h.hit) chain_done = true;
+          else {
+            P = add(mul(ray, h.dist), P);
+            if (!(h.type == 0 && h.idx == 0)) chain_done = true;
+            else {
+              ray = refract3(sc, ray, P, h.type, h.idx, P, 1.0f);
+              P = add(mul(ray, 0.00001f), P);
+              org = P; state = ST_CHAIN_F1;
+            }
+          }
+        } else if (state == ST_CHAIN_F1) {
+          P = add(mul(ray, h.dist), P);   // executed even on a miss
+          if (!(h.hit && h.type == 0 && h.idx == 0)) chain_done = true;
+          else {
+            ray = refract3(sc, ray, P, h.type, h.idx, P, -1.0f);
+            P = add(mul(ray, 0.00001f), P);
+            org = P; state = ST_CHAIN_F2;
+          }
+        } else {   // ST_CHAIN_F2
+          P = add(mul(ray, h.dist), P);
+          if (level == 4 || !(h.type == 0 && h.idx == 1)) chain_done = true;   // not gated on h.hit: stale ids, as PMK:807
+          else {
+            level++;
+            ray = reflect3<kStd>(sc, ray, prev, h.type, h.idx, P);
+            org = P; state = ST_CHAIN_R;
+          }
+        }
+        if (!chain_done) continue;
+        caustics = chain_glass; new_point = false; bounces++;
+        state = ST_PRIMARY;   // falls through: the while-condition is evaluated on the chain's last intersection
+      }
+
+      // ---- both remaining states deposit one photon at the intersection just found (single store site) ----
+      v3 loc, e;
+      if (state == ST_PRIMARY) {   // top of the bounce loop, PMK:1289-1301
+        if (!(h.hit && bounces <= 5)) { state = ST_IDLE; continue; }
+        if (new_point) P = add(mul(ray, h.dist), prev);
+        if (caustics) rgb = mul(V(1.0f, 1.0f, 1.0f), 10.0f);
+        else rgb = mul(mul(mul(get_color(rgb, h.type, h.idx), 1.0f), sc.inv_sqrt_bounce[bounces & 7]), 5.0f);   // 1 <= bounces <= 5 here
+        loc = P; e = rgb;
+      } else {                     // shadowPhoton, PMK:1185-1196: -0.25 at the next hit along the same ray
+        loc = add(mul(ray, h.dist), org);
+        e = V(-0.25f, -0.25f, -0.25f);
+      }
+      store_photon(sk, sa, h.type, h.idx, loc, e, state == ST_SHADOW);
+      if (rec) append_record(sk, seq, 0, h.type, h.idx, index, loc, ray, e);
+      seq++;
+      if (state == ST_PRIMARY && !caustics) {
+        t_type = h.type; t_idx = h.idx;
+        org = add(P, mul(ray, 0.00001f));   // the shadow ray starts just beyond the hit
+        state = ST_SHADOW;
+        continue;
+      }
+      if (state == ST_SHADOW) { h.type = t_type; h.idx = t_idx; }   // dist/hit stay clobbered, as in the reference
+      // PMK:1305-1370: where does the photon go next
       prev = P;
       if (h.type == 0 && h.idx == 1) {          // mirror sphere
         chain_glass = false; level = 1;
@@ -587,26 +738,14 @@ __global__ void __launch_bounds__(kSurfaceThreads, 1) trace_kernel(const __grid_
         const float wd = comp(prev, wax) - sc.pl_off[h.type == 1 ? h.idx : 0];
         const float wdd = wd * wd;
         if (h.type == 1 && wax >= 0 && wax <= 2 && (wdd == 0.0f || wdd != wdd)) { state = ST_IDLE; continue; }
-        if (kStd) {
-          // planeNormal + reflect3 (PMK:196-209, :664-668) for an axis-aligned wall, scalar: the normal is (0, .., wd / |wd|, .., 0) --
-          // sqrt(RN(wd * wd)) == |wd| in binary floating point when the square neither under- nor overflows (2^-34 <= |wd| <= ~1e6 under
-          // std_walls_ok) --, its two zero components contribute +-0 to the dot product (ray[axis] != 0: the ray has just hit this wall)
-          // and (+0) * k to the subtraction, which is kept because it turns a -0 ray component into +0 when k < 0
-          const float na = wd * rcp_rn(fabsf(wd));
-          const float ra = comp(ray, wax);
-          const float k = 2.0f * (ra * na);
-          const float z = 0.0f * k;
-          v3 rr = V(ray.x - z, ray.y - z, ray.z - z);
-          set_comp(rr, wax, ra - na * k);
-          ray = normalize(rr);
-        } else {
-          ray = reflect3<kStd>(sc, ray, prev, h.type, h.idx, P);
-        }
+        if (kStd) ray = reflect_wall_std(sc, ray, prev, h.idx, wax);
+        else ray = reflect3<kStd>(sc, ray, prev, h.type, h.idx, P);
         org = P;
         caustics = false; new_point = true; bounces++;
         state = ST_PRIMARY;
       }
     }
+    if (!(kTwoPhase && two_phase)) break;
   }
 
   // ---- flush the CTA-private accumulators ----
@@ -708,7 +847,7 @@ cudaError_t launch_philox_table(float4 *table, long long n, unsigned long long s
 static Sink make_sink(unsigned flags, unsigned long long *acc, float4 *rec_pos, float4 *rec_pow, float4 *rec_dir,
                       unsigned long long *rec_count, long long rec_cap) {
   Sink sk;
-  sk.vol_cnt = nullptr; sk.vrec_pos = sk.vrec_pow = nullptr; sk.vrec_cap = 0; sk.dbg = nullptr; sk.vox_touched = nullptr;
+  sk.vol_cnt = nullptr; sk.vrec_pos = sk.vrec_pow = nullptr; sk.vrec_cap = 0; sk.dbg = nullptr; sk.vox_touched = nullptr; sk.queue = nullptr;
   sk.acc = (flags & PM_TRACE_NO_MAP) ? nullptr : acc;
   sk.rec_pos = rec_pos; sk.rec_pow = rec_pow; sk.rec_dir = rec_dir; sk.rec_count = rec_count; sk.rec_cap = rec_cap;
   return sk;
@@ -748,12 +887,13 @@ int launch_trace_volume(const DeviceScene &sc, const float4 *table, long long fi
 int launch_trace(const DeviceScene &sc, const float4 *table, long long first, long long last, unsigned flags, int vol_warps, uint32_t w0,
                  uint32_t z0, const MwcJump *J, unsigned long long *acc, uint32_t *vol_cnt, float4 *rec_pos, float4 *rec_pow,
                  float4 *rec_dir, float4 *vrec_pos, float4 *vrec_pow, long long vrec_cap, unsigned long long *rec_count, long long rec_cap,
-                 int num_sms, cudaStream_t st, cudaError_t *err, unsigned long long *dbg, uint32_t *vox_touched) {
+                 int num_sms, cudaStream_t st, cudaError_t *err, unsigned long long *dbg, uint32_t *vox_touched, uint32_t *queue) {
   *err = cudaSuccess;
   long long n = last - first;
   if (n <= 0) return 0;
   Sink sk = make_sink(flags, acc, rec_pos, rec_pow, rec_dir, rec_count, rec_cap);
   sk.vol_cnt = vol_cnt; sk.vrec_pos = vrec_pos; sk.vrec_pow = vrec_pow; sk.vrec_cap = vrec_cap; sk.dbg = dbg; sk.vox_touched = vox_touched;
+  sk.queue = (flags & PM_TRACE_ONE_PHASE) ? nullptr : queue;
   const bool rec = (flags & PM_TRACE_RECORDS) != 0;
   // the reference's object layout (only the layout: offsets, centres and radii stay scene data) selects the specialised instantiation
   bool std_scene = sc.n_spheres == 2 && sc.n_planes == 5;

@@ -113,9 +113,12 @@ int pm_get_mwc_state(const pm_context *ctx, uint32_t *w, uint32_t *z);
 #define PM_TRACE_EXACT_MEDIUM 16u /* medium walk: every deposit point with the reference's exact arithmetic.  By default a Mode A trace
                                   (counts only) computes steps 1-2 approximately and redoes, exactly, the photons that come near a voxel
                                   boundary (csrc/pm_trace.cu volume_photon_fast) -- same counts; kept as the cross-check */
+#define PM_TRACE_ONE_PHASE 32u    /* surface walk: every photon through the general state machine.  By default a Mode A trace of a scene
+                                  with the reference's object layout takes fresh photons through the common path in lock-step and hands
+                                  the rest to the machine through per-warp queues (csrc/pm_trace.cu) -- same deposits; the cross-check */
 int pm_clear_map(pm_context *ctx);                                 /* init_photons_kernel, PMK:1503-1521 */
 int pm_trace(pm_context *ctx, float animTime, unsigned flags);
-/* tuning: how many of a CTA's 32 warps run the medium walk in the fused trace kernel (default 6; 1..16) */
+/* tuning: how many of a CTA's 32 warps run the medium walk in the fused trace kernel (default 7; 1..16) */
 int pm_set_volume_warps(pm_context *ctx, int warps);
 /* tuning: CTAs of the persistent trace kernel (default 0 = one per SM).  Fewer leaves SMs free for the previous frame's exchange +
  * map build + render, which the pipelined frame calls run on a second stream (worth it when those are a large part of the frame,

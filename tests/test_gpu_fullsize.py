@@ -232,6 +232,45 @@ def test_medium_walk_filter_gives_the_exact_counts_at_16M(pm, t, light):
     m.close()
 
 
+@pytest.mark.parametrize("n,t,media,variant", [(16777216, 0.0, True, "default"), (16777216, 1.3, False, "default"), (1 << 20, 0.7, True, "shifted"),
+                                               (1 << 20, 2.3, True, "default"), (1 << 20, 0.0, True, "light_low"), (1 << 20, 0.4, False, "big_spheres"),
+                                               (100003, 0.0, True, "default"), (37, 0.0, True, "default")])
+def test_two_phase_walk_gives_the_machine_s_deposits(pm, n, t, media, variant):
+    """Mode A takes fresh photons through the common path in lock-step and queues the rest for the general state machine
+    (csrc/pm_trace.cu, phase F / phase G).  Its accumulators must equal, bit for bit, those of the machine alone (PM_TRACE_ONE_PHASE)
+    and those of the records instantiation -- the one the record tests pin to the oracle, photon by photon."""
+    m = pm.PhotonMapper(n_photons=n)
+    sc = m.get_scene()
+    if variant == "shifted":
+        for i, off in enumerate((1.2, -1.1, -1.7, 1.6, 5.5)):
+            sc.planes[i][1] = off
+    elif variant == "light_low":      # the light next to the floor and a wall: most shadow rays leave through them
+        sc.light[0], sc.light[1], sc.light[2] = -1.3, -1.35, 0.4
+    elif variant == "big_spheres":    # spheres that reach through walls: their shadow tests cannot be skipped
+        sc.animate = 0
+        sc.spheres[0][0], sc.spheres[0][1], sc.spheres[0][2], sc.spheres[0][3] = 1.2, -1.0, 3.0, 0.7
+        sc.spheres[1][0], sc.spheres[1][1], sc.spheres[1][2], sc.spheres[1][3] = -0.5, 0.9, 5.6, 0.9
+    m.set_scene(sc)
+    m.init_random_numbers()
+    st = m.get_mwc_state()
+    accs = []
+    for kw in ({}, {"one_phase": True}, {"records": True}):
+        if "records" in kw:
+            if n > (1 << 20):
+                continue
+            m.set_record_capacity(8 * n)
+        m.set_mwc_state(*st)
+        m.clear_map()
+        m.trace(t, media=media, **kw)
+        accs.append(m.get_accumulators())
+    assert np.array_equal(accs[0], accs[1])
+    assert np.abs(accs[1][:pm.ACC_HIT_ENTRIES]).sum() > 0
+    if len(accs) == 3:
+        head = pm.ACC_HIT_ENTRIES + 32 * 32 * 32 * 3
+        assert np.array_equal(accs[0][:head], accs[2][:head])
+    m.close()
+
+
 def test_mode_b_full_size_properties(pm, oracle):
     """4M photons (BASELINE config 3): sorted keys are sorted, the permutation is a bijection onto the kept records, and
     64 random k=100 queries agree bit-exactly with brute force over all 9.6M wall photons."""
