@@ -154,6 +154,7 @@ __device__ __forceinline__ VolumeCtx volume_ctx(const DeviceScene &sc, const flo
   ok = ok && fabsf(c.light.x) < 4.9f && fabsf(c.light.y) < 4.9f && fabsf(c.light.z) < 4.9f;
   c.g0 = 4096.0f * (t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
   c.g1 = 4096.0f * (t[3] * t[3] + t[4] * t[4] + t[5] * t[5]);
+  asm volatile("" : "+f"(c.g0), "+f"(c.g1));   // keep them in registers: the compiler would otherwise recompute both for every photon
   ok = ok && c.g0 > 0.0f && c.g1 > 0.0f;
 #ifdef PM_NO_FAST_VOLUME
   ok = false;
@@ -278,28 +279,32 @@ __device__ __forceinline__ void volume_walk_sliced(const DeviceScene &sc, const 
                                                    uint32_t w0, uint32_t z0, const MwcJump *__restrict__ J, SliceJump jump, int replica,
                                                    const Sink &sk) {
   const int lane = threadIdx.x & 31;
-  int s = threadIdx.x >> 5;            // V <= S: the warp's first block is block 0 of slice `warp`
-  long long b = 0;                     // block (32 photons) inside the slice
-  long long gi = cta_first + s * per + lane;
   if (cta_first >= cta_last || per <= 0) return;
+  // 32-bit offsets inside the CTA's range (it holds < 2^31 photons): the loop's bookkeeping is a handful of integer instructions
+  const int per32 = (int)per, n_cta = (int)(cta_last - cta_first);
+  const float4 *__restrict__ tab = table + cta_first;
+  int s = threadIdx.x >> 5;            // V <= S: the warp's first block is block 0 of slice `warp`
+  int b32 = 0;                         // first photon of the lane's block inside the slice
+  int off = s * per32 + lane;          // the lane's photon, relative to cta_first
+  const int step_f = V * per32, step_w = (V - S) * per32 + 32;
   const VolumeCtx c = volume_ctx(sc, table, first, flags, replica, sk);
   Mwc base;
-  base.z = mwc_jump(J, 0, z0, 9u * (uint32_t)gi);
-  base.w = mwc_jump(J, 1, w0, 9u * (uint32_t)gi);
-  bool valid = lane < per && gi < cta_last;
-  float4 td_next = valid ? __ldg(table + gi) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-  while (b * 32 < per) {
+  base.z = mwc_jump(J, 0, z0, 9u * (uint32_t)(cta_first + off));
+  base.w = mwc_jump(J, 1, w0, 9u * (uint32_t)(cta_first + off));
+  bool valid = lane < per32 && off < n_cta;
+  float4 td_next = valid ? __ldg(tab + off) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  while (b32 < per32) {
     const float4 td = td_next;
-    const long long gi_now = gi;
+    const int off_now = off;
     const bool valid_now = valid;
     // the lane's next block
     s += V;
     const bool wrap = s >= S;
-    if (wrap) { s -= S; b += 1; }
-    gi = cta_first + s * per + b * 32 + lane;
-    valid = b * 32 + lane < per && gi < cta_last;
-    if (valid) td_next = __ldg(table + gi);   // in flight under this photon's walk
-    if (valid_now && !(c.fast && volume_photon_fast(c, td, base))) volume_photon(c, sk, td, gi_now, base);
+    if (wrap) { s -= S; b32 += 32; }
+    off += wrap ? step_w : step_f;
+    valid = b32 + lane < per32 && off < n_cta;
+    if (valid) td_next = __ldg(tab + off);   // in flight under this photon's walk
+    if (valid_now && !(c.fast && volume_photon_fast(c, td, base))) volume_photon(c, sk, td, cta_first + off_now, base);
     base.z = mulmod(base.z, wrap ? jump.wz : jump.fz, mwc_modulus(0));
     base.w = mulmod(base.w, wrap ? jump.ww : jump.fw, mwc_modulus(1));
   }
@@ -470,6 +475,10 @@ constexpr int kRefillLanes = 8;   // measured: 4 is 13% slower, 12 and 16 are th
                                   // Round 2 (the slowest warp of a CTA ends 5% after the mean at 16M photons, 11% at 2M): pooling only the
                                   // last 1/8..1/2 of every slice in 32..256-photon chunks, 32-bit cursors, no spills: still 4-27% slower
                                   // (0.985 -> 1.03..1.25 ms) -- every refill at a chunk boundary leaves lanes idle for an iteration
+#ifndef PM_QREFILL
+#define PM_QREFILL 8
+#endif
+constexpr int kQueueRefillLanes = PM_QREFILL;   // the same threshold when the lanes are refilled from the two-phase walk's queue
 constexpr int kShadowEntries = kAccHitEntries / 4;                                      // one per wall texel
 constexpr size_t kSurfaceSmem = sizeof(uint32_t) * (2 * kAccHitEntries + kShadowEntries);   // 184 320 B
 
@@ -609,7 +618,7 @@ __global__ void __launch_bounds__(kSurfaceThreads, 1) trace_kernel(const __grid_
       //      prologue runs with only the idle lanes active, so it is deferred until a quarter of the warp is idle ----
       const unsigned idle = __ballot_sync(0xffffffffu, state == ST_IDLE);
       const long long avail = (kTwoPhase && two_phase) ? (long long)qn : end - cur;
-      if (avail > 0 && (__popc(idle) >= kRefillLanes || idle == 0xffffffffu)) {
+      if (avail > 0 && (__popc(idle) >= ((kTwoPhase && two_phase) ? kQueueRefillLanes : kRefillLanes) || idle == 0xffffffffu)) {
         const int rank = __popc(idle & lt_mask);
         if (state == ST_IDLE && rank < avail) {
           long long cand = cur + rank;
