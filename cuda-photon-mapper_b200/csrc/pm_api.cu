@@ -50,28 +50,29 @@ static void position_objects(pm_scene *sc, float t) {
 }
 
 // Terms of trace_kernel's two-phase surface walk (csrc/pm_trace.cu).
-//   light_s / light_C: raySphere's ray-independent terms for rays that start at the light, with the kernel's own FP32 operations
-//   (one subtraction per component; x*x + y*y + z*z summed left to right, then - r^2; this file is compiled without FMA contraction).
-//   shadow_need[w], bit i clear: a shadow ray (PMK:1185-1196) that continues a primary ray FROM THE LIGHT behind wall w cannot be
-//   credited with sphere i, so the kernel skips that raySphere.  Condition: the sphere lies on the light's side of the wall's plane
-//   with a margin m = 0.05, i.e. side * (c[axis] - offset) - R >= m.  Argument: the shadow ray starts within 2e-5 of the plane
-//   and moves away from it, so for t >= 0 it stays >= m - 2e-5 from every point of the sphere.  With s = c - o, t* = (s.r)/A:
+//   shadow_need[w], bit i clear: a shadow ray (PMK:1185-1196) behind wall w cannot be credited with sphere i, so the kernel skips that
+//   raySphere -- provided the ray has crossed w's plane coming from the light's side (wall_side[w]; the kernel checks the sign of the ray
+//   component) and starts within 16 of the origin (checked in the kernel as well).  Condition here: the sphere lies on the light's side
+//   of the plane with a margin m = 0.05, i.e. side * (c[axis] - offset) - R >= m.  Argument: the shadow ray starts within 2e-5 of the
+//   plane and moves away from it, so for t >= 0 it stays >= m - 2e-5 from every point of the sphere.  With s = c - o, t* = (s.r)/A:
 //     t* >= 0: the line's closest approach is on the far side, its distance to the centre >= R + m - 2e-5, so the true discriminant is
-//       <= -4A(2Rm + m^2) <= -0.03; the computed one differs by <= 3.3e-6 |s|^2 <= 0.0104 (|s| <= 56 here: t* >= 0 needs the hit point
-//       within |c - light| <= 27.8 of the light), so D <= 0 and raySphere returns without a candidate;
-//     t* < 0 and the computed s.r <= 0: B >= 0 and C > 0 (the origin is outside the sphere by >= m), so the root -B - sqrt(D) <= 0 is
-//       rejected by checkDistance whatever D is;
-//     t* < 0 but the computed s.r > 0: then |s.r| <= 1.8e-7 |s| |r|, which needs near-perpendicularity, i.e. again |s| <= 56, so the
-//       closest approach lies within 1e-5 of the origin and the first case applies.
+//       <= -4A(2Rm + m^2) <= -0.03; the computed one differs by <= 3.3e-6 |s|^2 <= 0.006 (|s| <= 41.6), so D <= 0 and raySphere
+//       returns without a candidate;
+//     t* < 0 and the computed s.r <= 0: B >= 0 and C > 0 (the origin is outside the sphere by >= m: |s|^2 - R^2 >= 0.0075, error 3e-4),
+//       so the root -B - sqrt(D) <= 0 is rejected by checkDistance whatever D is;
+//     t* < 0 but the computed s.r > 0: then |s.r| <= 1.8e-7 |s| |r|, the closest approach lies within 1e-5 of the origin and the first
+//       case applies.
 //   The bounds used: light, sphere centres and wall offsets within [-8, 8], 0.05 <= R <= 4.
 //   fast_ok: reference layout (2 spheres, 5 walls x,y,x,y,z, std_walls_ok), the bounds above, the light >= m from every wall plane and
-//   outside both spheres with light_C >= 0 (the kernel's rejection test for the primary ray needs raySphere's sign = -1).
+//   outside both spheres with light_C >= 0 (the rejection test for a fresh photon's ray needs raySphere's sign = -1).
 static void two_phase_terms(DeviceScene &d) {
   const float m = 0.05f;
   bool ok = d.n_spheres == 2 && d.n_planes == 5 && std_walls_ok(d.pl_off);
   for (int w = 0; w < PM_MAX_PLANES; w++) ok = ok && d.pl_axis[w] == std_axis(w) && fabsf(d.pl_off[w]) <= 8.0f;
   for (int j = 0; j < 3; j++) ok = ok && fabsf(d.light[j]) <= 8.0f;
   for (int i = 0; i < 2; i++) {
+    // raySphere's ray-independent terms for rays that start at the light, with the kernel's own FP32 operations (one subtraction per
+    // component; x*x + y*y + z*z summed left to right, then - r^2; volatile keeps the compiler from contracting or widening anything)
     volatile float s0 = d.sph[i][0] - d.light[0], s1 = d.sph[i][1] - d.light[1], s2 = d.sph[i][2] - d.light[2];
     volatile float p0 = s0 * s0, p1 = s1 * s1, p2 = s2 * s2;
     volatile float sum = p0 + p1;
@@ -83,13 +84,14 @@ static void two_phase_terms(DeviceScene &d) {
   }
   for (int w = 0; w < PM_MAX_PLANES; w++) {
     d.shadow_need[w] = 3u;
+    d.wall_side[w] = 1.0f;
     if (!ok) continue;
     const int a = d.pl_axis[w];
     const float gap = d.light[a] - d.pl_off[w];
     if (!(fabsf(gap) >= m)) { ok = false; continue; }
-    const float side = gap > 0.0f ? 1.0f : -1.0f;
+    d.wall_side[w] = gap > 0.0f ? 1.0f : -1.0f;
     for (int i = 0; i < 2; i++)
-      if (side * (d.sph[i][a] - d.pl_off[w]) - d.sph[i][3] >= m) d.shadow_need[w] &= ~(1u << i);
+      if (d.wall_side[w] * (d.sph[i][a] - d.pl_off[w]) - d.sph[i][3] >= m) d.shadow_need[w] &= ~(1u << i);
   }
   d.fast_ok = ok ? 1 : 0;
 }

@@ -31,8 +31,8 @@ int launch_trace(const DeviceScene &sc, const float4 *table, long long first, lo
                  float4 *rec_dir, float4 *vrec_pos, float4 *vrec_pow, long long vrec_cap, unsigned long long *rec_count, long long rec_cap,
                  int num_sms, cudaStream_t st, cudaError_t *err, unsigned long long *dbg = nullptr, uint32_t *vox_touched = nullptr,
                  uint32_t *queue = nullptr);
-// per-warp queues of trace_kernel's two-phase surface walk: structure of arrays, word k of entry j at [k * kTraceQueueCap + j]
-constexpr int kTraceQueueCap = 256, kTraceQueueWords = 7 * kTraceQueueCap;
+// per-warp queues of trace_kernel's two-phase surface walk: two queues of kTraceQueueCap entries of 8 words, structure of arrays
+constexpr int kTraceQueueCap = 128, kTraceQueueWords = 2 * 8 * kTraceQueueCap;
 constexpr size_t kTraceQueueWordsPerCta = (size_t)32 * kTraceQueueWords;   // scratch the caller provides: this many words per SM
 constexpr int kTraceDbgWords = 48;   // pm_trace_profile: per CTA [0] start, [1] accumulators zeroed, [2] all warps done, [3] flushed, [8+w] warp w done (ns)
 

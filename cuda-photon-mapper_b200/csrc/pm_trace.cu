@@ -417,8 +417,9 @@ __device__ __forceinline__ void store_photon(const Sink &sk, SmemAcc &sa, int ty
 }
 
 // store_photon for phase F of the two-phase walk: the hit is on wall `id` of the reference's layout, and the deposit is either a shadow
-// photon or the first bounce's energy, which is one value `v` (fixed point) in one channel `ch` of the wall texel (green wall: g,
-// red wall: r, white walls: the grey plane).  Same voxel, same slab test, same accumulator entries as store_photon.
+// photon or a bounce's energy, which is one value `v` (fixed point) in one channel `ch` of the wall texel (after a green wall: g, after
+// a red one: r, white walls only: the grey plane; nothing, v = 0, after both).  Same voxel, same slab test, same accumulator entries as
+// store_photon; e = the same energy as a vector, for the off-slab expansion.
 __device__ __forceinline__ void store_photon_wall_std(const Sink &sk, SmemAcc &sa, int id, v3 loc, bool shadow, int ch, uint32_t v, v3 e) {
   if (!sk.acc) return;
   const int vx = voxel_x_clamped(loc.x), vy = voxel_x_clamped(loc.y), vz = voxel_z_clamped(loc.z);
@@ -429,7 +430,7 @@ __device__ __forceinline__ void store_photon_wall_std(const Sink &sk, SmemAcc &s
   if (vfix == slab) {
     const int tex = (id * PM_GRID_N + a) * PM_GRID_N + b;
     if (shadow) atomicAdd(sa.shadow + tex, 1u);
-    else {
+    else if (v) {   // a photon that has lost all three channels still casts its shadow photons
       const uint32_t old = atomicAdd(sa.lo + tex * 4 + ch, v);
       if ((uint32_t)(old + v) < old) atomicAdd(sa.hi + tex * 4 + ch, 1u);
     }
@@ -462,8 +463,8 @@ __device__ __forceinline__ v3 reflect_wall_std(const DeviceScene &sc, v3 ray, v3
   return normalize(rr);
 }
 
-// per-warp queue of the two-phase walk: structure of arrays, word k of entry j at [k * kQueueCap + j]; word 0 = photon index
-// (27 bits) | wall id << 27 | fresh << 31, words 1-3 the incoming ray, 4-6 the hit point (survivors only)
+// per-warp queues QL, QM of the two-phase walk: structure of arrays, word k of entry j at [k * kQueueCap + j]; word 0 = photon index
+// (27 bits) | id of the wall last hit << 27 | fresh << 31, words 1-3 a ray, 4-6 a point, word 7 = colour mask | bounce number << 3
 constexpr int kQueueCap = kTraceQueueCap, kQueueWords = kTraceQueueWords;
 
 // lane states: what the NEXT intersection result means for this lane
@@ -525,87 +526,164 @@ __global__ void __launch_bounds__(kSurfaceThreads, 1) trace_kernel(const __grid_
   const v3 light = V(sc.light[0], sc.light[1], sc.light[2]);
   const v3 rgb0 = media ? V(7.0f, 7.0f, 7.0f) : V(10.0f, 10.0f, 10.0f);   // the medium walk leaves rgb = 10-1-1-1
   // ---- two-phase walk (Mode A, reference layout, scene conditions checked by the host: DeviceScene::fast_ok) ----
-  // Phase F: 32 fresh photons in lock-step through the common path -- primary ray from the light that provably misses both spheres,
-  // wall hit, deposit, shadow ray, deposit, and the bounce that dies on normalize(0) (hazard H1, ~88% of them).  Everything a lane
-  // cannot finish there goes to the warp's queue: photons aimed at a sphere or at the caustic emitter as their bare index ("fresh"),
-  // survivors of the wall bounce with their state.  Phase G, when the queue is nearly full or the slice is used up: the general state
-  // machine below, its lanes refilled from the queue instead of the slice.  Per photon the operations are those of the machine.
+  // Phase F, lock-step: 32 photons at the same point of their life -- fresh from the light, or just past a wall bounce they survived --
+  // go through the common path together: [reflection off the wall,] a ray that provably misses both spheres, wall hit, deposit, shadow
+  // ray, deposit, and the bounce that dies on normalize(0) (hazard H1, ~88% of them).  Survivors of the bounce go to the warp's queue
+  // QL and come back as a later block; a photon whose ray cannot be shown to miss the spheres, or that belongs to the caustic emitter,
+  // goes to the queue QM.  Phase G, when QM is nearly full or nothing else is left: the general state machine below, its lanes
+  // refilled from QM instead of the slice.  Per photon the operations are those of the machine, in the same order.
   constexpr bool kTwoPhase = kStd && !kRec;
   const bool two_phase = kTwoPhase && sc.fast_ok && sk.queue != nullptr && warp >= vol_warps;
-  uint32_t *const q = sk.queue + ((size_t)blockIdx.x * (kSurfaceThreads / 32) + warp) * kQueueWords;
-  int qn = 0;   // entries in the queue (warp-uniform)
+  uint32_t *const ql_base = sk.queue + ((size_t)blockIdx.x * (kSurfaceThreads / 32) + warp) * kQueueWords;
+  uint32_t *const qm_base = ql_base + 8 * kQueueCap;
+  int ql = 0, qm = 0;   // entries in the queues (warp-uniform)
   // first-bounce energy of a channel the wall's colour lets through: min(1, rgb0) * 1 / sqrt(1) * 5 with the machine's operations
   const float e1 = fminf(1.0f, rgb0.x) * 1.0f * sc.inv_sqrt_bounce[1] * 5.0f;
   const uint32_t v1 = __float2uint_rn(e1 * (float)kHitScale);
-  float4 td_next = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-  if (kTwoPhase && two_phase && cur + lane < end) td_next = __ldg(table + cur + lane);
-
   for (;;) {
     if (kTwoPhase && two_phase) {
-      while (cur < end && qn <= kQueueCap - 32) {
-        const long long gi = cur + lane;
-        const bool act = gi < end;
-        cur = cur + 32 < end ? cur + 32 : end;
-        const float4 td = td_next;
-        if (cur + lane < end) td_next = __ldg(table + cur + lane);   // the next block's rows are in flight under this block
-        bool push_fresh = false, push_post = false;
-        v3 fr = V(0.0f, 0.0f, 0.0f), fP = fr;
-        int fid = 0;
-        if (act) {
-          fr = table_direction(td);
-          // the primary ray leaves the light: sphere terms that do not depend on the ray come from the host (same operations).  A sphere
-          // is out when D <= 0, or when B >= 0 with the light outside it (light_C >= 0, part of fast_ok: sign = -1, so the root
-          // -B - sqrt(D) is <= 0 and checkDistance rejects it) -- pure FP32 logic, no geometry; anything else goes to the machine.
-          const float A = dot(fr, fr);
-          bool aimed = (int)gi < 100;   // CAUSTICS_PHOTONS
-#pragma unroll
-          for (int i = 0; i < 2; i++) {
-            const float B = -2.0f * dot(V(sc.light_s[i][0], sc.light_s[i][1], sc.light_s[i][2]), fr);
-            const float D = B * B - 4.0f * A * sc.light_C[i];
-            aimed = aimed | ((D > 0.0f) & !(B >= 0.0f));
+      bool have_next = false;
+      float4 td_next = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      // QL entry: the incoming ray and the hit point of the bounce just survived, the wall, the colour mask and bounce number that come
+      // next; QM entry: the ray about to be traced and its origin with the mask / bounce number it has now, or a bare index (bit 31)
+      auto push = [&](bool to_l, bool to_m, int index, int wall, bool fresh, v3 r, v3 pt, int mk, int bn) {
+        const unsigned ml = __ballot_sync(0xffffffffu, to_l), mm = __ballot_sync(0xffffffffu, to_m);
+        if (to_l | to_m) {
+          uint32_t *const qb = to_l ? ql_base : qm_base;
+          const int j = to_l ? ql + __popc(ml & lt_mask) : qm + __popc(mm & lt_mask);
+          qb[j] = (uint32_t)index | ((uint32_t)wall << 27) | (fresh ? 0x80000000u : 0u);
+          if (!fresh) {
+            qb[1 * kQueueCap + j] = __float_as_uint(r.x); qb[2 * kQueueCap + j] = __float_as_uint(r.y); qb[3 * kQueueCap + j] = __float_as_uint(r.z);
+            qb[4 * kQueueCap + j] = __float_as_uint(pt.x); qb[5 * kQueueCap + j] = __float_as_uint(pt.y); qb[6 * kQueueCap + j] = __float_as_uint(pt.z);
+            qb[7 * kQueueCap + j] = (uint32_t)(mk | (bn << 3));
           }
-          if (aimed) push_fresh = true;
-          else {
-            float dist = 999999.9f;
-            int best = -1;
-            ray_walls_std(sc, fr, light, dist, best);
-            if (best >= 0) {   // bounces == 1
-              const int id = best & 7;
-              fP = add(mul(fr, dist), light);
-              {   // the first bounce's energy: e1 in the wall's colour channels (getColor: green wall 0, red wall 2), PMK:1296-1298
-                const v3 e = V(id == 0 ? 0.0f : e1, id == 2 ? 0.0f : e1, (id == 0 || id == 2) ? 0.0f : e1);
-                store_photon_wall_std(sk, sa, id, fP, false, id == 0 ? 1 : (id == 2 ? 0 : 3), v1, e);
+        }
+        ql += __popc(ml); qm += __popc(mm);
+        __syncwarp();
+      };
+      for (;;) {
+        if (qm > kQueueCap - 32) break;   // a block may add 32 entries to QM: the machine drains it first
+        if (ql >= 32 || (cur >= end && ql > 0)) {
+          // ---- a block of survivors: the rest of their wall bounce (PMK:1365-1369), then the next one ----
+          const int n = ql < 32 ? ql : 32;
+          const bool act = lane < n;
+          int index = 0, b = 2, mask = 7, id_prev = 0;
+          v3 ray = V(0.0f, 0.0f, 0.0f), org = ray;
+          if (act) {
+            const int j = ql - 1 - lane;
+            const uint32_t w0q = ql_base[j], w7q = ql_base[7 * kQueueCap + j];
+            index = (int)(w0q & 0x07ffffffu); id_prev = (int)(w0q >> 27) & 7;
+            mask = (int)(w7q & 7u); b = (int)(w7q >> 3);
+            const v3 rin = V(__uint_as_float(ql_base[1 * kQueueCap + j]), __uint_as_float(ql_base[2 * kQueueCap + j]), __uint_as_float(ql_base[3 * kQueueCap + j]));
+            org = V(__uint_as_float(ql_base[4 * kQueueCap + j]), __uint_as_float(ql_base[5 * kQueueCap + j]), __uint_as_float(ql_base[6 * kQueueCap + j]));
+            ray = reflect_wall_std(sc, rin, org, id_prev, std_axis(id_prev));
+          }
+          ql -= n;
+          __syncwarp();   // the entries are read before this block's survivors overwrite them
+          bool push_l = false, push_m = false;
+          v3 P2 = org;
+          int id = id_prev, mask2 = mask;
+          if (act) {
+            // A sphere is out when raySphere finds D <= 0, or B >= 0 with the origin outside it (sign = -1: the root -B - sqrt(D) is <= 0 and
+            // checkDistance rejects it) -- FP32 logic on raySphere's own terms, no geometry; anything else is the machine's business
+            const float A = dot(ray, ray);
+            bool aimed = false;
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+              const v3 sv = sub(V(sc.sph[i][0], sc.sph[i][1], sc.sph[i][2]), org);
+              const float B = -2.0f * dot(sv, ray);
+              const float C = dot(sv, sv) - sc.sph_r2[i];
+              const float D = B * B - 4.0f * A * C;
+              aimed = aimed | ((D > 0.0f) & !((B >= 0.0f) & !(C < -0.00001f)));   // (double)C < -0.00001 <=> C < (float)-0.00001 for a float C
+            }
+            if (aimed) push_m = true;
+            else {
+              float dist = 999999.9f;
+              int best = -1;
+              ray_walls_std(sc, ray, org, dist, best);
+              if (best >= 0) {   // b <= 5 by construction
+                id = best & 7;
+                P2 = add(mul(ray, dist), org);
+                // getColor + PMK:1298: a channel keeps min(1, previous >= 1) = 1, or is 0 from the first coloured wall on; times 1/sqrt(b), times 5
+                mask2 = mask & (id == 0 ? 2 : (id == 2 ? 1 : 7));
+                const float eb = 1.0f * 1.0f * sc.inv_sqrt_bounce[b] * 5.0f;
+                {
+                  const v3 e = V((mask2 & 1) ? eb : 0.0f, (mask2 & 2) ? eb : 0.0f, (mask2 & 4) ? eb : 0.0f);
+                  store_photon_wall_std(sk, sa, id, P2, false, mask2 == 7 ? 3 : (mask2 == 2 ? 1 : 0), mask2 ? __float2uint_rn(eb * (float)kHitScale) : 0u, e);
+                }
+                const v3 o2 = add(P2, mul(ray, 0.00001f));
+                float d2 = 999999.9f;
+                int b2 = -1;
+                const bool skippable = (comp(ray, std_axis(id)) * sc.wall_side[id] < 0.0f) & (fmaxf(fmaxf(fabsf(o2.x), fabsf(o2.y)), fabsf(o2.z)) <= 16.0f);
+                const unsigned need = skippable ? sc.shadow_need[id] : 3u;
+                if (need & 1u) ray_sphere(sc, 0, ray, o2, A, d2, b2);
+                if (need & 2u) ray_sphere(sc, 1, ray, o2, A, d2, b2);
+                ray_walls_std(sc, ray, o2, d2, b2);
+                if (b2 < 0 || b2 >= 8)   // a miss keeps the primary hit's ids (stale, as in the reference); a sphere stores nothing
+                  store_photon_wall_std(sk, sa, b2 >= 0 ? (b2 & 7) : id, add(mul(ray, d2), o2), true, 3, 0u, V(-0.25f, -0.25f, -0.25f));
+                const float wd = comp(P2, std_axis(id)) - sc.pl_off[id];
+                const float wdd = wd * wd;
+                push_l = !(wdd == 0.0f || wdd != wdd) && b < 5;   // after the fifth bounce the loop condition ends the photon (PMK:1289)
               }
-              // shadowPhoton: the spheres that lie wholly on the light's side of the wall just crossed cannot be hit again
-              // (DeviceScene::shadow_need, argued in pm_api.cu make_device_scene); the others are tested as usual
-              const v3 o2 = add(fP, mul(fr, 0.00001f));
-              float d2 = 999999.9f;
-              int b2 = -1;
-              const unsigned need = sc.shadow_need[id];
-              if (need & 1u) ray_sphere(sc, 0, fr, o2, A, d2, b2);
-              if (need & 2u) ray_sphere(sc, 1, fr, o2, A, d2, b2);
-              ray_walls_std(sc, fr, o2, d2, b2);
-              if (b2 < 0 || b2 >= 8)   // a miss keeps the primary hit's ids (stale, as in the reference); a sphere stores nothing
-                store_photon_wall_std(sk, sa, b2 >= 0 ? (b2 & 7) : id, add(mul(fr, d2), o2), true, 3, 0u, V(-0.25f, -0.25f, -0.25f));
-              const float wd = comp(fP, std_axis(id)) - sc.pl_off[id];
-              const float wdd = wd * wd;
-              if (!(wdd == 0.0f || wdd != wdd)) { push_post = true; fid = id; }
             }
           }
-        }
-        const unsigned mpush = __ballot_sync(0xffffffffu, push_fresh | push_post);
-        if (push_fresh | push_post) {
-          const int j = qn + __popc(mpush & lt_mask);
-          q[j] = (uint32_t)(int)gi | ((uint32_t)fid << 27) | (push_fresh ? 0x80000000u : 0u);
-          if (push_post) {
-            q[1 * kQueueCap + j] = __float_as_uint(fr.x); q[2 * kQueueCap + j] = __float_as_uint(fr.y); q[3 * kQueueCap + j] = __float_as_uint(fr.z);
-            q[4 * kQueueCap + j] = __float_as_uint(fP.x); q[5 * kQueueCap + j] = __float_as_uint(fP.y); q[6 * kQueueCap + j] = __float_as_uint(fP.z);
+          push(push_l, push_m, index, push_l ? id : id_prev, false, ray, push_l ? P2 : org, push_l ? mask2 : mask, push_l ? b + 1 : b);
+        } else if (cur < end) {
+          // ---- a block of fresh photons: the same path from the light, with what is known about it ----
+          if (!have_next) { if (cur + lane < end) td_next = __ldg(table + cur + lane); have_next = true; }
+          const long long gi = cur + lane;
+          const bool act = gi < end;
+          cur = cur + 32 < end ? cur + 32 : end;
+          const float4 td = td_next;
+          if (cur + lane < end) td_next = __ldg(table + cur + lane);   // the next block's rows are in flight under this block
+          bool push_l = false, push_m = false;
+          v3 fr = V(0.0f, 0.0f, 0.0f), fP = fr;
+          int fid = 0;
+          if (act) {
+            fr = table_direction(td);
+            // raySphere's ray-independent terms come from the host (same operations); the light is outside both spheres (light_C >= 0,
+            // part of fast_ok), so the rejection test is D <= 0 or B >= 0
+            const float A = dot(fr, fr);
+            bool aimed = (int)gi < 100;   // CAUSTICS_PHOTONS
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+              const float B = -2.0f * dot(V(sc.light_s[i][0], sc.light_s[i][1], sc.light_s[i][2]), fr);
+              const float D = B * B - 4.0f * A * sc.light_C[i];
+              aimed = aimed | ((D > 0.0f) & !(B >= 0.0f));
+            }
+            if (aimed) push_m = true;
+            else {
+              float dist = 999999.9f;
+              int best = -1;
+              ray_walls_std(sc, fr, light, dist, best);
+              if (best >= 0) {   // bounces == 1
+                const int id = best & 7;
+                fP = add(mul(fr, dist), light);
+                {   // the first bounce's energy: e1 in the wall's colour channels (getColor: green wall 0, red wall 2), PMK:1296-1298
+                  const v3 e = V(id == 0 ? 0.0f : e1, id == 2 ? 0.0f : e1, (id == 0 || id == 2) ? 0.0f : e1);
+                  store_photon_wall_std(sk, sa, id, fP, false, id == 0 ? 1 : (id == 2 ? 0 : 3), v1, e);
+                }
+                // shadowPhoton: a ray that has just crossed the wall's plane from the light's side cannot come back to a sphere that lies
+                // wholly on that side (DeviceScene::shadow_need, argued in pm_api.cu); the other spheres are tested as usual
+                const v3 o2 = add(fP, mul(fr, 0.00001f));
+                float d2 = 999999.9f;
+                int b2 = -1;
+                const unsigned need = fmaxf(fmaxf(fabsf(o2.x), fabsf(o2.y)), fabsf(o2.z)) <= 16.0f ? sc.shadow_need[id] : 3u;
+                if (need & 1u) ray_sphere(sc, 0, fr, o2, A, d2, b2);
+                if (need & 2u) ray_sphere(sc, 1, fr, o2, A, d2, b2);
+                ray_walls_std(sc, fr, o2, d2, b2);
+                if (b2 < 0 || b2 >= 8)
+                  store_photon_wall_std(sk, sa, b2 >= 0 ? (b2 & 7) : id, add(mul(fr, d2), o2), true, 3, 0u, V(-0.25f, -0.25f, -0.25f));
+                const float wd = comp(fP, std_axis(id)) - sc.pl_off[id];
+                const float wdd = wd * wd;
+                if (!(wdd == 0.0f || wdd != wdd)) { push_l = true; fid = id; }
+              }
+            }
           }
-        }
-        qn += __popc(mpush);
-        __syncwarp();
+          push(push_l, push_m, (int)gi, fid, push_m, fr, fP, fid == 0 ? 2 : (fid == 2 ? 1 : 7), 2);
+        } else break;   // no fresh photons, QL empty
       }
-      if (qn == 0) break;   // the slice is used up as well
+      if (qm == 0) break;   // nothing fresh, QL and QM empty
     }
 
     // ---- phase G / the only phase otherwise: the state machine ----
@@ -617,29 +695,30 @@ __global__ void __launch_bounds__(kSurfaceThreads, 1) trace_kernel(const __grid_
       // ---- refill idle lanes from the warp's slice (emitPhotons prologue, PMK:1229-1237, :1274-1280) or from its queue.  The
       //      prologue runs with only the idle lanes active, so it is deferred until a quarter of the warp is idle ----
       const unsigned idle = __ballot_sync(0xffffffffu, state == ST_IDLE);
-      const long long avail = (kTwoPhase && two_phase) ? (long long)qn : end - cur;
+      const long long avail = (kTwoPhase && two_phase) ? (long long)qm : end - cur;
       if (avail > 0 && (__popc(idle) >= ((kTwoPhase && two_phase) ? kQueueRefillLanes : kRefillLanes) || idle == 0xffffffffu)) {
         const int rank = __popc(idle & lt_mask);
         if (state == ST_IDLE && rank < avail) {
           long long cand = cur + rank;
           bool resumed = false;
           if (kTwoPhase && two_phase) {
-            const int j = qn - 1 - rank;
-            const uint32_t w0q = q[j];
+            const int j = qm - 1 - rank;
+            const uint32_t w0q = qm_base[j];
             cand = (long long)(w0q & 0x07ffffffu);
             if (!(w0q & 0x80000000u)) {
-              // a survivor of the first wall bounce: the rest of its bounce (PMK:1365-1369) -- the machine's wall branch, die-check passed
+              // past a wall bounce, about to trace the reflected ray (top of the bounce loop, PMK:1289): the state phase F left it in
               resumed = true;
-              const int id = (int)(w0q >> 27) & 7, wax = std_axis(id);
-              const v3 rin = V(__uint_as_float(q[1 * kQueueCap + j]), __uint_as_float(q[2 * kQueueCap + j]), __uint_as_float(q[3 * kQueueCap + j]));
-              P = V(__uint_as_float(q[4 * kQueueCap + j]), __uint_as_float(q[5 * kQueueCap + j]), __uint_as_float(q[6 * kQueueCap + j]));
-              ray = reflect_wall_std(sc, rin, P, id, wax);
+              const uint32_t w7q = qm_base[7 * kQueueCap + j];
+              ray = V(__uint_as_float(qm_base[1 * kQueueCap + j]), __uint_as_float(qm_base[2 * kQueueCap + j]), __uint_as_float(qm_base[3 * kQueueCap + j]));
+              P = V(__uint_as_float(qm_base[4 * kQueueCap + j]), __uint_as_float(qm_base[5 * kQueueCap + j]), __uint_as_float(qm_base[6 * kQueueCap + j]));
               index = (int)cand;
-              rgb = mul(mul(mul(get_color(rgb0, 1, id), 1.0f), sc.inv_sqrt_bounce[1]), 5.0f);
+              bounces = (int)(w7q >> 3);
+              const float ep = 1.0f * 1.0f * sc.inv_sqrt_bounce[(bounces - 1) & 7] * 5.0f;   // the colour the previous bounce left
+              rgb = V((w7q & 1u) ? ep : 0.0f, (w7q & 2u) ? ep : 0.0f, (w7q & 4u) ? ep : 0.0f);
               prev = P; org = P;
-              bounces = 2; seq = (media ? 3 : 0) + 2;
+              seq = (media ? 3 : 0) + 2 * (bounces - 1);
               caustics = false; new_point = true;
-              h.type = 1; h.idx = id;
+              h.type = 1; h.idx = (int)(w0q >> 27) & 7;
               state = ST_PRIMARY;
             }
           }
@@ -659,10 +738,10 @@ __global__ void __launch_bounds__(kSurfaceThreads, 1) trace_kernel(const __grid_
           }
         }
         const int took = __popc(idle) < avail ? __popc(idle) : (int)avail;
-        if (kTwoPhase && two_phase) qn -= took; else cur += took;
+        if (kTwoPhase && two_phase) qm -= took; else cur += took;
       }
       if (__ballot_sync(0xffffffffu, state != ST_IDLE) == 0u) {
-        if (((kTwoPhase && two_phase) ? (long long)qn : end - cur) <= 0) break;
+        if (((kTwoPhase && two_phase) ? (long long)qm : end - cur) <= 0) break;
         continue;
       }
       if (state == ST_IDLE) continue;
