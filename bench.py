@@ -53,7 +53,7 @@ def parse():
                     help="Mode A, N > 1: how the accumulators are summed -- peer (default): our kernel pulls them over NVLink peer "
                          "memory inside pm_build_map (CUDA IPC between the ranks); nccl: dist.all_reduce (round 1's path)")
     ap.add_argument("--trace-sms", type=int, default=-1,
-                    help="CTAs of the persistent trace kernel (pm_set_trace_sms); -1 (default): every SM at N <= 2, all but 16 at N >= 4, "
+                    help="CTAs of the persistent trace kernel (pm_set_trace_sms); -1 (default): every SM at N <= 2, all but 16 at N = 4, all but 32 at N = 8, "
                          "which leaves room for the previous frame's exchange + map build + render on the second stream")
     ap.add_argument("--no-extras", action="store_true", help="skip Mode B at N, config 5 and the single-GPU side benchmarks")
     ap.add_argument("--passes", type=int, default=1,
@@ -367,7 +367,10 @@ def main():
     y0, y1 = pmdist.row_band_uneven(H, rank, world)
     rows = y1 - y0
     m.set_row_band(y0, y1)
-    trace_sms = a.trace_sms if a.trace_sms >= 0 else (0 if world <= 2 else torch.cuda.get_device_properties(local).multi_processor_count - 16)
+    # measured (gpurun, B200): N = 4 is fastest with 132 of 148 trace CTAs, N = 8 with 116 -- the shorter the trace, the more of the frame
+    # is the chain of small kernels behind it, and the more SMs that chain needs to keep up
+    trace_sms = a.trace_sms if a.trace_sms >= 0 else (
+        0 if world <= 2 else torch.cuda.get_device_properties(local).multi_processor_count - (16 if world < 8 else 32))
     m.set_trace_sms(trace_sms)
 
     # N > 1: the ranks' exchange blocks are mapped into each other (CUDA IPC) and the frame lives on rank 0, every rank
