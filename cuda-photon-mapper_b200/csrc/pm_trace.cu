@@ -4,15 +4,18 @@
 // emit_photons_kernel/emitPhotons (PMK:1464-1480, :1215-1375).  Per photon the FP32 operation order is
 // identical to the sequential oracle (pm_math.cuh), but the work is organised for the hardware:
 //   * the MWC generator is index-addressed (jump-ahead), so the table fill and the medium-scatter draws are
-//     fully parallel yet bit-identical to the reference's serial stream;
-//   * the medium walk (3 fixed steps, PMK:1239-1272) does not influence the surface walk.  It is bound by L2 atomics and leaves
-//     the issue slots idle, the surface walk is bound by instruction issue and makes no L2 traffic: trace_kernel is warp-specialised,
-//     warps [0, vol_warps) of every 1024-thread CTA run the medium walk of the CTA's photon range, the other warps the surface
-//     walk (PM_TRACE_SPLIT keeps the medium walk as its own launch, volume_kernel, for measurement);
-//   * the surface walk is persistent, one CTA per SM: every lane runs a small state machine with ONE ray-scene intersection site
-//     per iteration, and a lane that finishes its photon is refilled from its warp's contiguous photon slice.  Primary rays,
-//     shadow rays, wall bounces and the mirror/glass chain therefore share the same instructions instead of diverging (the first
-//     version of this kernel ran 17 of 32 lanes on average and stalled on instruction fetch);
+//     fully parallel yet bit-identical to the reference's serial stream; a table row also carries 1/|row| (table_row);
+//   * the medium walk (3 fixed steps, PMK:1239-1272) does not influence the surface walk.  trace_kernel is warp-specialised: warps
+//     [0, vol_warps) of every 1024-thread CTA run the medium walk of the CTA's photon range, the other warps the surface walk
+//     (PM_TRACE_SPLIT keeps the medium walk as its own launch, volume_kernel, for measurement).  When only deposit counts are wanted
+//     (Mode A) the medium walk is a floating-point filter: approximate arithmetic, exact redo next to voxel boundaries
+//     (volume_photon_fast; PM_TRACE_EXACT_MEDIUM switches it off);
+//   * the surface walk is persistent, one CTA per SM.  Its general form is a state machine: every lane has ONE ray-scene intersection
+//     site per iteration, and a lane that finishes its photon is refilled.  Mode A on a scene with the reference's object layout runs
+//     in two phases instead (PM_TRACE_ONE_PHASE switches that off): 32 photons at the same point of their life go through the common
+//     path in lock-step -- a ray that provably misses the spheres, wall hit, deposit, shadow ray, deposit, the bounce that dies on
+//     normalize(0) --, survivors of the bounce are queued and come back as a block of their own, and only the photons whose ray may
+//     hit a sphere are handed to the state machine (through a second queue);
 //   * deposits go into exact int64 fixed-point accumulators keyed by wall voxel (pm_layout.h) instead of ~65 racy float RMWs per
 //     photon; the wall accumulators are privatised per CTA in shared memory (184 320 B: 20 480 entries as 32-bit halves, because
 //     shared memory has no native 64-bit add, plus 5 120 shadow-photon counters) and flushed once per CTA; medium deposits are
