@@ -30,6 +30,13 @@ m.init_random_numbers_philox(7)
 m.clear_map(); m.trace(0.0, media=True); m.build_map()
 m.trace(0.0, media=True, split=True)                      # the two-launch form of the trace
 m.set_volume_warps(3); m.trace(0.0, media=True)           # fused, another warp split
+m.set_volume_warps(7)
+m.trace(0.0, media=True, one_phase=True); m.trace(0.0, media=True, exact_medium=True)   # the cross-check forms of the Mode A trace
+# the two-phase walk with queues that fill and drain: many photons on ONE CTA (8 000 per warp: ~240 queued for the state machine)
+m2 = pmb200.PhotonMapper(n_photons=200000)
+m2.init_random_numbers(); m2.set_trace_sms(1)
+m2.clear_map(); m2.trace(0.0, media=True); m2.trace(1.3, media=False); m2.build_map()
+m2.sync(); m2.close()
 pin = [torch.empty((h, w, 4), dtype=torch.uint8).pin_memory() for _ in range(2)]
 tk = [m.frame_async(w, h, pin[i & 1], t=0.1 * i, emit=True, interp=True, media=True) for i in range(2)]   # pipelined frames
 for t_ in tk:
