@@ -612,10 +612,17 @@ __global__ void __launch_bounds__(kQueryThreads) knn_render_kernel(const __grid_
   // (same wall / same march step): searching within 1.2x the neighbour's radius first skips the phase in which every
   // candidate passes.  If fewer than k photons lie within the hinted radius the search is repeated without it, so the
   // result is exact either way.  Hints: lane i holds the hint of march step i, lane 10 the wall hint.
-  constexpr int kRun = 16, kRows = kQueryThreads / 32;
+#ifndef PM_KNN_RUN
+#define PM_KNN_RUN 16
+#endif
+  constexpr int kRun = PM_KNN_RUN, kRows = kQueryThreads / 32;
   const int tiles_x = (width + kRun - 1) / kRun, tiles_y = (nrows + kRows - 1) / kRows;
-  auto search = [&](const TreeView &tv, const float *sbox, float qx, float qy, float qz, float hint_r2, TopK<KL> &top) -> float {
-    float lim = fminf(max_r2, hint_r2 * 1.44f);
+  // `step` = distance of this query from the one the hint belongs to: its k nearest photons lie within sqrt(hint) + step of this
+  // query (triangle inequality), so that radius -- with a margin for the FP32 roundings of both distances -- needs no retry in exact
+  // arithmetic and is usually tighter than the 1.2x guess; the retry below still covers every rounding case
+  auto search = [&](const TreeView &tv, const float *sbox, float qx, float qy, float qz, float hint_r2, float step, TopK<KL> &top) -> float {
+    const float tri = (__fsqrt_rn(hint_r2) + step) * 1.00001f;
+    float lim = fminf(max_r2, fminf(hint_r2 * 1.44f, tri * tri));
     KSTAT(6, lim < max_r2 ? 1 : 0);
     u64 kth;
     for (;;) {
@@ -637,6 +644,7 @@ __global__ void __launch_bounds__(kQueryThreads) knn_render_kernel(const __grid_
    const int row = (int)(tile / tiles_x) * kRows + (int)(u % kRows), x0 = (int)(tile % tiles_x) * kRun;
    if (row >= nrows) continue;
    float hint = inf;
+   v3 ray_prev = V(0.0f, 0.0f, 0.0f), P_prev = ray_prev;
    for (int px = x0; px < width && px < x0 + kRun; px++) {
     const int py = y0 + row * y_step;
     const long long pix = (long long)py * width + px;
@@ -648,12 +656,15 @@ __global__ void __launch_bounds__(kQueryThreads) knn_render_kernel(const __grid_
     const v3 origin = V(0.0f, 0.0f, 0.0f);
     v3 ray = V((float)((double)__fdiv_rn(x, sc.sz_img) - 0.5), (float)(-((double)__fdiv_rn(y, sc.sz_img) - 0.5)), 1.0f);
     TopK<KL> top;
+    const v3 dray = sub(ray, ray_prev);
+    const float dr = __fsqrt_rn(dot(dray, dray)) * 0.6001f;   // march step i of neighbouring pixels: (i + 1) * 0.6 * |ray - ray_prev| apart
+    ray_prev = ray;
     if (media) {
       v3 prev = origin;
 #pragma unroll 1
       for (int i = 0; i < 10; i++) {
         prev = add(mul(ray, 0.6f), prev);
-        float r2 = search(tvv, sbox_v, prev.x, prev.y, prev.z, __shfl_sync(0xffffffffu, hint, i), top);
+        float r2 = search(tvv, sbox_v, prev.x, prev.y, prev.z, __shfl_sync(0xffffffffu, hint, i), (float)(i + 1) * dr, top);
         if (lane == i) hint = r2;
         float4 e = knn_radiance<KL>(top, k, pow_v, 1, lane);
         rgb = add(rgb, mul(V(e.x, e.y, e.z), w_vol));
@@ -668,7 +679,9 @@ __global__ void __launch_bounds__(kQueryThreads) knn_render_kernel(const __grid_
       else if (h.type == 0 && h.idx == 0) follow_specular(sc, ray, origin, h, P, 0);
       if (h.hit && h.type == 1) {   // warp-uniform: every lane traced the same ray
         wall = true;
-        float r2 = search(tvs, sbox_s, P.x, P.y, P.z, __shfl_sync(0xffffffffu, hint, 10), top);
+        const v3 dP = sub(P, P_prev);
+        float r2 = search(tvs, sbox_s, P.x, P.y, P.z, __shfl_sync(0xffffffffu, hint, 10), __fsqrt_rn(dot(dP, dP)), top);
+        P_prev = P;
         if (lane == 10) hint = r2;
         float4 e = knn_radiance<KL>(top, k, pow_s, 0, lane);
         v3 c = mul(V(e.x, e.y, e.z), w_surf);
@@ -1127,9 +1140,11 @@ cudaError_t knn_build(KnnMap &m, const float4 *pos, const float4 *power, long lo
   }
   m.sorted = cur;
   KCK(cudaGetLastError());
-  unsigned long long nv = 0;
-  KCK(cudaMemcpyAsync(&nv, m.d_count, sizeof(nv), cudaMemcpyDeviceToHost, st));
-  KCK(cudaStreamSynchronize(st));   // the number of kept points sizes the tree
+  unsigned long long nv = (unsigned long long)n;   // an unfiltered build keeps every row: nothing to wait for
+  if (filter) {
+    KCK(cudaMemcpyAsync(&nv, m.d_count, sizeof(nv), cudaMemcpyDeviceToHost, st));
+    KCK(cudaStreamSynchronize(st));   // the number of kept points sizes the tree
+  }
   m.n = (long long)nv; m.n_sorted_pad = n_pad;
   if (m.n == 0) return cudaSuccess;
   // level geometry
