@@ -16,7 +16,9 @@
 //                   node with six coalesced loads.  The two top levels (<= 1056 boxes, 25 KB) are staged into shared
 //                   memory once per CTA with a TMA bulk copy (cp.async.bulk + mbarrier).
 //   query           one warp per query.  Depth-first, nearest child first (warp min-reduction over the lanes' box
-//                   distances), pruned by the current k-th distance.  Candidates of a leaf that beat the current k-th
+//                   distances), pruned by the current k-th distance; the lowest levels are explicit nested loops (a node's 32
+//                   children are evaluated once, qualifying children visited from the distances the lanes hold).  In the renderer
+//                   the neighbouring pixel's k-th distance bounds the search through the triangle inequality.  Candidates of a leaf that beat the current k-th
 //                   key are appended to a per-warp shared-memory buffer; every 32 candidates the buffer is sorted (bitonic,
 //                   shuffles) and merged into the sorted top-K list that lives in registers (K/32 keys per lane).
 //                   Keys are (bits(d2) << 32 | original index): the k smallest keys are exactly the oracle's answer.
