@@ -818,9 +818,9 @@ int pm_knn_level_host(pm_context *c, int which, int level, int64_t *count, float
   CK(c, cudaStreamSynchronize(c->stream));
   if (count) *count = m.cnt[level];
   if (boxes6)
-    for (int a = 0; a < 6; a++)
-      CK(c, cudaMemcpy(boxes6 + (size_t)a * m.cnt[level], m.boxes + m.off[level] + (size_t)a * m.pad[level], sizeof(float) * (size_t)m.cnt[level],
-                       cudaMemcpyDeviceToHost));
+    for (int a = 0; a < 6; a++)   // device layout: six floats per entity; the caller gets six arrays
+      CK(c, cudaMemcpy2D(boxes6 + (size_t)a * m.cnt[level], sizeof(float), m.boxes + m.off[level] + a, 6 * sizeof(float), sizeof(float),
+                         (size_t)m.cnt[level], cudaMemcpyDeviceToHost));
   return PM_OK;
 }
 

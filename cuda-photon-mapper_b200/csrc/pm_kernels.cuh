@@ -69,7 +69,7 @@ struct KnnMap {
   long long n = 0;                 // points in the map (after filtering)
   int levels = 0;                  // box levels, level 0 = leaves of 32 points
   long long cnt[8] = {0}, pad[8] = {0};
-  size_t off[8] = {0};             // float offset of each level's six box arrays inside `boxes`
+  size_t off[8] = {0};             // float offset of each level's boxes (6 floats per entity) inside `boxes`
   float *boxes = nullptr; size_t cap_boxes = 0;
   uint32_t *keys[2] = {nullptr, nullptr}, *vals[2] = {nullptr, nullptr};
   size_t cap_keys[2] = {0, 0}, cap_vals[2] = {0, 0};

@@ -12,8 +12,8 @@
 //   spos[n]         float4 (x, y, z, bits(original record index)) in sorted order: a leaf = 32 consecutive rows = one
 //                   coalesced 512-byte load by one warp
 //   tree            implicit and 32-wide: level 0 = leaves, level l+1 groups 32 entities of level l; only axis-aligned
-//                   boxes are stored, as six float arrays per level, so the 32 lanes of a warp test the 32 children of a
-//                   node with six coalesced loads.  The two top levels (<= 1056 boxes, 25 KB) are staged into shared
+//                   boxes are stored, six floats per entity, so the 32 lanes of a warp test the 32 children of a node with
+//                   three 8-byte loads each (six separate arrays cost twice the instructions: address arithmetic).  The two top levels (<= 1056 boxes, 25 KB) are staged into shared
 //                   memory once per CTA with a TMA bulk copy (cp.async.bulk + mbarrier).
 //   query           one warp per query.  Depth-first, nearest child first (warp min-reduction over the lanes' box
 //                   distances), pruned by the current k-th distance; the lowest levels are explicit nested loops (a node's 32
@@ -29,6 +29,14 @@
 #include "pm_kernels.cuh"
 
 namespace pm {
+
+// box e of a level: six floats (lx, ly, lz, hx, hy, hz) at b + 6 e, read as three 8-byte loads (global or shared memory)
+__device__ __forceinline__ void load_box(const float *__restrict__ b, long long e, bool global, float &lx, float &ly, float &lz, float &hx,
+                                         float &hy, float &hz) {
+  const float2 *q = (const float2 *)b + 3 * e;
+  const float2 a = global ? __ldg(q) : q[0], c = global ? __ldg(q + 1) : q[1], d = global ? __ldg(q + 2) : q[2];
+  lx = a.x; ly = a.y; lz = c.x; hx = c.y; hy = d.x; hz = d.y;
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // Morton keys
@@ -242,7 +250,7 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint3
 }
 
 // sorted rows: (x, y, z, bits(original index)), and -- a warp's 32 rows being exactly one leaf -- the leaf boxes
-// (six arrays of length p_out; leaves >= n_out, the padding, stay empty)
+// (six floats per leaf, p_out leaves; leaves >= n_out, the padding, stay empty)
 __device__ __forceinline__ float warp_min(float v);
 __device__ __forceinline__ float warp_max(float v);
 __global__ void __launch_bounds__(256) permute_kernel(const float4 *__restrict__ pos, const uint32_t *__restrict__ vals, long long n,
@@ -260,7 +268,8 @@ __global__ void __launch_bounds__(256) permute_kernel(const float4 *__restrict__
   }
   lx = warp_min(lx); ly = warp_min(ly); lz = warp_min(lz); hx = warp_max(hx); hy = warp_max(hy); hz = warp_max(hz);
   if ((threadIdx.x & 31) == 0) {
-    boxes[e] = lx; boxes[p_out + e] = ly; boxes[2 * p_out + e] = lz; boxes[3 * p_out + e] = hx; boxes[4 * p_out + e] = hy; boxes[5 * p_out + e] = hz;
+    float2 *q = (float2 *)boxes + 3 * e;
+    q[0] = make_float2(lx, ly); q[1] = make_float2(lz, hx); q[2] = make_float2(hy, hz);
   }
 }
 
@@ -285,9 +294,12 @@ __global__ void __launch_bounds__(256) node_box_kernel(const float *__restrict__
   const float inf = cuda::std::numeric_limits<float>::infinity();
   float lx = inf, ly = inf, lz = inf, hx = -inf, hy = -inf, hz = -inf;
   long long c = e * 32 + lane;
-  if (e < n_out && c < n_in) { lx = in[c]; ly = in[p_in + c]; lz = in[2 * p_in + c]; hx = in[3 * p_in + c]; hy = in[4 * p_in + c]; hz = in[5 * p_in + c]; }
+  if (e < n_out && c < n_in) load_box(in, c, true, lx, ly, lz, hx, hy, hz);
   lx = warp_min(lx); ly = warp_min(ly); lz = warp_min(lz); hx = warp_max(hx); hy = warp_max(hy); hz = warp_max(hz);
-  if (lane == 0) { out[e] = lx; out[p_out + e] = ly; out[2 * p_out + e] = lz; out[3 * p_out + e] = hx; out[4 * p_out + e] = hy; out[5 * p_out + e] = hz; }
+  if (lane == 0) {
+    float2 *q = (float2 *)out + 3 * e;
+    q[0] = make_float2(lx, ly); q[1] = make_float2(lz, hx); q[2] = make_float2(hy, hz);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -354,7 +366,7 @@ struct TreeView {
   int levels;             // number of box levels (level 0 = leaves); 0 when n == 0
   long long cnt[8];       // entities per level
   long long pad[8];       // padded (multiple of 32) array length per level
-  const float *box[8];    // six arrays of length pad[l] each
+  const float *box[8];    // pad[l] entities of six floats (lx, ly, lz, hx, hy, hz) each
   int staged_from;        // levels >= staged_from are read from shared memory
   long long staged_floats;
   int staged_off[8];      // float offset of a staged level inside the shared-memory copy
@@ -412,14 +424,8 @@ __device__ __forceinline__ void knn_search(const TreeView &tv, const float *__re
   auto child_dist = [&](int cl, long long e) -> float {
     if (e >= tv.cnt[cl]) return cuda::std::numeric_limits<float>::infinity();
     float lx, ly, lz, hx, hy, hz;
-    if (cl >= tv.staged_from) {
-      const float *b = sbox + tv.staged_off[cl];
-      long long p = tv.pad[cl];
-      lx = b[e]; ly = b[p + e]; lz = b[2 * p + e]; hx = b[3 * p + e]; hy = b[4 * p + e]; hz = b[5 * p + e];
-    } else {
-      const float *b = tv.box[cl]; long long p = tv.pad[cl];
-      lx = __ldg(b + e); ly = __ldg(b + p + e); lz = __ldg(b + 2 * p + e); hx = __ldg(b + 3 * p + e); hy = __ldg(b + 4 * p + e); hz = __ldg(b + 5 * p + e);
-    }
+    if (cl >= tv.staged_from) load_box(sbox + tv.staged_off[cl], e, false, lx, ly, lz, hx, hy, hz);
+    else load_box(tv.box[cl], e, true, lx, ly, lz, hx, hy, hz);
     return box_dist2(lx, ly, lz, hx, hy, hz, qx, qy, qz);
   };
   // The two lowest levels are explicit loops: a node's 32 children are evaluated ONCE, every child that still qualifies is visited
@@ -836,8 +842,7 @@ __device__ __forceinline__ void batch_walk(const TreeView &tv, float4 *__restric
       const long long e = j * 32 + lane;
       bool ok = false;
       if (e < tv.cnt[cl]) {
-        const float *b = tv.box[cl]; const long long p = tv.pad[cl];
-        lx = __ldg(b + e); ly = __ldg(b + p + e); lz = __ldg(b + 2 * p + e); hx = __ldg(b + 3 * p + e); hy = __ldg(b + 4 * p + e); hz = __ldg(b + 5 * p + e);
+        load_box(tv.box[cl], e, true, lx, ly, lz, hx, hy, hz);
         const float dx = fmaxf(fmaxf(lx - bhx, 0.0f), blx - hx), dy = fmaxf(fmaxf(ly - bhy, 0.0f), bly - hy), dz = fmaxf(fmaxf(lz - bhz, 0.0f), blz - hz);
         ok = (dx * dx + dy * dy) + dz * dz <= max_lim;
       }
