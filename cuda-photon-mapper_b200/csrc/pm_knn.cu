@@ -265,6 +265,9 @@ __global__ void __launch_bounds__(256) permute_kernel(const float4 *__restrict__
     float4 p = pos[v];
     spos[i] = make_float4(p.x, p.y, p.z, __uint_as_float(v));
     lx = hx = p.x; ly = hy = p.y; lz = hz = p.z;
+  } else {   // rows of the padding leaves and the tail of the last leaf: NaN, so that a search needs no bounds test (no distance passes)
+    const float nan = __int_as_float(0x7fc00000);
+    spos[i] = make_float4(nan, nan, nan, 0.0f);
   }
   lx = warp_min(lx); ly = warp_min(ly); lz = warp_min(lz); hx = warp_max(hx); hy = warp_max(hy); hz = warp_max(hz);
   if ((threadIdx.x & 31) == 0) {
@@ -389,13 +392,15 @@ __device__ __forceinline__ void knn_search(const TreeView &tv, const float *__re
   u64 thr_key = kMaxKey;
   int npend = 0;
   if (tv.n <= 0) return;
+  // a NaN query is at distance NaN from every photon and finds nothing; it must not walk the tree either, where fmaxf drops the NaN
+  // and every box -- the empty padding boxes included -- comes out at distance 0
+  if (!(qx == qx && qy == qy && qz == qz)) return;
   KSTAT(4, 1);
 
   auto leaf = [&](long long e) {
-    long long i = e * 32 + lane;
     u64 key = kMaxKey;
-    if (i < tv.n) {
-      float4 p = __ldg(tv.spos + i);
+    {   // rows past the last photon are NaN (permute_kernel): their distance passes no test
+      float4 p = __ldg(tv.spos + (e * 32 + lane));
       float dx = p.x - qx, dy = p.y - qy, dz = p.z - qz;
       float d2 = (dx * dx + dy * dy) + dz * dz;
       if (d2 <= max_r2) key = ((u64)__float_as_uint(d2) << 32) | __float_as_uint(p.w);
@@ -421,8 +426,7 @@ __device__ __forceinline__ void knn_search(const TreeView &tv, const float *__re
   };
 
   // distance of this lane's child (entity e of level cl) from the query: infinity when the child does not exist
-  auto child_dist = [&](int cl, long long e) -> float {
-    if (e >= tv.cnt[cl]) return cuda::std::numeric_limits<float>::infinity();
+  auto child_dist = [&](int cl, long long e) -> float {   // e < pad[cl]: the padding entities are empty boxes, infinitely far away
     float lx, ly, lz, hx, hy, hz;
     if (cl >= tv.staged_from) load_box(sbox + tv.staged_off[cl], e, false, lx, ly, lz, hx, hy, hz);
     else load_box(tv.box[cl], e, true, lx, ly, lz, hx, hy, hz);
@@ -1165,7 +1169,7 @@ cudaError_t knn_build(KnnMap &m, const float4 *pos, const float4 *power, long lo
   KCK(ensure((void **)&m.vals[1], &m.cap_vals[1], sizeof(uint32_t) * n_pad));
   KCK(ensure((void **)&m.ghist, &m.cap_ghist, sizeof(uint32_t) * 256 * tiles));
   KCK(ensure((void **)&m.scan_sums, &m.cap_scan_sums, sizeof(uint32_t) * ((256 * tiles + kScanChunk - 1) / kScanChunk + 1)));
-  KCK(ensure((void **)&m.spos, &m.cap_spos, sizeof(float4) * n));
+  KCK(ensure((void **)&m.spos, &m.cap_spos, sizeof(float4) * (n + 2048)));   // whole (padded) leaves: rows past the last photon are NaN
   if (!m.d_count) KCK(cudaMalloc(&m.d_count, sizeof(unsigned long long)));
   KCK(cudaMemsetAsync(m.d_count, 0, sizeof(unsigned long long), st));
   morton_kernel<<<(unsigned)((n_pad + 255) / 256), 256, 0, st>>>(pos, n, n_pad, filter, curve, m.keys[0], m.vals[0], m.d_count);
