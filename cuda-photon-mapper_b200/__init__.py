@@ -56,6 +56,7 @@ def lib():
             "pm_scene_default": (None, [C.POINTER(Scene)]), "pm_set_scene": (i32, [vp, C.POINTER(Scene)]),
             "pm_get_scene": (i32, [vp, C.POINTER(Scene)]),
             "pm_position_objects": (i32, [C.POINTER(Scene), f32, C.POINTER(Scene)]),
+            "pm_trace_plan": (i32, [C.POINTER(Scene), f32, C.POINTER(i32), C.POINTER(C.c_uint32)]),
             "pm_set_photon_count": (i32, [vp, i64]), "pm_set_photon_range": (i32, [vp, i64, i64]),
             "pm_set_energy_scale": (i32, [vp, f32]),
             "pm_init_random_table": (i32, [vp]), "pm_init_random_table_philox": (i32, [vp, C.c_uint64]), "pm_set_random_table_host": (i32, [vp, vp, i64]),
@@ -122,6 +123,16 @@ def default_scene(sz_img=512, animate=1):
     s.sz_img = sz_img
     s.animate = animate
     return s
+
+
+def trace_plan(scene, t=0.0):
+    """(two_phase, [shadow_need of walls 0..4]): what a Mode A trace of `scene` at time t will do (pm_trace_plan; host side only)."""
+    tp = C.c_int32()
+    need = (C.c_uint32 * 5)()
+    rc = lib().pm_trace_plan(C.byref(scene), t, C.byref(tp), need)
+    if rc != 0:
+        raise PmError(f"pmb200 error {rc}")
+    return bool(tp.value), [int(x) for x in need]
 
 
 def _ptr(a):

@@ -132,6 +132,14 @@ void pm_scene_default(pm_scene *sc) {
   sc->sz_img = 512; sc->cam_ox = 0.0f; sc->cam_oy = 0.0f; sc->animate = 1;
 }
 
+int pm_trace_plan(const pm_scene *in, float t, int32_t *two_phase, uint32_t *shadow_need5) {
+  if (!in || !two_phase || !shadow_need5) return PM_ERR_ARG;
+  const DeviceScene d = make_device_scene(*in, t);
+  *two_phase = d.fast_ok;
+  for (int w = 0; w < PM_MAX_PLANES; w++) shadow_need5[w] = d.shadow_need[w];
+  return PM_OK;
+}
+
 int pm_position_objects(const pm_scene *in, float t, pm_scene *out) {
   if (!in || !out) return PM_ERR_ARG;
   *out = *in;

@@ -89,6 +89,11 @@ void pm_scene_default(pm_scene *scene);
 int  pm_set_scene(pm_context *ctx, const pm_scene *scene);
 int  pm_get_scene(const pm_context *ctx, pm_scene *scene);
 int  pm_position_objects(const pm_scene *in, float animTime, pm_scene *out);   /* PMK:1380-1404, host side */
+/* What a Mode A trace of this scene at animTime will do (host side, no device needed): *two_phase = 1 when the scene meets the conditions
+ * of the lock-step surface path (reference object layout, everything within [-8, 8], light >= 0.05 from every wall plane and outside the
+ * spheres; otherwise every photon goes through the general state machine -- same results); shadow_need5[w] bit i = the shadow ray behind
+ * wall w still has to test sphere i (0: the sphere lies wholly on the light's side of the wall, with margin, and is skipped) */
+int  pm_trace_plan(const pm_scene *in, float animTime, int32_t *two_phase, uint32_t *shadow_need5);
 int  pm_set_photon_count(pm_context *ctx, int64_t n_photons);                  /* table size, nrPhotons */
 int  pm_set_photon_range(pm_context *ctx, int64_t first, int64_t last);        /* this GPU traces [first,last) */
 int  pm_set_energy_scale(pm_context *ctx, float scale);   /* photon map is multiplied by this when built (1 = reference) */

@@ -50,3 +50,35 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "libpm_oracle" not in txt, f
+
+
+def test_trace_plan_host_logic(pm):
+    """pm_trace_plan (host side, no device): when the lock-step surface path is taken and which spheres a shadow ray may skip."""
+    sc = pm.default_scene()
+    two_phase, need = pm.trace_plan(sc, 0.0)
+    assert two_phase
+    # t = 0: the glass sphere (1, 0, 3.5; r 0.4) is 0.1 inside the x = +1.5 wall, the mirror sphere (0, -1.21, 3.5; r 0.4) reaches through
+    # the floor (wall 1, y = -1.5): rays that leave through the floor must still test it, every other pair is skipped
+    assert need == [0, 2, 0, 0, 0]
+    # t = pi/2: the glass sphere sits at z = 4.5, the mirror sphere at y = sin(pi/4 + 5) - 0.25 = -0.73: both clear of every wall
+    two_phase, need = pm.trace_plan(sc, 1.5707963)
+    assert two_phase and need == [0, 0, 0, 0, 0]
+    # spheres given as they are (no animation), the first one touching the back wall z = 6
+    sc2 = pm.default_scene(animate=0)
+    sc2.spheres[0][0], sc2.spheres[0][1], sc2.spheres[0][2], sc2.spheres[0][3] = 0.0, 0.0, 5.7, 0.4
+    two_phase, need = pm.trace_plan(sc2, 0.0)
+    assert two_phase and need[4] == 1 and need[0] == 0
+    # conditions that switch the lock-step path off: light outside the box / on a wall plane, three spheres, walls 0.8 apart, far scene
+    for edit in ("light_on_wall", "smoke", "narrow", "far", "light_in_sphere"):
+        s3 = pm.default_scene(animate=0)
+        if edit == "light_on_wall":
+            s3.light[0] = 1.5
+        elif edit == "smoke":
+            s3.n_spheres = 3
+        elif edit == "narrow":
+            s3.planes[0][1], s3.planes[2][1] = 0.4, -0.4
+        elif edit == "far":
+            s3.light[2] = 9.0
+        elif edit == "light_in_sphere":
+            s3.spheres[1][0], s3.spheres[1][1], s3.spheres[1][2] = s3.light[0], s3.light[1] - 0.1, s3.light[2]
+        assert pm.trace_plan(s3, 0.0)[0] is False, edit
