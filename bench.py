@@ -53,8 +53,8 @@ def parse():
                     help="Mode A, N > 1: how the accumulators are summed -- peer (default): our kernel pulls them over NVLink peer "
                          "memory inside pm_build_map (CUDA IPC between the ranks); nccl: dist.all_reduce (round 1's path)")
     ap.add_argument("--trace-sms", type=int, default=-1,
-                    help="CTAs of the persistent trace kernel (pm_set_trace_sms); -1 (default): every SM at N <= 2, all but 16 at N = 4, all but 32 at N = 8, "
-                         "which leaves room for the previous frame's exchange + map build + render on the second stream")
+                    help="CTAs of the persistent trace kernel (pm_set_trace_sms); -1 (default): every SM at N = 1, all but 8 at N = 2, all but 16 at N >= 4, "
+                         "which leaves room for the previous frames' exchange + map build and render on the other two streams")
     ap.add_argument("--no-extras", action="store_true", help="skip Mode B at N, config 5 and the single-GPU side benchmarks")
     ap.add_argument("--passes", type=int, default=1,
                     help="progressive photon mapping (BASELINE config 5): photon passes accumulated per frame, each with a fresh "
@@ -367,10 +367,11 @@ def main():
     y0, y1 = pmdist.row_band_uneven(H, rank, world)
     rows = y1 - y0
     m.set_row_band(y0, y1)
-    # measured (gpurun, B200): N = 4 is fastest with 132 of 148 trace CTAs, N = 8 with 116 -- the shorter the trace, the more of the frame
-    # is the chain of small kernels behind it, and the more SMs that chain needs to keep up
-    trace_sms = a.trace_sms if a.trace_sms >= 0 else (
-        0 if world <= 2 else torch.cuda.get_device_properties(local).multi_processor_count - (16 if world < 8 else 32))
+    # measured (gpurun, B200, three-stage frames: trace | exchange + map build | render + barrier): N = 2 is fastest with 140 of 148
+    # trace CTAs (0.330 ms against 0.406 with all 148), N = 8 with 132 (0.125; 124: 0.128, 116: 0.135); N = 4 keeps 132 -- the shorter
+    # the trace, the more of the frame is the chain of small kernels behind it, and that chain needs SMs of its own to keep up
+    sms = torch.cuda.get_device_properties(local).multi_processor_count
+    trace_sms = a.trace_sms if a.trace_sms >= 0 else (0 if world == 1 else sms - 8 if world == 2 else sms - 16)
     m.set_trace_sms(trace_sms)
 
     # N > 1: the ranks' exchange blocks are mapped into each other (CUDA IPC) and the frame lives on rank 0, every rank
@@ -655,7 +656,7 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": workload_config(a, {"parallelism": "photon-range x%d + row-band x%d" % (world, world),
                                           "exchange": ("peer memory (pm_peer.cu, CUDA IPC)" if peers else "NCCL all-reduce") if world > 1 else "none",
-                                          "frames_in_flight": 1 if (a.no_overlap or a.mode == "b") else 2, "trace_sms": trace_sms or props.multi_processor_count}),
+                                          "frames_in_flight": 1 if (a.no_overlap or a.mode == "b") else 3, "trace_sms": trace_sms or props.multi_processor_count}),
             "photons_per_s": NP * a.passes / (ms_per_step * 1e-3), "pixels_per_s": W * H / (ms_per_step * 1e-3),
             "frame_latency_ms": latency_ms,
             "stages_ms": ({"clear+trace": float(stages[0]), "allreduce": (kern.get("peer_reduce_kernel", {}).get("avg_ms", 0.0) if peers else float(stages[1])),

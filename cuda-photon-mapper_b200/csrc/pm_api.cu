@@ -175,8 +175,13 @@ int pm_create(pm_context **out, int device) {
     if ((e = cudaEventCreateWithFlags(&c->ev_cleared[b], cudaEventDisableTiming)) != cudaSuccess) return fail(e);
   }
   if ((e = cudaMalloc(&c->d_grid, sizeof(float) * PM_GRID_FLOATS)) != cudaSuccess) return fail(e);
-  if ((e = cudaMalloc(&c->d_vol, sizeof(float4) * kVolTableEntries)) != cudaSuccess) return fail(e);
-  if ((e = cudaMalloc(&c->d_surf, sizeof(float4) * kSurfTableEntries)) != cudaSuccess) return fail(e);
+  for (int b = 0; b < 2; b++) {
+    if ((e = cudaMalloc(&c->d_vol_buf[b], sizeof(float4) * kVolTableEntries)) != cudaSuccess) return fail(e);
+    if ((e = cudaMalloc(&c->d_surf_buf[b], sizeof(float4) * kSurfTableEntries)) != cudaSuccess) return fail(e);
+    if ((e = cudaEventCreateWithFlags(&c->ev_tbl_read[b], cudaEventDisableTiming)) != cudaSuccess) return fail(e);
+  }
+  if ((e = cudaEventCreateWithFlags(&c->ev_tbl_built, cudaEventDisableTiming)) != cudaSuccess) return fail(e);
+  c->d_vol = c->d_vol_buf[0]; c->d_surf = c->d_surf_buf[0];
   if ((e = cudaMalloc(&c->d_jump, sizeof(MwcJump))) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&c->d_rec_count, sizeof(unsigned long long))) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&c->d_vol_cnt, sizeof(uint32_t) * kVolCntEntries)) != cudaSuccess) return fail(e);
@@ -199,7 +204,12 @@ int pm_destroy(pm_context *c) {
   if (!c) return PM_ERR_ARG;
   cudaSetDevice(c->device);
   pm_peer_disconnect(c);
-  cudaFree(c->d_table); cudaFree(c->d_xchg); cudaFree(c->d_acc_sum); cudaFree(c->d_vol_cnt); cudaFree(c->d_grid); cudaFree(c->d_vol); cudaFree(c->d_surf);
+  cudaFree(c->d_table); cudaFree(c->d_xchg); cudaFree(c->d_acc_sum); cudaFree(c->d_vol_cnt); cudaFree(c->d_grid);
+  for (int b = 0; b < 2; b++) {
+    cudaFree(c->d_vol_buf[b]); cudaFree(c->d_surf_buf[b]);
+    if (c->ev_tbl_read[b]) cudaEventDestroy(c->ev_tbl_read[b]);
+  }
+  if (c->ev_tbl_built) cudaEventDestroy(c->ev_tbl_built);
   cudaFree(c->d_jump); cudaFree(c->d_rec_pos); cudaFree(c->d_rec_pow); cudaFree(c->d_rec_dir); cudaFree(c->d_rec_count);
   cudaFree(c->d_fb_u8); cudaFree(c->d_fb_f32); cudaFree(c->d_vrec_pos); cudaFree(c->d_vrec_pow); cudaFree(c->d_trace_dbg); cudaFree(c->d_trace_queue);
   for (int k = 0; k < pm_context::kFrameRing; k++) {
@@ -209,6 +219,7 @@ int pm_destroy(pm_context *c) {
   }
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+  if (c->render_stream) cudaStreamDestroy(c->render_stream);
   if (c->ev_traced) cudaEventDestroy(c->ev_traced);
   for (int b = 0; b < kAccBuffers; b++) {
     if (c->ev_reduced[b]) cudaEventDestroy(c->ev_reduced[b]);
@@ -252,7 +263,8 @@ int pm_sync(pm_context *c) {
   if (!c) return PM_ERR_ARG;
   CK(c, cudaSetDevice(c->device));
   CK(c, cudaStreamSynchronize(c->stream));
-  if (c->aux_stream) CK(c, cudaStreamSynchronize(c->aux_stream));   // the second half of pipelined frames
+  if (c->aux_stream) CK(c, cudaStreamSynchronize(c->aux_stream));   // the later stages of pipelined frames
+  if (c->render_stream) CK(c, cudaStreamSynchronize(c->render_stream));
   return PM_OK;
 }
 
@@ -523,6 +535,7 @@ int pm_get_accumulators_host(pm_context *c, int64_t *out) {
   ARG(c, c && out, "null argument");
   CK(c, cudaSetDevice(c->device));
   if (c->aux_stream) CK(c, cudaStreamSynchronize(c->aux_stream));
+  if (c->render_stream) CK(c, cudaStreamSynchronize(c->render_stream));
   CK(c, cudaMemcpyAsync(out, c->acc_summed ? c->d_acc_sum : c->d_acc, sizeof(long long) * kAccEntries, cudaMemcpyDeviceToHost, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));
   return PM_OK;
@@ -536,7 +549,11 @@ int pm_build_map(pm_context *c) {
     SpanGuard g(c, K_PEER_REDUCE);
     c->pv.hdr[c->rank] = (ExchangeHeader *)c->d_xchg;
     // ranks that share a device (tests) must leave SMs for each other's trace while they spin
-    const int blocks = c->peer_on_same_device ? 16 : c->num_sms;
+    // ... and while the persistent trace kernel of the next frame holds all but a few SMs (pm_set_trace_sms) the spinning blocks
+    // must not fill every free one either: the render of the previous frame runs beside this kernel (render_stream)
+    int blocks = c->num_sms;
+    if (c->trace_sms > 0 && c->trace_sms < c->num_sms) blocks = std::max(16, std::min(c->num_sms, 4 * (c->num_sms - c->trace_sms)));
+    if (c->peer_on_same_device) blocks = 16;
     CK(c, launch_peer_reduce(c->pv, c->cur, ++c->seq[0], c->d_acc_sum, blocks, c->stream));
     CK(c, cudaEventRecord(c->ev_reduced[c->cur], c->stream));
     c->launches++;
@@ -560,8 +577,15 @@ int pm_build_map(pm_context *c) {
     c->preclear_frame = c->frame_no;
   }
   {
-    SpanGuard g(c, K_BUILD_TABLES);
-    CK(c, launch_build_tables(c->d_grid, c->d_vol, c->d_surf, c->stream));
+    // into the table buffer the renders are NOT reading: the render of the previous frame may still be running (render_stream)
+    const int nb = c->tbl ^ 1;
+    CK(c, cudaStreamWaitEvent(c->stream, c->ev_tbl_read[nb], 0));   // the last render that read this buffer (two frames ago)
+    {
+      SpanGuard g(c, K_BUILD_TABLES);
+      CK(c, launch_build_tables(c->d_grid, c->d_vol_buf[nb], c->d_surf_buf[nb], c->stream));
+    }
+    CK(c, cudaEventRecord(c->ev_tbl_built, c->stream));
+    c->tbl = nb; c->d_vol = c->d_vol_buf[nb]; c->d_surf = c->d_surf_buf[nb];
   }
   c->launches += 2;
   c->tables_valid = true;
@@ -571,6 +595,7 @@ int pm_get_map_host(pm_context *c, float *grid) {
   ARG(c, c && grid, "null argument");
   CK(c, cudaSetDevice(c->device));
   if (c->aux_stream) CK(c, cudaStreamSynchronize(c->aux_stream));
+  if (c->render_stream) CK(c, cudaStreamSynchronize(c->render_stream));
   CK(c, cudaMemcpyAsync(grid, c->d_grid, sizeof(float) * PM_GRID_FLOATS, cudaMemcpyDeviceToHost, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));
   return PM_OK;
@@ -578,8 +603,11 @@ int pm_get_map_host(pm_context *c, float *grid) {
 int pm_set_map_host(pm_context *c, const float *grid) {
   ARG(c, c && grid, "null argument");
   CK(c, cudaSetDevice(c->device));
+  if (c->aux_stream) CK(c, cudaStreamSynchronize(c->aux_stream));         // pipelined frames still building / rendering from the map
+  if (c->render_stream) CK(c, cudaStreamSynchronize(c->render_stream));
   CK(c, cudaMemcpyAsync(c->d_grid, grid, sizeof(float) * PM_GRID_FLOATS, cudaMemcpyHostToDevice, c->stream));
   CK(c, launch_build_tables(c->d_grid, c->d_vol, c->d_surf, c->stream));
+  CK(c, cudaEventRecord(c->ev_tbl_built, c->stream));
   c->launches++;
   CK(c, cudaStreamSynchronize(c->stream));
   c->tables_valid = true;
@@ -839,10 +867,12 @@ int pm_render(pm_context *c, float t, bool interp, bool media, int width, int he
   if (!c->tables_valid) { c->err = "pm_render before pm_build_map / pm_set_map_host"; return PM_ERR_STATE; }
   CK(c, cudaSetDevice(c->device));
   c->dsc = make_device_scene(c->scene, t);
+  CK(c, cudaStreamWaitEvent(c->stream, c->ev_tbl_built, 0));   // the tables may have been built on another stream (pipelined frames)
   {
     SpanGuard g(c, K_RENDER);
     CK(c, launch_render(c->dsc, c->d_vol, c->d_surf, width, height, y0, y1, interp, media, (uchar4 *)dev_rgba, (float4 *)dev_rgbf, c->stream));
   }
+  CK(c, cudaEventRecord(c->ev_tbl_read[c->tbl], c->stream));
   if (y1 > y0) c->launches++;
   return PM_OK;
 }
@@ -935,7 +965,10 @@ int pm_frame_host(pm_context *c, float t, bool emit, bool interp, bool media, in
 static int frame_stages(pm_context *c, float t, bool emit, bool interp, bool media, int width, int height, int y0, int y1,
                         pm_uchar4 *dev_rgba, float *dev_rgbf, cudaEvent_t wait_before_render, bool barrier_after) {
   if (!c->aux_stream) {
-    CK(c, cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+    int least = 0, greatest = 0;   // the small kernels of the later stages take whatever SMs the trace kernel leaves, before anything else
+    CK(c, cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    CK(c, cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, greatest));
+    CK(c, cudaStreamCreateWithPriority(&c->render_stream, cudaStreamNonBlocking, greatest));
     CK(c, cudaEventCreateWithFlags(&c->ev_traced, cudaEventDisableTiming));
   }
   int rc;
@@ -945,10 +978,14 @@ static int frame_stages(pm_context *c, float t, bool emit, bool interp, bool med
   }
   CK(c, cudaEventRecord(c->ev_traced, c->stream));
   CK(c, cudaStreamWaitEvent(c->aux_stream, c->ev_traced, 0));
-  if (wait_before_render) CK(c, cudaStreamWaitEvent(c->aux_stream, wait_before_render, 0));
   cudaStream_t main_stream = c->stream;
   c->stream = c->aux_stream;   // pm_build_map / pm_render / pm_peer_barrier launch on the context's current stream
   rc = emit ? pm_build_map(c) : PM_OK;
+  // third stage: the render waits for this frame's tables (pm_render waits for ev_tbl_built) -- and, without an emit, for the trace
+  // stream's earlier work -- while aux_stream is free for the next frame's exchange and map build
+  c->stream = c->render_stream;
+  if (rc == PM_OK && !emit) rc = cudaStreamWaitEvent(c->render_stream, c->ev_traced, 0) == cudaSuccess ? PM_OK : PM_ERR_CUDA;
+  if (rc == PM_OK && wait_before_render) rc = cudaStreamWaitEvent(c->render_stream, wait_before_render, 0) == cudaSuccess ? PM_OK : PM_ERR_CUDA;
   if (rc == PM_OK) rc = pm_render(c, t, interp, media, width, height, y0, y1, dev_rgba, dev_rgbf);
   if (rc == PM_OK && barrier_after) rc = pm_peer_barrier(c);
   c->stream = main_stream;
@@ -981,7 +1018,7 @@ int pm_frame_host_async(pm_context *c, float t, bool emit, bool interp, bool med
   // the render waits until the copy three frames ago has drained this frame buffer
   int rc = frame_stages(c, t, emit, interp, media, width, height, y0, y1, (pm_uchar4 *)c->d_fb_async[k], nullptr, c->ev_copied[k], false);
   if (rc != PM_OK) return rc;
-  CK(c, cudaEventRecord(c->ev_rendered[k], c->aux_stream));
+  CK(c, cudaEventRecord(c->ev_rendered[k], c->render_stream));
   CK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_rendered[k], 0));
   const size_t off = (size_t)y0 * width, cnt = (size_t)(y1 - y0) * width;
   if (cnt) CK(c, cudaMemcpyAsync(host_rgba + off, c->d_fb_async[k] + off, sizeof(uchar4) * cnt, cudaMemcpyDeviceToHost, c->copy_stream));
@@ -1146,6 +1183,7 @@ int pm_peer_status(pm_context *c) {
   CK(c, cudaSetDevice(c->device));
   CK(c, cudaStreamSynchronize(c->stream));
   if (c->aux_stream) CK(c, cudaStreamSynchronize(c->aux_stream));
+  if (c->render_stream) CK(c, cudaStreamSynchronize(c->render_stream));
   uint32_t e = 0;
   CK(c, cudaMemcpy(&e, &((ExchangeHeader *)c->d_xchg)->error, sizeof(e), cudaMemcpyDeviceToHost));
   if (e) { c->err = e == 1 ? "a peer never signalled its accumulators (wait timed out)" : "a peer never reached the barrier (wait timed out)"; return PM_ERR_STATE; }

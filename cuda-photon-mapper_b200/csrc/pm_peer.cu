@@ -19,6 +19,7 @@
 // two frames old by then): that reduce saw every peer's signal f+1, which each peer sends only after finishing its reduce of
 // frame f -- its reads of buffer b -- in stream order.  So no "consumed" handshake is needed.  A peer that never arrives trips
 // a timeout (error word) instead of hanging the GPU.
+#include <cstdlib>
 #include "pm_kernels.cuh"
 
 namespace pm {
@@ -65,8 +66,12 @@ __device__ __forceinline__ bool signal_and_wait(const PeerView &pv, int channel,
   return ok != 0;
 }
 
-__global__ void __launch_bounds__(256) peer_reduce_kernel(const __grid_constant__ PeerView pv, int buf, uint32_t seq, long long *__restrict__ out) {
-  signal_and_wait(pv, 0, seq, blockIdx.x == 0);   // on a timeout the sums are garbage; the host sees the error word
+// seq_or_nowait: the frame's sequence number; kNoWait when the signal + wait ran as a kernel of its own in front of this one
+// (PMB200_PEER_SPLIT, see launch_peer_reduce)
+constexpr uint32_t kNoWait = 0xffffffffu;
+__global__ void __launch_bounds__(256) peer_reduce_kernel(const __grid_constant__ PeerView pv, int buf, uint32_t seq_or_nowait,
+                                                          long long *__restrict__ out) {
+  if (seq_or_nowait != kNoWait) signal_and_wait(pv, 0, seq_or_nowait, blockIdx.x == 0);   // on a timeout the sums are garbage; the host sees the error word
   __shared__ unsigned vox_mask;
   if (threadIdx.x == 0) {
     unsigned m = 0;
@@ -92,8 +97,8 @@ __global__ void __launch_bounds__(256) peer_reduce_kernel(const __grid_constant_
 }
 
 // stand-alone device-side barrier between the ranks (e.g. "every rank's band has landed in rank 0's frame buffer")
-__global__ void __launch_bounds__(32) peer_barrier_kernel(const __grid_constant__ PeerView pv, uint32_t seq) {
-  signal_and_wait(pv, 1, seq, true);
+__global__ void __launch_bounds__(32) peer_barrier_kernel(const __grid_constant__ PeerView pv, int channel, uint32_t seq) {
+  signal_and_wait(pv, channel, seq, true);   // on a timeout the host sees the error word (a reduce that follows sums garbage)
 }
 
 cudaError_t preload_peer_kernels() {
@@ -105,11 +110,20 @@ cudaError_t preload_peer_kernels() {
 
 cudaError_t launch_peer_reduce(const PeerView &pv, int buf, uint32_t seq, long long *out, int blocks, cudaStream_t st) {
   static_assert(kAccEntries % 2 == 0 && kAccHitEntries % 2 == 0 && kAccVoxEntries % 2 == 0, "sections must be 16-byte aligned");
-  peer_reduce_kernel<<<blocks, 256, 0, st>>>(pv, buf, seq, out);
+  // PMB200_PEER_SPLIT=1: signal + wait as a one-warp kernel in front of the reduce, so that no SM is held by the reduce's spinning
+  // blocks at the moment the next frame's persistent trace kernel wants its SMs.  One measurement at 8 GPUs (132 trace CTAs): end to
+  // end 0.152 -> 0.148 ms, but the device-resident frame 0.125 -> 0.158 ms -- not understood, so off by default.
+  static const bool split = getenv("PMB200_PEER_SPLIT") != nullptr && getenv("PMB200_PEER_SPLIT")[0] == '1';
+  if (split && seq != kNoWait) {
+    peer_barrier_kernel<<<1, 32, 0, st>>>(pv, 0, seq);
+    peer_reduce_kernel<<<blocks, 256, 0, st>>>(pv, buf, kNoWait, out);
+  } else {
+    peer_reduce_kernel<<<blocks, 256, 0, st>>>(pv, buf, seq, out);
+  }
   return cudaGetLastError();
 }
 cudaError_t launch_peer_barrier(const PeerView &pv, uint32_t seq, cudaStream_t st) {
-  peer_barrier_kernel<<<1, 32, 0, st>>>(pv, seq);
+  peer_barrier_kernel<<<1, 32, 0, st>>>(pv, 1, seq);
   return cudaGetLastError();
 }
 
