@@ -47,8 +47,8 @@ def parse():
                          "tree built on every rank, row bands) -- for Mode B scaling runs")
     ap.add_argument("--knn", type=int, default=50, help="k of the Mode B estimate")
     ap.add_argument("--no-overlap", action="store_true",
-                    help="Mode A: one stream, no frames in flight (the headline keeps two frames in flight: exchange + map build + render "
-                         "of frame f run on a second stream under the trace of frame f+1)")
+                    help="Mode A: one stream, no frames in flight (the headline is a three-stage pipeline: exchange + map build of frame f on a second "
+                         "stream and its render on a third, under the trace of frame f+1)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="Mode A, N > 1: how the accumulators are summed -- peer (default): our kernel pulls them over NVLink peer "
                          "memory inside pm_build_map (CUDA IPC between the ranks); nccl: dist.all_reduce (round 1's path)")
@@ -434,7 +434,7 @@ def main():
     ev_traced = torch.cuda.Event()
 
     def step_pipelined(e=None):
-        """Two frames in flight: clear + trace on the main stream, exchange + map build + render (+ barrier) on the second one."""
+        """Frames in flight: clear + trace on the main stream, exchange + map build on a second, render (+ barrier) on a third."""
         if a.passes == 1 and (peers or world == 1):
             m.frame_device(W, H, rgba=rgba, rgbf=rgbf, t=0.0, emit=True, interp=False, media=True)     # the library's own pipeline
             return
@@ -529,7 +529,7 @@ def main():
     stages = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(4)] for e in ev]).mean(0)
 
     # ---- end to end through the C-ABI with HOST buffers: scene struct in, the reference's uchar4 frame out.  Mode A: every rank
-    #      calls pm_frame_host_async (two frames in flight, exchange inside) and copies ITS row band into one host frame -- pinned
+    #      calls pm_frame_host_async (three-stage pipeline, exchange inside) and copies ITS row band into one host frame -- pinned
     #      memory, shared between the rank processes at N > 1 -- over its own PCIe link; the host waits for every frame, one frame
     #      behind, and rank 0 also waits until every rank has reported its band of that frame. ----
     e2e_steps = max(3, min(a.steps, 30))

@@ -958,10 +958,11 @@ int pm_frame_host(pm_context *c, float t, bool emit, bool interp, bool media, in
   return pm_render_host(c, t, interp, media, width, height, host_rgba, host_rgbf);
 }
 
-// One frame with two frames in flight: (emit: clear + trace) on the context's stream, then exchange + map build + render -- and the
-// rank barrier when asked -- on the auxiliary stream, so the next frame's trace does not wait for them (the accumulators
-// rotate through three buffers for exactly that, pm_peer.cu).  At 8 GPUs the part after the trace is a chain of small,
-// latency-bound kernels about half as long as the trace itself.
+// One frame of a three-stage pipeline: (emit: clear + trace) on the context's stream, then exchange + map build on the auxiliary
+// stream, then the render -- and the rank barrier when asked -- on the render stream, so the next frame's trace does not wait for them
+// and the next frame's exchange does not wait for this frame's render (the accumulators rotate through three buffers for exactly
+// that, pm_peer.cu, and the gather tables through two, pm_build_map).  At 8 GPUs the part after the trace is a chain of small,
+// latency-bound kernels with two cross-rank waits in it, longer than the trace itself.
 static int frame_stages(pm_context *c, float t, bool emit, bool interp, bool media, int width, int height, int y0, int y1,
                         pm_uchar4 *dev_rgba, float *dev_rgbf, cudaEvent_t wait_before_render, bool barrier_after) {
   if (!c->aux_stream) {

@@ -14,7 +14,7 @@
 //            only read from ranks whose vox_touched flag is set.
 //
 // The accumulators rotate through three buffers, so that a frame's trace never waits for the previous frame's exchange (the
-// host side runs clear + trace on one stream and exchange + map build + render on another, two frames in flight).  A rank
+// host side runs clear + trace on one stream, exchange + map build on a second and the render on a third).  A rank
 // clears buffer b again three frames later, after its OWN reduce of frame f+1 has completed (an event wait in pm_clear_map,
 // two frames old by then): that reduce saw every peer's signal f+1, which each peer sends only after finishing its reduce of
 // frame f -- its reads of buffer b -- in stream order.  So no "consumed" handshake is needed.  A peer that never arrives trips

@@ -125,9 +125,9 @@ int pm_clear_map(pm_context *ctx);                                 /* init_photo
 int pm_trace(pm_context *ctx, float animTime, unsigned flags);
 /* tuning: how many of a CTA's 32 warps run the medium walk in the fused trace kernel (default 7; 1..16) */
 int pm_set_volume_warps(pm_context *ctx, int warps);
-/* tuning: CTAs of the persistent trace kernel (default 0 = one per SM).  Fewer leaves SMs free for the previous frame's exchange +
- * map build + render, which the pipelined frame calls run on a second stream (worth it when those are a large part of the frame,
- * i.e. at 4-8 GPUs) */
+/* tuning: CTAs of the persistent trace kernel (default 0 = one per SM).  Fewer leaves SMs free for the previous frames' exchange +
+ * map build and render, which the pipelined frame calls run on two further streams (worth it when those are a large part of the
+ * frame, i.e. at 2-8 GPUs: 140 of 148 at 2, 132 at 4 and 8 measured best) */
 int pm_set_trace_sms(pm_context *ctx, int sms);
 /* the exact (int64 fixed-point) accumulators of the CURRENT frame (they rotate through three buffers, one per pm_clear_map).  Multi-GPU:
  * connect the ranks (pm_peer_* / pm_group_*, below) and pm_build_map sums them itself over NVLink; summing them by hand between
@@ -216,7 +216,8 @@ int pm_frame_host_async(pm_context *ctx, float animTime, bool emitFlag, bool int
 int pm_frame_wait(pm_context *ctx, int64_t ticket);
 /* the same pipeline with the frame left in DEVICE memory (dev_rgba / dev_rgbf: whole-frame buffers, either may be NULL; the
  * rows of pm_set_row_band are written).  Everything is enqueued: (emit: clear + trace) on the context's stream, exchange +
- * map build + render on a second stream, so two frames are in flight.  With peers connected, dev_* may be another rank's
+ * map build on a second stream, render (+ barrier) on a third, so up to three frames are in flight (the accumulators rotate
+ * through three buffers and the gather tables through two for that).  With peers connected, dev_* may be another rank's
  * memory (pm_shared_open): every rank renders its band straight into rank 0's frame over NVLink, and a device-side barrier
  * follows -- when a rank's pm_sync returns, every band of that frame has landed. */
 int pm_frame_device(pm_context *ctx, float animTime, bool emitFlag, bool interpolateFlag, bool participatingMediaFlag,
