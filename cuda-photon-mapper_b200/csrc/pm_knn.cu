@@ -644,10 +644,13 @@ __global__ void __launch_bounds__(kQueryThreads, PM_KNN_MINBLOCKS) knn_render_ke
                                                                    const float4 *__restrict__ pow_v, int k, float max_r2, float w_surf,
                                                                    float w_vol, int width, int height, int y0, int y1, int y_step, int media,
                                                                    uchar4 *__restrict__ rgba, float4 *__restrict__ rgbf,
-                                                                   unsigned long long *__restrict__ work_counter) {
+                                                                   unsigned long long *__restrict__ work_counter, int staged_stride) {
+  // dynamic shared memory: the staged top levels of the two trees (staged_stride floats each: what the trees need, not the
+  // kMaxStagedFloats they may need -- 2.3 KB instead of 25 KB per tree at 16 M photons, which leaves the rest of the SM's 256 KB to L1),
+  // the warps' candidate buffers, two mbarriers
   extern __shared__ __align__(128) unsigned char dyn[];
-  float *sbox_s = (float *)dyn, *sbox_v = sbox_s + kMaxStagedFloats;
-  u64 *pend_all = (u64 *)(sbox_v + kMaxStagedFloats);
+  float *sbox_s = (float *)dyn, *sbox_v = sbox_s + staged_stride;
+  u64 *pend_all = (u64 *)(sbox_v + staged_stride);
   unsigned long long *bars = (unsigned long long *)(pend_all + (kQueryThreads / 32) * 64);
   stage_top_levels(tvs, sbox_s, bars + 0);
   if (media) stage_top_levels(tvv, sbox_v, bars + 1);
@@ -1290,13 +1293,18 @@ cudaError_t knn_render(const DeviceScene &sc, const KnnMap &ms, const KnnMap &mv
   TreeView tvs = make_view(ms), tvv = make_view(mv);
   long long want = (long long)((width + 15) / 16) * (((y1 - y0 + y_step - 1) / y_step + 7) / 8), cap = (long long)num_sms * 16;   // 8x16-pixel tiles
   unsigned grid = (unsigned)(want < cap ? want : cap);
-  size_t smem = sizeof(float) * 2 * kMaxStagedFloats + sizeof(u64) * (kQueryThreads / 32) * 64 + 2 * sizeof(unsigned long long);
+  long long staged = tvs.staged_floats > tvv.staged_floats ? tvs.staged_floats : tvv.staged_floats;
+#ifdef PM_KNN_STATIC_SMEM
+  staged = kMaxStagedFloats;   // the A/B baseline: room for the largest staged levels whatever the trees need (54.8 KB per CTA)
+#endif
+  const int stride = (int)((staged + 31) / 32 * 32 > 32 ? (staged + 31) / 32 * 32 : 32);   // 128-byte multiples (bulk-copy alignment)
+  size_t smem = sizeof(float) * 2 * (size_t)stride + sizeof(u64) * (kQueryThreads / 32) * 64 + 2 * sizeof(unsigned long long);
   KCK(cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), st));
 #define LAUNCH_RENDER(KL)                                                                                                  \
   do {                                                                                                                     \
     KCK(cudaFuncSetAttribute(knn_render_kernel<KL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
     knn_render_kernel<KL><<<grid, kQueryThreads, smem, st>>>(sc, tvs, tvv, ms.power, mv.power, k, max_r2, w_surf, w_vol, width, height, y0, \
-                                                              y1, y_step, media ? 1 : 0, rgba, rgbf, work_counter);                               \
+                                                              y1, y_step, media ? 1 : 0, rgba, rgbf, work_counter, stride);                       \
   } while (0)
   if (k <= 32) LAUNCH_RENDER(1); else if (k <= 64) LAUNCH_RENDER(2); else LAUNCH_RENDER(4);
 #undef LAUNCH_RENDER

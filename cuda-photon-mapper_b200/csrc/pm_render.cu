@@ -76,9 +76,12 @@ __device__ __forceinline__ unsigned char quantise(float v) {
 __global__ void __launch_bounds__(256) render_kernel(const __grid_constant__ DeviceScene sc, const float4 *__restrict__ vol_table,
                                                      const float4 *__restrict__ surf_table, int width, int height, int y0, int y1,
                                                      int interp, int media, uchar4 *__restrict__ rgba, float4 *__restrict__ rgbf) {
-  long long pix = (long long)y0 * width + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= (long long)y1 * width) return;
-  int px = (int)(pix % width), py = (int)(pix / width);
+  // 32-bit index arithmetic (launch_render checks that the band has fewer than 2^32 pixels): the 64-bit % and / were 8 % of the samples
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (unsigned)(y1 - y0) * (unsigned)width) return;
+  const unsigned row = i / (unsigned)width;
+  const int px = (int)(i - row * (unsigned)width), py = y0 + (int)row;
+  const long long pix = (long long)py * width + px;
   float x = (float)px + sc.cam_ox, y = (float)py + sc.cam_oy;
 
   v3 rgb = V(0.0f, 0.0f, 0.0f);
@@ -86,8 +89,10 @@ __global__ void __launch_bounds__(256) render_kernel(const __grid_constant__ Dev
   v3 ray = V((float)((double)__fdiv_rn(x, sc.sz_img) - 0.5), (float)(-((double)__fdiv_rn(y, sc.sz_img) - 0.5)), 1.0f);
   Hit h; h.hit = 0; h.type = 0; h.idx = 0; h.dist = -1.0f;
   if (media) {   // PMK:937-965: 10 steps of 0.6 along the unnormalised ray, raw box sums
+    // unrolled: ray.z is the literal 1.0f, so the z coordinate of every march step -- and its voxel, and that voxel's range test --
+    // is a compile-time constant (the same IEEE operations, folded by the compiler)
     v3 prev = origin;
-#pragma unroll 1
+#pragma unroll
     for (int i = 0; i < 10; i++) { prev = add(mul(ray, 0.6f), prev); rgb = add(rgb, vol_lookup(vol_table, prev)); }
   }
   raytrace(sc, ray, origin, h);
@@ -108,6 +113,7 @@ cudaError_t launch_render(const DeviceScene &sc, const float4 *vol_table, const 
                           int y0, int y1, bool interp, bool media, uchar4 *rgba, float4 *rgbf, cudaStream_t st) {
   long long n = (long long)(y1 - y0) * width;
   if (n <= 0) return cudaSuccess;
+  if (n >= (1ll << 32) - 256) return cudaErrorInvalidValue;   // the kernel indexes the band's pixels with 32 bits
   unsigned blocks = (unsigned)((n + 255) / 256);
   render_kernel<<<blocks, 256, 0, st>>>(sc, vol_table, surf_table, width, height, y0, y1, interp ? 1 : 0, media ? 1 : 0, rgba, rgbf);
   return cudaGetLastError();

@@ -106,6 +106,17 @@ def test_div65535_constant_reciprocal_is_correctly_rounded():
     assert int(out[0]) == 0 and int(out[1]) > 70_000_000
 
 
+def test_voxel_wide_one_conversion_form_strided():
+    """strided subset of oracle/check_voxel_wide.c: the render kernel's one-conversion voxel_x_wide / voxel_z_wide against the
+    two-conversion form and the reference's literal double form (the exhaustive run, stride 1, reports 0 0 of 2^32 patterns)"""
+    import os, subprocess
+    exe = os.path.join(os.path.dirname(__file__), "..", "oracle", "check_voxel_wide")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.dirname(exe), "check_voxel_wide"])
+    out = subprocess.run([exe, "61"], capture_output=True, text=True, check=True).stdout.split()
+    assert int(out[0]) == 0 and int(out[1]) == 0 and int(out[2]) > 70_000_000
+
+
 def _div3_trunc(n):
     return np.where(n >= 0, (n * 43691) >> 17, -((-n * 43691) >> 17))
 
