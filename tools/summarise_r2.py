@@ -102,8 +102,8 @@ for sym, name in (("trace_kernelILb0", "r2_sass_trace_kernel.txt"), ("knn_render
     blk = next((b for b in blocks if sym in b.split("\n")[0]), None)
     if blk is None:
         continue
-    lines = [l for l in blk.splitlines() if re.match(r"\s+/\*[0-9a-f]{4}\*/", l)]
-    ops = collections.Counter(re.sub(r"^@!?U?P\d+\s+", "", re.sub(r"\s+/\*[0-9a-f]{4}\*/\s+", "", l)).split()[0].split(".")[0].rstrip(";") for l in lines)
+    lines = [l for l in blk.splitlines() if re.match(r"\s+/\*[0-9a-f]{4,}\*/", l)]
+    ops = collections.Counter(re.sub(r"^@!?U?P\d+\s+", "", re.sub(r"\s+/\*[0-9a-f]{4,}\*/\s+", "", l)).split()[0].split(".")[0].rstrip(";") for l in lines)
     with open(os.path.join(prof, name), "w") as f:
         f.write("cuobjdump -sass cuda-photon-mapper_b200/libpmb200.so, function %s\n%d instructions; opcode histogram:\n" % (blk.split("\n")[0], len(lines)))
         for op, c in ops.most_common():
