@@ -158,7 +158,8 @@ def test_ipc_ranks_bit_identical(pm, world):
 
 
 def test_frame_device_pipeline_matches_serial_frames(pm):
-    """pm_frame_device (clear + trace on one stream, map build + render on a second, accumulators rotating through three buffers)
+    """pm_frame_device (clear + trace on one stream, map build on a second, render on a third; accumulators rotating through three
+    buffers, gather tables through two)
     gives the frames of the one-stream pm_frame_host, bit for bit, also when several frames are enqueued back to back."""
     import torch
     ref = _single(pm, True, 0.0, frames=5)
